@@ -1,0 +1,765 @@
+// s3d_extract.cu — host orchestration + C ABI of the extraction path.
+// Compiled with -fmad=false (see s3d_kernels.cuh).  Mirrors, stage by stage,
+// CSIFT3D::KpSiftAlgorithm (/root/reference/3DSIFT/Src/cSIFT3D.cc:165-235).
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "s3d_common.h"
+#include "s3d_kernels.cuh"
+
+namespace s3d {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+void clear_error() { g_err[0] = 0; }
+
+int use_device(int device, int* resolved) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(S3D_ERR_CUDA, "no CUDA device available (%s); libsift3d_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0) S3D_CUDA(cudaGetDevice(&device));
+    if (device >= n) return fail(S3D_ERR_ARG, "device %d out of range (%d devices)", device, n);
+    S3D_CUDA(cudaSetDevice(device));
+    static std::mutex mu;
+    static bool pool_set[64] = {false};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (device < 64 && !pool_set[device]) {
+            int major = 0;
+            S3D_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+            if (major != 10)
+                return fail(S3D_ERR_CUDA, "device %d has compute capability %d.x; this library is built for sm_100a only",
+                            device, major);
+            // keep freed pyramid memory in the stream-ordered pool: the next volume reuses it
+            cudaMemPool_t pool;
+            S3D_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+            uint64_t thr = UINT64_MAX;
+            S3D_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+            pool_set[device] = true;
+        }
+    }
+    if (resolved) *resolved = device;
+    return S3D_OK;
+}
+
+// ---- host-side constants, computed exactly as the reference does (App. A.1, Q10) -------------
+
+// Src/cSIFT3D.cc:270-287,299
+static void host_sigmas(int L, float sigma_default, float sigma_n, float* sig) {
+    float k = (float)pow(2.0, 1.0 / L);
+    float base = (float)(sigma_default * pow(2.0, -1.0 / 3.0));
+    sig[0] = sqrtf(base * base - sigma_n * sigma_n);
+    for (int i = 1; i < L + 3; i++) {
+        float sig_prev = (float)(pow((double)k, (double)(i - 1)) * base);
+        float sig_total = sig_prev * k;
+        sig[i] = sqrtf(sig_total * sig_total - sig_prev * sig_prev);
+    }
+}
+
+// Src/cSIFT3D.cc:541-572.  Returns hw (or -1 if the kernel is wider than kMaxHW).
+static int host_taps(float sigma, Taps* t) {
+    sigma = sigma > 0 ? sigma : 0;
+    int c = (int)ceil(sigma * 3.0);
+    const int hw = sigma > 0 ? (c > 1 ? c : 1) : 1;
+    if (hw > kMaxHW) return -1;
+    const int width = 2 * hw + 1;
+    float acc = 0;
+    for (int i = 0; i < width; i++) {
+        float x = (float)(i - hw);
+        x = (float)((double)x / ((double)sigma + DBL_EPSILON));
+        t->w[i] = (float)exp(-0.5 * (double)x * (double)x);
+        acc += t->w[i];
+    }
+    for (int i = 0; i < width; i++) t->w[i] /= acc;
+    for (int i = width; i < 2 * kMaxHW + 1; i++) t->w[i] = 0.0f;
+    t->hw = hw;
+    return hw;
+}
+
+// Src/cUtil.cc:182,209-210
+static float host_level_scale(int o, int s, int L, float sigma_default) {
+    double sigma0 = sigma_default * pow(2.0, -1.0 / 3.0);
+    double scale_factor = pow(2.0, o + (double)s / L);
+    return (float)(scale_factor * sigma0);
+}
+
+// Icosahedron, Src/cUtil.cc:19-55 + Initialize_geometry :113-175, and the face-only terms of
+// cart2bary (Src/cSIFT3D.cc:1600-1619,1634) in the same FP32 arithmetic.  `volatile` keeps the
+// host compiler from contracting or reassociating anything.
+static void host_mesh(MeshConst* M) {
+    const double gr = 1.6180339887;
+    const double vert[36] = {0, 1, gr, 0, -1, gr, 0, 1, -gr, 0, -1, -gr, 1, gr, 0, -1, gr, 0,
+                             1, -gr, 0, -1, -gr, 0, gr, 0, 1, -gr, 0, 1, gr, 0, -1, -gr, 0, -1};
+    const int faces[60] = {0, 1, 8, 0, 8, 4, 0, 4, 5, 0, 5, 9, 0, 9, 1, 1, 6, 8, 8, 6, 10, 8, 10, 4, 4, 10, 2,
+                           4, 2, 5, 5, 2, 11, 5, 11, 9, 9, 11, 7, 9, 7, 1, 1, 7, 6, 3, 6, 7, 3, 7, 11, 3, 11, 2,
+                           3, 2, 10, 3, 10, 6};
+    auto mul = [](float a, float b) { volatile float r = a * b; return (float)r; };
+    auto add = [](float a, float b) { volatile float r = a + b; return (float)r; };
+    auto sub = [](float a, float b) { volatile float r = a - b; return (float)r; };
+    for (int i = 0; i < 20; i++) {
+        float v[3][3];
+        for (int j = 0; j < 3; j++) {
+            M->idx[i][j] = faces[i * 3 + j];
+            for (int c = 0; c < 3; c++) v[j][c] = (float)vert[faces[i * 3 + j] * 3 + c];
+            float n2 = add(add(mul(v[j][0], v[j][0]), mul(v[j][1], v[j][1])), mul(v[j][2], v[j][2]));
+            double mag = (double)sqrtf(n2);
+            double s = 1.0 / mag;
+            for (int c = 0; c < 3; c++) v[j][c] = (float)((double)v[j][c] * s);
+        }
+        float a[3], b[3], n[3];
+        for (int c = 0; c < 3; c++) { a[c] = sub(v[2][c], v[1][c]); b[c] = sub(v[1][c], v[0][c]); }
+        n[0] = sub(mul(a[1], b[2]), mul(a[2], b[1]));
+        n[1] = sub(mul(a[2], b[0]), mul(a[0], b[2]));
+        n[2] = sub(mul(a[0], b[1]), mul(a[1], b[0]));
+        float dot = add(add(mul(n[0], v[0][0]), mul(n[1], v[0][1])), mul(n[2], v[0][2]));
+        if (dot < 0)
+            for (int c = 0; c < 3; c++) { float tmp = v[0][c]; v[0][c] = v[1][c]; v[1][c] = tmp; }
+        float* e1 = M->e1[i]; float* e2 = M->e2[i]; float* t = M->t[i]; float* q = M->q[i];
+        for (int c = 0; c < 3; c++) {
+            e1[c] = sub(v[1][c], v[0][c]);
+            e2[c] = sub(v[2][c], v[0][c]);
+            t[c] = (float)((double)v[0][c] * (-1.0));
+        }
+        q[0] = sub(mul(t[1], e1[2]), mul(t[2], e1[1]));
+        q[1] = sub(mul(t[2], e1[0]), mul(t[0], e1[2]));
+        q[2] = sub(mul(t[0], e1[1]), mul(t[1], e1[0]));
+        M->qe2[i] = add(add(mul(q[0], e2[0]), mul(q[1], e2[1])), mul(q[2], e2[2]));
+    }
+}
+
+static bool supported_fast_hw(int hw) { return hw == 2 || hw == 3 || hw == 4 || hw == 5 || hw == 6 || hw == 8; }
+
+template <int HW>
+static void launch_x(const float* src, float* dst, int nx, ll nrows, const Taps& t, ll total, cudaStream_t st) {
+    ll threads = nrows * (nx >> 2);
+    auto kfn = blur_x_kernel<HW>;
+    S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 256), 256, 0, st, src, dst, nx, nrows, t, total);
+}
+
+static int pick_seg(int nx4, int n_other, int n) {
+    // longest segment that still yields >= ~256k threads, so small octaves keep the GPU busy
+    int seg = 64;
+    while (seg > 8 && (ll)nx4 * n_other * ((n + seg - 1) / seg) < 262144) seg >>= 1;
+    return seg;
+}
+
+template <int HW>
+static void launch_march(const float* src, float* dst, int nx, int n, ll st_m, int n_other, ll st_other, const Taps& t,
+                         ll total, const float* prev, float* dog, unsigned* slot, cudaStream_t st) {
+    const int nx4 = nx >> 2;
+    const int seg = pick_seg(nx4, n_other, n);
+    const int nseg = (n + seg - 1) / seg;
+    ll threads = (ll)nx4 * n_other * nseg;
+    if (dog) {
+        auto kfn = blur_march_kernel<HW, true>;
+        S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 128), 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
+                   total, prev, dog, slot);
+    } else {
+        auto kfn = blur_march_kernel<HW, false>;
+        S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 128), 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
+                   total, (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr);
+    }
+}
+
+#define S3D_HW_SWITCH(hw, CALL)            \
+    switch (hw) {                          \
+        case 2: CALL(2); break;            \
+        case 3: CALL(3); break;            \
+        case 4: CALL(4); break;            \
+        case 5: CALL(5); break;            \
+        case 6: CALL(6); break;            \
+        case 8: CALL(8); break;            \
+        default: break;                    \
+    }
+
+// One separable pass.  variant 0 = generic kernel; 1 = fast kernels when eligible.
+// prev/dog/slot non-null fuses the DoG subtraction + max|DoG| (only meaningful on the last pass).
+static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int axis, const Taps& t, int variant,
+                      const float* prev, float* dog, unsigned* slot, cudaStream_t st) {
+    const ll total = (ll)nx * ny * nz;
+    const int n = axis == 0 ? nx : (axis == 1 ? ny : nz);
+    const bool fast = variant == 1 && (nx % 4 == 0) && supported_fast_hw(t.hw) && n >= 2 * t.hw + 2 && total >= 4096 &&
+                      !(axis == 0 && dog);
+    if (!fast) {
+        S3D_LAUNCH(blur_generic_kernel, s3d_blocks((size_t)total, 256), 256, 0, st, src, dst, nx, ny, nz, axis, t, prev,
+                   dog, slot);
+        return;
+    }
+    if (axis == 0) {
+#define CALLX(H) launch_x<H>(src, dst, nx, (ll)ny * nz, t, total, st)
+        S3D_HW_SWITCH(t.hw, CALLX)
+#undef CALLX
+    } else if (axis == 1) {
+#define CALLY(H) launch_march<H>(src, dst, nx, ny, (ll)nx, nz, (ll)nx * ny, t, total, prev, dog, slot, st)
+        S3D_HW_SWITCH(t.hw, CALLY)
+#undef CALLY
+    } else {
+#define CALLZ(H) launch_march<H>(src, dst, nx, nz, (ll)nx * ny, ny, (ll)nx, t, total, prev, dog, slot, st)
+        S3D_HW_SWITCH(t.hw, CALLZ)
+#undef CALLZ
+    }
+}
+
+}  // namespace s3d
+
+using namespace s3d;
+
+// ---------------------------------------------------------------------------------------------
+struct s3d_ctx {
+    s3d_params prm;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int nx = 0, ny = 0, nz = 0;
+    size_t n0 = 0;
+    int noct = 0, G = 0, D = 0, L = 0;
+    int dims[kMaxOct][3];
+    size_t nvox[kMaxOct];
+    float sig[kMaxG];
+    Taps taps[kMaxG];
+    float* d_input = nullptr;       // normalised input (Host_Im)
+    std::vector<float*> gss, dog;   // device levels
+    float* d_tmp[2] = {nullptr, nullptr};
+    unsigned* d_slots = nullptr;    // [0] input max|v|, [1 + o*D + i] max|DoG(o,i)|
+    float* d_thres = nullptr;       // noct * L thresholds
+    MeshConst* d_mesh = nullptr;
+    // sparse stage
+    int n_extre = 0, n_kps = 0;
+    s3d_keypoint* d_extre = nullptr;
+    int* d_codes = nullptr;
+    int* d_xyz5 = nullptr;
+    s3d_keypoint* d_kps = nullptr;
+    float* d_desc = nullptr;
+    int n_rechecked = 0, n_flipped = 0;
+    bool ran = false, levels_alive = false, queued = false;
+    cudaEvent_t ev[8];
+    bool ev_ok = false;
+    double timers[10] = {0};
+};
+
+static void free_levels(s3d_ctx* c) {
+    for (auto& p : c->gss) if (p) { cudaFreeAsync(p, c->stream); p = nullptr; }
+    for (auto& p : c->dog) if (p) { cudaFreeAsync(p, c->stream); p = nullptr; }
+    for (int i = 0; i < 2; i++) if (c->d_tmp[i]) { cudaFreeAsync(c->d_tmp[i], c->stream); c->d_tmp[i] = nullptr; }
+    c->levels_alive = false;
+}
+
+static int ctx_common_init(s3d_ctx* c, int nx, int ny, int nz, const s3d_params* p) {
+    s3d_params def;
+    s3d_default_params(&def);
+    c->prm = p ? *p : def;
+    if (nx < 8 || ny < 8 || nz < 8) return fail(S3D_ERR_ARG, "volume %dx%dx%d too small (min 8 per axis)", nx, ny, nz);
+    if ((double)nx * ny * nz >= 4294967295.0) return fail(S3D_ERR_ARG, "volume too large for 32-bit voxel keys");
+    c->L = c->prm.num_kp_levels;
+    if (c->L < 1 || c->L + 3 > kMaxG) return fail(S3D_ERR_ARG, "num_kp_levels %d unsupported (1..%d)", c->L, kMaxG - 3);
+    c->G = c->L + 3;
+    c->D = c->L + 2;
+    S3D_TRY(use_device(c->prm.device, &c->device));
+    c->nx = nx; c->ny = ny; c->nz = nz;
+    c->n0 = (size_t)nx * ny * nz;
+    S3D_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) S3D_CUDA(cudaEventCreate(&c->ev[i]));
+    c->ev_ok = true;
+    return S3D_OK;
+}
+
+static int ctx_normalize(s3d_ctx* c, const float* d_raw) {
+    // ctor: data_scale (Src/cUtil.cc:536-564)
+    S3D_CUDA(cudaMallocAsync((void**)&c->d_input, c->n0 * sizeof(float), c->stream));
+    S3D_CUDA(cudaMallocAsync((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
+    S3D_CUDA(cudaMemsetAsync(c->d_slots, 0, 256 * sizeof(unsigned), c->stream));
+    const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks(c->n0 / 4 + 1, 256), 148 * 16);
+    S3D_LAUNCH(maxabs_kernel, grid, 256, 0, c->stream, d_raw, c->n0, c->d_slots);
+    S3D_LAUNCH(normalize_kernel, grid, 256, 0, c->stream, d_raw, c->d_input, c->n0, c->d_slots);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+extern "C" {
+
+int s3d_version(void) { return 100; }
+const char* s3d_last_error(void) { return g_err; }
+uint64_t s3d_launch_count(void) { return g_launches.load(); }
+
+int s3d_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+void s3d_default_params(s3d_params* p) {
+    p->num_kp_levels = 3;       // NUM_KP_LEVELS   Include/cSIFT3D.h:15
+    p->sigma_default = 1.6f;    // SIGMA_DEFAULT   :13
+    p->sigma_n_default = 1.15f; // SIGMA_N_DEFAULT :14
+    p->peak_thresh = 0.1f;      // PEAK_THRESH     :18
+    p->max_eig_thres = 0.9f;    // EIG_THRES       :19
+    p->corner_thresh = 0.4f;    // CORNER_THRESH   :20
+    p->device = -1;
+    p->keep_levels = 0;
+    p->exact_recheck = 1;
+    p->reserved = 0;
+}
+
+int s3d_selftest(int device) {
+    clear_error();
+    int dev;
+    S3D_TRY(use_device(device, &dev));
+    float* d;
+    S3D_CUDA(cudaMalloc((void**)&d, 8 * sizeof(float)));
+    // a*b+c differs between fused and unfused evaluation for these values
+    const float a = 1.0f + 0x1p-12f, b = 1.0f + 0x1p-12f, c = -1.0f, dd = 3.0f;
+    S3D_LAUNCH(selftest_kernel, 1, 1, 0, 0, a, b, c, dd, d);
+    float h[8];
+    S3D_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    if (h[1] == h[2]) return fail(S3D_ERR_STATE, "selftest values do not separate fma from mul+add");
+    if (h[0] != h[1]) return fail(S3D_ERR_STATE, "FP32 a*b+c was contracted to FMA: build s3d_extract.cu with -fmad=false");
+    if (h[3] != h[4]) return fail(S3D_ERR_STATE, "FP32 division is not IEEE (-prec-div=true required)");
+    if (h[5] != h[6]) return fail(S3D_ERR_STATE, "FP32 sqrt is not IEEE (-prec-sqrt=true required)");
+    if (h[7] != s3d_expf_ref(-dd)) return fail(S3D_ERR_STATE, "device expf_ref differs from host expf_ref");
+    return S3D_OK;
+}
+
+int s3d_create(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
+    clear_error();
+    if (!vol || !out) return fail(S3D_ERR_ARG, "null argument");
+    s3d_ctx* c = new s3d_ctx();
+    int r = ctx_common_init(c, nx, ny, nz, p);
+    if (r != S3D_OK) { s3d_destroy(c); return r; }
+    float* d_raw = nullptr;
+    cudaEventRecord(c->ev[6], c->stream);
+    if (cudaMallocAsync((void**)&d_raw, c->n0 * sizeof(float), c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(d_raw, vol, c->n0 * sizeof(float), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
+        r = fail(S3D_ERR_CUDA, "H2D copy of the volume failed: %s", cudaGetErrorString(cudaGetLastError()));
+        s3d_destroy(c);
+        return r;
+    }
+    cudaEventRecord(c->ev[7], c->stream);
+    r = ctx_normalize(c, d_raw);
+    cudaFreeAsync(d_raw, c->stream);
+    if (r != S3D_OK) { s3d_destroy(c); return r; }
+    // the caller may free/reuse `vol` as soon as we return (the reference's ctor memcpy's it)
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+        r = fail(S3D_ERR_CUDA, "create: %s", cudaGetErrorString(cudaGetLastError()));
+        s3d_destroy(c);
+        return r;
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+    c->timers[8] = ms * 1e-3;
+    *out = c;
+    return S3D_OK;
+}
+
+int s3d_create_device(const float* d_vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
+    clear_error();
+    if (!d_vol || !out) return fail(S3D_ERR_ARG, "null argument");
+    s3d_ctx* c = new s3d_ctx();
+    int r = ctx_common_init(c, nx, ny, nz, p);
+    if (r == S3D_OK) r = ctx_normalize(c, d_vol);
+    if (r == S3D_OK && cudaStreamSynchronize(c->stream) != cudaSuccess)
+        r = fail(S3D_ERR_CUDA, "create_device: %s", cudaGetErrorString(cudaGetLastError()));
+    if (r != S3D_OK) { s3d_destroy(c); return r; }
+    *out = c;
+    return S3D_OK;
+}
+
+void s3d_destroy(s3d_handle c) {
+    if (!c) return;
+    if (c->stream) {
+        cudaSetDevice(c->device);
+        free_levels(c);
+        void* ptrs[] = {c->d_input, c->d_slots, c->d_thres, c->d_mesh, c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc};
+        for (void* q : ptrs) if (q) cudaFreeAsync(q, c->stream);
+        cudaStreamSynchronize(c->stream);
+        if (c->ev_ok) for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+        cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+// Initialize (Src/cSIFT3D.cc:237-266) + Build_Gaussian_Scale_Space (:268-319) +
+// Build_DOG_Scale_Space (:346-360; fused into the Z pass) + Detect_KeyPoints (:362-425) +
+// Assign_Orientation (:427-482) + Extract_Description (:484-502).
+static int run_impl(s3d_ctx* c) {
+    if (c->ran) return fail(S3D_ERR_STATE, "s3d_run called twice on one handle (KpSiftAlgorithm is single-shot)");
+    cudaStream_t st = c->stream;
+    S3D_CUDA(cudaSetDevice(c->device));
+    const int L = c->L, G = c->G, D = c->D;
+    S3D_CUDA(cudaEventRecord(c->ev[0], st));
+    // ---- Initialize --------------------------------------------------------------------------
+    int mn = std::min(c->nx, std::min(c->ny, c->nz));
+    c->noct = (int)log2f((float)mn) - 3 + 1;  // :254-255
+    if (c->noct < 1 || c->noct > kMaxOct) return fail(S3D_ERR_ARG, "octave count %d out of range", c->noct);
+    if (1 + c->noct * D > 256) return fail(S3D_ERR_ARG, "too many levels");
+    {
+        int nx = c->nx, ny = c->ny, nz = c->nz;
+        for (int o = 0; o < c->noct; o++) {
+            c->dims[o][0] = nx; c->dims[o][1] = ny; c->dims[o][2] = nz;
+            c->nvox[o] = (size_t)nx * ny * nz;
+            nx /= 2; ny /= 2; nz /= 2;  // Src/cUtil.cc:219-221
+        }
+    }
+    host_sigmas(L, c->prm.sigma_default, c->prm.sigma_n_default, c->sig);
+    for (int i = 0; i < G; i++)
+        if (host_taps(c->sig[i], &c->taps[i]) < 0)
+            return fail(S3D_ERR_ARG, "sigma %g needs more than %d taps per side", c->sig[i], kMaxHW);
+    c->gss.assign((size_t)c->noct * G, nullptr);
+    c->dog.assign((size_t)c->noct * D, nullptr);
+    for (int o = 0; o < c->noct; o++) {
+        const size_t bytes = std::max<size_t>(c->nvox[o], 4) * sizeof(float);
+        for (int i = 0; i < G; i++) S3D_CUDA(cudaMallocAsync((void**)&c->gss[o * G + i], bytes, st));
+        for (int i = 0; i < D; i++) S3D_CUDA(cudaMallocAsync((void**)&c->dog[o * D + i], bytes, st));
+    }
+    for (int i = 0; i < 2; i++) S3D_CUDA(cudaMallocAsync((void**)&c->d_tmp[i], c->n0 * sizeof(float), st));
+    c->levels_alive = true;
+    S3D_CUDA(cudaMallocAsync((void**)&c->d_thres, sizeof(float) * c->noct * L, st));
+    {
+        MeshConst hm;
+        host_mesh(&hm);
+        S3D_CUDA(cudaMallocAsync((void**)&c->d_mesh, sizeof(MeshConst), st));
+        S3D_CUDA(cudaMemcpyAsync(c->d_mesh, &hm, sizeof(MeshConst), cudaMemcpyHostToDevice, st));
+        S3D_CUDA(cudaStreamSynchronize(st));  // hm is a stack object
+    }
+    S3D_CUDA(cudaEventRecord(c->ev[1], st));
+
+    // ---- Gaussian scale space + DoG ------------------------------------------------------------
+    for (int o = 0; o < c->noct; o++) {
+        const int nx = c->dims[o][0], ny = c->dims[o][1], nz = c->dims[o][2];
+        for (int i = 0; i < G; i++) {
+            float* dst = c->gss[o * G + i];
+            if (i == 0 && o > 0) {
+                // octave seed = even-index decimation of level L of the previous octave (:311)
+                S3D_LAUNCH(downsample_kernel, s3d_blocks(c->nvox[o], 256), 256, 0, st, c->gss[(o - 1) * G + L],
+                           c->dims[o - 1][0], c->dims[o - 1][1], dst, nx, ny, nz);
+                continue;
+            }
+            const float* src = (o == 0 && i == 0) ? c->d_input : c->gss[o * G + i - 1];
+            const Taps& t = c->taps[i];
+            // X -> Y -> Z (:609-617); the Z pass of level i >= 1 also emits DoG[i-1] = G[i-1] - G[i]
+            blur_pass(src, c->d_tmp[0], nx, ny, nz, 0, t, 1, nullptr, nullptr, nullptr, st);
+            blur_pass(c->d_tmp[0], c->d_tmp[1], nx, ny, nz, 1, t, 1, nullptr, nullptr, nullptr, st);
+            if (i >= 1)
+                blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, src, c->dog[o * D + i - 1], c->d_slots + 1 + o * D + i - 1, st);
+            else
+                blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, nullptr, nullptr, nullptr, st);
+        }
+    }
+    S3D_CUDA(cudaGetLastError());
+    S3D_CUDA(cudaEventRecord(c->ev[2], st));
+
+    // ---- Detection -------------------------------------------------------------------------------
+    std::vector<uint32_t> gb_base((size_t)c->noct * L + 1, 0);
+    for (int o = 0; o < c->noct; o++)
+        for (int j = 0; j < L; j++)
+            gb_base[o * L + j + 1] = gb_base[o * L + j] + s3d_blocks(c->nvox[o], kDetectChunk);
+    const int nblk = (int)gb_base[(size_t)c->noct * L];
+    const unsigned stage_cap = (unsigned)std::max<size_t>(65536, c->n0 / 32);
+    int *d_blk_cnt = nullptr, *d_blk_off = nullptr, *d_total = nullptr;
+    StageEntry* d_stage = nullptr;
+    unsigned* d_stage_count = nullptr;
+    Cand* d_cand = nullptr;
+    S3D_CUDA(cudaMallocAsync((void**)&d_blk_cnt, sizeof(int) * nblk, st));
+    S3D_CUDA(cudaMallocAsync((void**)&d_blk_off, sizeof(int) * nblk, st));
+    S3D_CUDA(cudaMallocAsync((void**)&d_total, sizeof(int) * 4, st));
+    S3D_CUDA(cudaMallocAsync((void**)&d_stage, sizeof(StageEntry) * (size_t)stage_cap, st));
+    S3D_CUDA(cudaMallocAsync((void**)&d_stage_count, sizeof(unsigned), st));
+    S3D_CUDA(cudaMemsetAsync(d_stage_count, 0, sizeof(unsigned), st));
+    S3D_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int) * 4, st));
+    for (int o = 0; o < c->noct; o++)
+        for (int j = 1; j <= L; j++) {
+            const int unit = o * L + (j - 1);
+            S3D_LAUNCH(detect_kernel, s3d_blocks(c->nvox[o], kDetectChunk), 256, 0, st, c->dog[o * D + j - 1],
+                       c->dog[o * D + j], c->dog[o * D + j + 1], c->dims[o][0], c->dims[o][1], c->dims[o][2],
+                       c->d_slots + 1 + o * D + j, c->prm.peak_thresh, (uint32_t)unit, gb_base[unit], d_blk_cnt, d_stage,
+                       d_stage_count, stage_cap, c->d_thres + unit);
+        }
+    S3D_LAUNCH(scan_kernel, 1, 1024, 0, st, d_blk_cnt, d_blk_off, nblk, d_total);
+    unsigned h_stage = 0;
+    int h_total[4] = {0, 0, 0, 0};
+    S3D_CUDA(cudaMemcpyAsync(&h_stage, d_stage_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    S3D_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
+    S3D_CUDA(cudaStreamSynchronize(st));
+    if (h_stage > stage_cap)
+        return fail(S3D_ERR_CAPACITY, "detection staged %u candidates, capacity %u", h_stage, stage_cap);
+    c->n_extre = h_total[0];
+    const int ne = c->n_extre;
+    if (ne > 0) {
+        S3D_CUDA(cudaMallocAsync((void**)&d_cand, sizeof(Cand) * (size_t)ne, st));
+        S3D_LAUNCH(scatter_kernel, s3d_blocks(ne, 256), 256, 0, st, d_stage, d_stage_count, stage_cap, d_blk_off, d_cand);
+    }
+    S3D_CUDA(cudaEventRecord(c->ev[3], st));
+
+    // ---- Orientation -----------------------------------------------------------------------------
+    LevelTable tab;
+    memset(&tab, 0, sizeof(tab));
+    tab.L = L; tab.G = G;
+    for (int o = 0; o < c->noct; o++) {
+        for (int k = 0; k < 3; k++) tab.dims[o][k] = c->dims[o][k];
+        for (int i = 0; i < G; i++) {
+            tab.gss[o * G + i] = c->gss[o * G + i];
+            tab.scale[o * G + i] = host_level_scale(o, i, L, c->prm.sigma_default);
+        }
+    }
+    float* d_margins = nullptr;
+    int* d_surv = nullptr;
+    const size_t nea = std::max(ne, 1);
+    S3D_CUDA(cudaMallocAsync((void**)&c->d_extre, sizeof(s3d_keypoint) * nea, st));
+    S3D_CUDA(cudaMallocAsync((void**)&c->d_codes, sizeof(int) * nea, st));
+    S3D_CUDA(cudaMallocAsync((void**)&c->d_xyz5, sizeof(int) * 5 * nea, st));
+    S3D_CUDA(cudaMallocAsync((void**)&d_margins, sizeof(float) * nea, st));
+    S3D_CUDA(cudaMallocAsync((void**)&d_surv, sizeof(int) * nea, st));
+    if (ne > 0) {
+        const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks((size_t)ne * 32, 256), 148 * 32);
+        S3D_LAUNCH(orient_kernel, grid, 256, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes, c->d_xyz5, d_margins,
+                   c->prm.max_eig_thres, c->prm.corner_thresh);
+        if (c->prm.exact_recheck)
+            S3D_LAUNCH(orient_exact_kernel, s3d_blocks(ne, 64), 64, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes,
+                       d_margins, 2e-3f, c->prm.max_eig_thres, c->prm.corner_thresh, d_total + 1, d_total + 2);
+    }
+    S3D_LAUNCH(survivors_kernel, 1, 1024, 0, st, c->d_codes, ne, d_surv, d_total + 3);
+    S3D_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    S3D_CUDA(cudaStreamSynchronize(st));
+    c->n_rechecked = h_total[1];
+    c->n_flipped = h_total[2];
+    c->n_kps = h_total[3];
+    S3D_CUDA(cudaEventRecord(c->ev[4], st));
+
+    // ---- Description -----------------------------------------------------------------------------
+    const size_t nka = std::max(c->n_kps, 1);
+    S3D_CUDA(cudaMallocAsync((void**)&c->d_kps, sizeof(s3d_keypoint) * nka, st));
+    S3D_CUDA(cudaMallocAsync((void**)&c->d_desc, sizeof(float) * S3D_DESC_LEN * nka, st));
+    if (c->n_kps > 0)
+        S3D_LAUNCH(describe_kernel, c->n_kps, kDescWarps * 32, 0, st, c->d_extre, d_surv, c->n_kps, tab, c->d_mesh,
+                   c->d_kps, c->d_desc);
+    S3D_CUDA(cudaGetLastError());
+    S3D_CUDA(cudaEventRecord(c->ev[5], st));
+
+    // ---- Release_SIFT (:1659-1678) unless the caller asked to keep the pyramids ---------------
+    if (!c->prm.keep_levels) free_levels(c);
+    void* tmp[] = {d_blk_cnt, d_blk_off, d_total, d_stage, d_stage_count, d_cand, d_margins, d_surv};
+    for (void* q : tmp) if (q) cudaFreeAsync(q, st);
+    S3D_CUDA(cudaEventRecord(c->ev[6], st));
+    c->queued = true;
+    return S3D_OK;
+}
+
+int s3d_run_async(s3d_handle c) {
+    clear_error();
+    if (!c) return fail(S3D_ERR_ARG, "null handle");
+    return run_impl(c);
+}
+
+int s3d_wait(s3d_handle c) {
+    clear_error();
+    if (!c) return fail(S3D_ERR_ARG, "null handle");
+    if (!c->queued) return fail(S3D_ERR_STATE, "s3d_wait before s3d_run_async");
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    if (!c->ran) {
+        float ms;
+        for (int i = 0; i < 6; i++) {
+            cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
+            // alloc, gss(+dog fused), detect, orient, describe, release
+            static const int slot[6] = {0, 1, 3, 4, 5, 6};
+            c->timers[slot[i]] = ms * 1e-3;
+        }
+        c->timers[2] = 0.0;  // DoG is fused into the Z pass
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[6]);
+        c->timers[7] = ms * 1e-3;
+        c->ran = true;
+    }
+    return S3D_OK;
+}
+
+int s3d_run(s3d_handle c) {
+    int r = s3d_run_async(c);
+    if (r != S3D_OK) return r;
+    return s3d_wait(c);
+}
+
+int s3d_num_octaves(s3d_handle c, int* n) {
+    if (!c || !n) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    *n = c->noct;
+    return S3D_OK;
+}
+
+int s3d_level_dims(s3d_handle c, int o, int* d) {
+    if (!c || !d) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    if (o < 0 || o >= c->noct) return fail(S3D_ERR_ARG, "octave %d out of range", o);
+    d[0] = c->dims[o][0]; d[1] = c->dims[o][1]; d[2] = c->dims[o][2];
+    return S3D_OK;
+}
+
+int s3d_num_keypoints(s3d_handle c, int* n) {
+    if (!c || !n) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    *n = c->n_kps;
+    return S3D_OK;
+}
+
+int s3d_get_keypoints(s3d_handle c, s3d_keypoint* kp, float* desc) {
+    clear_error();
+    if (!c) return fail(S3D_ERR_ARG, "null handle");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    S3D_CUDA(cudaSetDevice(c->device));
+    cudaEvent_t e0 = c->ev[6], e1 = c->ev[7];
+    S3D_CUDA(cudaEventRecord(e0, c->stream));
+    if (c->n_kps > 0) {
+        if (kp) S3D_CUDA(cudaMemcpyAsync(kp, c->d_kps, sizeof(s3d_keypoint) * c->n_kps, cudaMemcpyDeviceToHost, c->stream));
+        if (desc)
+            S3D_CUDA(cudaMemcpyAsync(desc, c->d_desc, sizeof(float) * S3D_DESC_LEN * (size_t)c->n_kps,
+                                     cudaMemcpyDeviceToHost, c->stream));
+    }
+    S3D_CUDA(cudaEventRecord(e1, c->stream));
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c->timers[9] = ms * 1e-3;
+    return S3D_OK;
+}
+
+int s3d_num_extrema(s3d_handle c, int* n) {
+    if (!c || !n) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    *n = c->n_extre;
+    return S3D_OK;
+}
+
+int s3d_get_extrema(s3d_handle c, s3d_keypoint* kp, int* codes, int* xyz5) {
+    clear_error();
+    if (!c) return fail(S3D_ERR_ARG, "null handle");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    S3D_CUDA(cudaSetDevice(c->device));
+    if (c->n_extre > 0) {
+        if (kp) S3D_CUDA(cudaMemcpyAsync(kp, c->d_extre, sizeof(s3d_keypoint) * c->n_extre, cudaMemcpyDeviceToHost, c->stream));
+        if (codes) S3D_CUDA(cudaMemcpyAsync(codes, c->d_codes, sizeof(int) * c->n_extre, cudaMemcpyDeviceToHost, c->stream));
+        if (xyz5) S3D_CUDA(cudaMemcpyAsync(xyz5, c->d_xyz5, sizeof(int) * 5 * c->n_extre, cudaMemcpyDeviceToHost, c->stream));
+    }
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    return S3D_OK;
+}
+
+int s3d_get_level(s3d_handle c, int which, int idx, float* out) {
+    clear_error();
+    if (!c || !out) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    if (!c->levels_alive) return fail(S3D_ERR_STATE, "pyramids were released; create the handle with keep_levels=1");
+    const int per = which == 0 ? c->G : c->D;
+    if (which < 0 || which > 1 || idx < 0 || idx >= c->noct * per) return fail(S3D_ERR_ARG, "level index out of range");
+    const float* src = which == 0 ? c->gss[idx] : c->dog[idx];
+    S3D_CUDA(cudaSetDevice(c->device));
+    S3D_CUDA(cudaMemcpyAsync(out, src, c->nvox[idx / per] * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    return S3D_OK;
+}
+
+int s3d_get_input(s3d_handle c, float* out) {
+    clear_error();
+    if (!c || !out) return fail(S3D_ERR_ARG, "null argument");
+    S3D_CUDA(cudaSetDevice(c->device));
+    S3D_CUDA(cudaMemcpyAsync(out, c->d_input, c->n0 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    return S3D_OK;
+}
+
+int s3d_get_thresholds(s3d_handle c, float* out, int n) {
+    clear_error();
+    if (!c || !out) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    n = std::min(n, c->noct * c->L);
+    S3D_CUDA(cudaSetDevice(c->device));
+    S3D_CUDA(cudaMemcpyAsync(out, c->d_thres, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    return S3D_OK;
+}
+
+int s3d_get_timers(s3d_handle c, double* t) {
+    if (!c || !t) return fail(S3D_ERR_ARG, "null argument");
+    for (int i = 0; i < 10; i++) t[i] = c->timers[i];
+    return S3D_OK;
+}
+
+// ---- free kernels ------------------------------------------------------------------------------
+
+static int blur_host_buffers(const float* src, int nx, int ny, int nz, const Taps* taps3, const int* axes, int npass,
+                             int variant, float* dst) {
+    int dev;
+    S3D_TRY(use_device(-1, &dev));
+    const size_t n = (size_t)nx * ny * nz;
+    float *a = nullptr, *b = nullptr;
+    S3D_CUDA(cudaMalloc((void**)&a, std::max<size_t>(n, 4) * sizeof(float)));
+    S3D_CUDA(cudaMalloc((void**)&b, std::max<size_t>(n, 4) * sizeof(float)));
+    S3D_CUDA(cudaMemcpy(a, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    for (int p = 0; p < npass; p++) {
+        blur_pass(a, b, nx, ny, nz, axes[p], taps3[p], variant, nullptr, nullptr, nullptr, 0);
+        std::swap(a, b);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(dst, a, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(a);
+    cudaFree(b);
+    if (e != cudaSuccess) return fail(S3D_ERR_CUDA, "blur: %s", cudaGetErrorString(e));
+    return S3D_OK;
+}
+
+int s3d_gaussian_smooth(const float* src, int nx, int ny, int nz, float sigma, float* dst) {
+    clear_error();
+    if (!src || !dst || nx < 1 || ny < 1 || nz < 1) return fail(S3D_ERR_ARG, "bad argument");
+    Taps t[3];
+    if (host_taps(sigma, &t[0]) < 0) return fail(S3D_ERR_ARG, "sigma %g needs more than %d taps per side", sigma, kMaxHW);
+    t[1] = t[0]; t[2] = t[0];
+    const int axes[3] = {0, 1, 2};
+    return blur_host_buffers(src, nx, ny, nz, t, axes, 3, 1, dst);
+}
+
+int s3d_blur_axis(const float* src, int nx, int ny, int nz, int axis, const float* w, int hw, int variant, float* dst) {
+    clear_error();
+    if (!src || !dst || !w || nx < 1 || ny < 1 || nz < 1 || axis < 0 || axis > 2) return fail(S3D_ERR_ARG, "bad argument");
+    if (hw < 1 || hw > kMaxHW) return fail(S3D_ERR_ARG, "hw %d out of range (1..%d)", hw, kMaxHW);
+    Taps t;
+    memset(&t, 0, sizeof(t));
+    t.hw = hw;
+    for (int i = 0; i < 2 * hw + 1; i++) t.w[i] = w[i];
+    return blur_host_buffers(src, nx, ny, nz, &t, &axis, 1, variant, dst);
+}
+
+int s3d_downsample(const float* src, int nx, int ny, int nz, float* dst) {
+    clear_error();
+    if (!src || !dst || nx < 2 || ny < 2 || nz < 2) return fail(S3D_ERR_ARG, "bad argument");
+    int dev;
+    S3D_TRY(use_device(-1, &dev));
+    const int dx = nx / 2, dy = ny / 2, dz = nz / 2;
+    const size_t n = (size_t)nx * ny * nz, m = (size_t)dx * dy * dz;
+    float *a = nullptr, *b = nullptr;
+    S3D_CUDA(cudaMalloc((void**)&a, n * sizeof(float)));
+    S3D_CUDA(cudaMalloc((void**)&b, m * sizeof(float)));
+    S3D_CUDA(cudaMemcpy(a, src, n * sizeof(float), cudaMemcpyHostToDevice));
+    S3D_LAUNCH(downsample_kernel, s3d_blocks(m, 256), 256, 0, 0, a, nx, ny, b, dx, dy, dz);
+    cudaError_t e = cudaMemcpy(dst, b, m * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(a);
+    cudaFree(b);
+    if (e != cudaSuccess) return fail(S3D_ERR_CUDA, "downsample: %s", cudaGetErrorString(e));
+    return S3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,948 @@
+// s3d_kernels.cuh — device code of the extraction path (dense pyramid + sparse keypoint stages).
+//
+// COMPILED WITH -fmad=false.  The dense stages are bit-exact against the reference, which is
+// built for baseline x86-64 where `acc += w * v` is an IEEE multiply followed by an IEEE add.
+// With FMA contraction off, IEEE division/sqrt (nvcc defaults) and the same operation order,
+// FP32 expressions below round exactly like the reference's.  s3d_selftest() verifies the flags.
+//
+// Layout: every volume is float32, x fastest (xs=1, ys=nx, zs=nx*ny), as in
+// /root/reference/3DSIFT/Src/Util/cTexImage.cc:28-30.
+#pragma once
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "expf_ref.h"
+#include "sift3d_b200.h"
+
+namespace s3d {
+
+constexpr int kMaxHW = 16;   // taps up to 33 (sigma <= 5.33); defaults use hw in {2,3,4,5,6,8}
+constexpr int kMaxOct = 16;
+constexpr int kMaxG = 12;    // num_kp_levels + 3 <= 12
+
+struct Taps {
+    int hw;
+    float w[2 * kMaxHW + 1];
+};
+
+typedef long long ll;
+
+__device__ __forceinline__ float ld_clamped(const float* __restrict__ p, ll i, ll total) {
+    i = i < 0 ? 0 : (i >= total ? total - 1 : i);
+    return p[i];
+}
+
+// One output of the reference's boundary sweep (GaussianSmooth_3D_Imp second pass,
+// Src/cSIFT3D.cc:722-788): mirror about 0 without repeating the edge (:747-750), right edge
+// 2*(n-1)-c-0.1 (:751-755), (int) truncation and linear blend of in[lo], in[lo+1] (:757-764).
+// line0 = flat index of the element with coordinate 0 on this line, st = stride along the axis.
+// Reads are flat and unchecked in the reference (an out-of-row index lands in the neighbouring
+// row); indices outside the whole buffer are clamped to its ends.
+__device__ __forceinline__ float blur_boundary_one(const float* __restrict__ buf, ll line0, ll st, int n, int p,
+                                                   const Taps& t, ll total) {
+    float acc = 0.0f;
+    const int dim_end = n - 1;
+    for (int d = -t.hw; d <= t.hw; ++d) {
+        float c = (float)p - (float)d;
+        if (c < 0)
+            c = -1 * c;
+        else if (c >= dim_end)
+            c = (float)(2 * dim_end) - c - 0.1f;
+        int il = (int)c;
+        float frac = c - (float)il;
+        float lo = ld_clamped(buf, line0 + (ll)il * st, total);
+        float hi = ld_clamped(buf, line0 + (ll)(il + 1) * st, total);
+        acc += t.w[d + t.hw] * ((1.0f - frac) * lo + frac * hi);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ bool blur_is_interior(int p, int n, int hw) { return p >= hw && p <= n - hw - 2; }
+
+__device__ __forceinline__ void atomic_max_abs(unsigned* slot, float m) {
+    // non-negative floats order like their bit patterns
+    atomicMax(slot, __float_as_uint(m));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1  max|v| (im_max_abs / data_scale first sweep, Src/cUtil.cc:538-550,587-605) and the IEEE
+//     division sweep (Src/cUtil.cc:552-561).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxabs_kernel(const float* __restrict__ src, size_t n, unsigned* slot) {
+    float m = 0.0f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = n >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = s4[i];
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        m = fmaxf(m, fabsf(src[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomic_max_abs(slot, m);
+}
+
+__global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n,
+                                                        const unsigned* __restrict__ slot) {
+    const float mx = __uint_as_float(*slot);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n4 = n >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 v = s4[i];
+        v.x = v.x / mx; v.y = v.y / mx; v.z = v.z / mx; v.w = v.w / mx;
+        d4[i] = v;
+    }
+    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i] / mx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2  separable Gaussian pass.  GaussianSmooth_3D_Imp, Src/cSIFT3D.cc:624-790.
+//     Per output: taps d = -hw..+hw ascending, acc = acc + w[d+hw] * in[p-d] (interior samples
+//     are 1.0f*in[c] + 0.0f*in[c+1] == in[c]); boundary outputs use blur_boundary_one.
+//     DOG variants additionally write dog = (cur - prev) * (-1) (Sub, Src/cSIFT3D.cc:875) and
+//     fold max|dog| into *maxslot (im_max_abs for Detect_KeyPoints, Src/cSIFT3D.cc:384).
+// ---------------------------------------------------------------------------------------------
+
+// Generic: one thread per output, any dims, any hw <= kMaxHW, any axis.
+__global__ void __launch_bounds__(256) blur_generic_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
+                                                           int ny, int nz, int axis, Taps t,
+                                                           const float* __restrict__ prev, float* __restrict__ dog,
+                                                           unsigned* maxslot) {
+    const ll total = (ll)nx * ny * nz;
+    const ll idx = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.0f;
+    if (idx < total) {
+        const int x = (int)(idx % nx), y = (int)((idx / nx) % ny), z = (int)(idx / ((ll)nx * ny));
+        const int p = axis == 0 ? x : (axis == 1 ? y : z);
+        const int n = axis == 0 ? nx : (axis == 1 ? ny : nz);
+        const ll st = axis == 0 ? 1 : (axis == 1 ? (ll)nx : (ll)nx * ny);
+        const ll line0 = idx - (ll)p * st;
+        float acc;
+        if (blur_is_interior(p, n, t.hw)) {
+            acc = 0.0f;
+            for (int d = -t.hw; d <= t.hw; ++d) acc += t.w[d + t.hw] * src[line0 + (ll)(p - d) * st];
+        } else {
+            acc = blur_boundary_one(src, line0, st, n, p, t, total);
+        }
+        dst[idx] = acc;
+        if (dog) {
+            float dv = (acc - prev[idx]) * (-1);
+            dog[idx] = dv;
+            m = fabsf(dv);
+        }
+    }
+    if (dog) {
+        m = warp_max(m);
+        if ((threadIdx.x & 31) == 0) atomic_max_abs(maxslot, m);
+    }
+}
+
+// X pass, 4 outputs per thread (float4 store).  Requires nx % 4 == 0.
+template <int HW>
+__global__ void __launch_bounds__(256) blur_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
+                                                     ll nrows, Taps t, ll total) {
+    constexpr int PAD = (HW + 3) / 4 * 4;
+    constexpr int NV = (2 * PAD + 4) / 4;
+    const int nx4 = nx >> 2;
+    const ll gid = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nrows * nx4) return;
+    const ll row = gid / nx4;
+    const int x0 = (int)(gid - row * nx4) * 4;
+    const float* r = src + row * nx;
+    float v[2 * PAD + 4];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        const int xx = x0 - PAD + 4 * q;
+        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (xx >= 0 && xx < nx) f = *reinterpret_cast<const float4*>(r + xx);
+        v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+    }
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int x = x0 + j;
+        if (blur_is_interior(x, nx, HW)) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k <= 2 * HW; ++k) acc += t.w[k] * v[PAD + j + HW - k];
+            o[j] = acc;
+        } else {
+            o[j] = blur_boundary_one(src, row * nx, 1, nx, x, t, total);
+        }
+    }
+    *reinterpret_cast<float4*>(dst + row * nx + x0) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// Y / Z pass: each thread owns a float4 column (4 consecutive x) and marches along the axis over
+// a segment, keeping the 2*HW+1 most recent inputs in a register ring (static indices through a
+// (2*HW+1)-way unrolled loop), so every input is loaded once per segment.
+// Requires nx % 4 == 0.  n = length of the marched axis, st = its stride, n_other / st_other =
+// the remaining non-x axis.
+template <int HW, bool DOG>
+__global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
+                                                         int n, ll st, int n_other, ll st_other, int seg, Taps t,
+                                                         ll total, const float* __restrict__ prev,
+                                                         float* __restrict__ dog, unsigned* maxslot) {
+    constexpr int W = 2 * HW + 1;
+    const int nx4 = nx >> 2;
+    const int nseg = (n + seg - 1) / seg;
+    const ll gid = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.0f;
+    if (gid < (ll)nx4 * n_other * nseg) {
+        const int x4 = (int)(gid % nx4);
+        const ll tt = gid / nx4;
+        const int other = (int)(tt % n_other);
+        const int s = (int)(tt / n_other);
+        const int p0 = s * seg;
+        const int p1 = min(n, p0 + seg);
+        const ll line0 = (ll)x4 * 4 + (ll)other * st_other;  // flat index of coordinate 0 on this line
+        const float* col = src + line0;
+        float4 win[W];
+        // prologue: ring slots for inputs p0-HW .. p0+HW-1 (relative r = 0 .. 2HW-1)
+#pragma unroll
+        for (int r = 0; r < 2 * HW; ++r) {
+            const int q = p0 - HW + r;
+            win[r] = (q >= 0 && q < n) ? *reinterpret_cast<const float4*>(col + (ll)q * st) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        win[2 * HW] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ib = 0; p0 + ib < p1; ib += W) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const int p = p0 + ib + j;
+                if (p < p1) {
+                    // newest input p+HW goes to the slot of the oldest one (relative r = ib+j+2HW)
+                    const int q = p + HW;
+                    win[(j + 2 * HW) % W] = (q < n) ? *reinterpret_cast<const float4*>(col + (ll)q * st)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 acc;
+                    if (blur_is_interior(p, n, HW)) {
+                        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k <= 2 * HW; ++k) {
+                            const float4 v = win[(j + 2 * HW - k) % W];  // input p+HW-k
+                            const float w = t.w[k];
+                            acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+                        }
+                    } else {
+                        acc.x = blur_boundary_one(src, line0 + 0, st, n, p, t, total);
+                        acc.y = blur_boundary_one(src, line0 + 1, st, n, p, t, total);
+                        acc.z = blur_boundary_one(src, line0 + 2, st, n, p, t, total);
+                        acc.w = blur_boundary_one(src, line0 + 3, st, n, p, t, total);
+                    }
+                    const ll oidx = line0 + (ll)p * st;
+                    *reinterpret_cast<float4*>(dst + oidx) = acc;
+                    if (DOG) {
+                        const float4 pv = *reinterpret_cast<const float4*>(prev + oidx);
+                        float4 dv;
+                        dv.x = (acc.x - pv.x) * (-1); dv.y = (acc.y - pv.y) * (-1);
+                        dv.z = (acc.z - pv.z) * (-1); dv.w = (acc.w - pv.w) * (-1);
+                        *reinterpret_cast<float4*>(dog + oidx) = dv;
+                        m = fmaxf(m, fmaxf(fmaxf(fabsf(dv.x), fabsf(dv.y)), fmaxf(fabsf(dv.z), fabsf(dv.w))));
+                    }
+                }
+            }
+        }
+    }
+    if (DOG) {
+        m = warp_max(m);
+        if ((threadIdx.x & 31) == 0) atomic_max_abs(maxslot, m);
+    }
+}
+
+// K3  DownSample_3D, Src/cSIFT3D.cc:506-533: dst(n,m,k) = src(2n,2m,2k).
+__global__ void __launch_bounds__(256) downsample_kernel(const float* __restrict__ src, int sx, int sy, float* __restrict__ dst,
+                                                         int dx, int dy, int dz) {
+    const ll total = (ll)dx * dy * dz;
+    const ll idx = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int n = (int)(idx % dx), mm = (int)((idx / dx) % dy), k = (int)(idx / ((ll)dx * dy));
+    dst[idx] = src[(ll)(2 * n) + (ll)(2 * mm) * sx + (ll)(2 * k) * sx * sy];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4  Detection.  Detect_KeyPoints Src/cSIFT3D.cc:362-425 + IsExtrema_neighbor :884-911.
+//     thres = peak_thresh * max|D[j]| (:384-385); candidate iff |val| > thres (strict) and val is
+//     strictly below or strictly above its 6 face neighbours in D[j] and the same voxel in
+//     D[j-1], D[j+1] (8 neighbours, App. B Q1); x,y,z in [1, n-2].
+//     Ordered compaction: each CTA owns 1024 consecutive voxels; flagged voxels are ranked inside
+//     the CTA (ballot-free prefix over 4 flags/thread + warp scan), staged under an atomically
+//     claimed segment, and a later scan of per-CTA counts turns (cta, rank) into the raster
+//     position — the reference's (octave, level, z, y, x) emission order (App. B Q16).
+// ---------------------------------------------------------------------------------------------
+struct StageEntry {
+    uint32_t key;   // linear voxel index inside the level
+    uint32_t gb;    // global CTA index over all (octave, level) detect units
+    uint32_t rank;  // rank inside the CTA
+    uint32_t unit;  // octave * L + (level - 1)
+};
+
+constexpr int kDetectChunk = 1024;
+
+__global__ void __launch_bounds__(256) detect_kernel(const float* __restrict__ Dm, const float* __restrict__ D0,
+                                                     const float* __restrict__ Dp, int nx, int ny, int nz,
+                                                     const unsigned* __restrict__ maxslot, float peak, uint32_t unit,
+                                                     uint32_t gb_base, int* __restrict__ blk_cnt,
+                                                     StageEntry* __restrict__ stage, unsigned* stage_count,
+                                                     unsigned stage_cap, float* thres_out) {
+    __shared__ int warp_tot[8];
+    __shared__ unsigned seg_base;
+    const ll total = (ll)nx * ny * nz;
+    const ll base = ((ll)blockIdx.x * 256 + threadIdx.x) * 4;
+    const float thres = peak * __uint_as_float(*maxslot);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && thres_out) *thres_out = thres;
+    const ll ys = nx, zs = (ll)nx * ny;
+    unsigned flags = 0;
+    if (base < total) {
+        float v[4];
+        if (base + 3 < total && (total & 3) == 0) {
+            const float4 f = *reinterpret_cast<const float4*>(D0 + base);
+            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (base + j < total) ? D0[base + j] : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const ll i = base + j;
+            const float val = v[j];
+            if (i < total && (val > thres || val < -thres)) {
+                const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / zs);
+                if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
+                    const float t0 = Dm[i], t1 = D0[i - 1], t2 = D0[i + 1], t3 = D0[i + ys], t4 = D0[i - ys],
+                                t5 = D0[i + zs], t6 = D0[i - zs], t7 = Dp[i];
+                    const bool mn = val < t0 && val < t1 && val < t2 && val < t3 && val < t4 && val < t5 && val < t6 &&
+                                    val < t7;
+                    const bool mx = val > t0 && val > t1 && val > t2 && val > t3 && val > t4 && val > t5 && val > t6 &&
+                                    val > t7;
+                    if (mn || mx) flags |= 1u << j;
+                }
+            }
+        }
+    }
+    const int cnt = __popc(flags);
+    int incl = cnt;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        if (w < wid) wbase += warp_tot[w];
+        tot += warp_tot[w];
+    }
+    if (threadIdx.x == 0) {
+        blk_cnt[gb_base + blockIdx.x] = tot;
+        seg_base = tot ? atomicAdd(stage_count, (unsigned)tot) : 0u;
+    }
+    __syncthreads();
+    if (cnt) {
+        unsigned rank = (unsigned)(wbase + incl - cnt);
+        const unsigned sb = seg_base;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (flags & (1u << j)) {
+                const unsigned pos = sb + rank;
+                if (pos < stage_cap) {
+                    StageEntry e;
+                    e.key = (uint32_t)(base + j); e.gb = gb_base + blockIdx.x; e.rank = rank; e.unit = unit;
+                    stage[pos] = e;
+                }
+                ++rank;
+            }
+    }
+}
+
+// Exclusive scan of n ints by ONE CTA (1024 threads); total -> *total_out.
+__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int* total_out) {
+    __shared__ int part[1024];
+    const int per = (n + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += in[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;
+    for (int i = b; i < e; ++i) {
+        out[i] = run;
+        run += in[i];
+    }
+    if (threadIdx.x == 1023 && total_out) *total_out = part[1023];
+}
+
+struct Cand {
+    uint32_t key;
+    uint32_t unit;
+};
+
+__global__ void __launch_bounds__(256) scatter_kernel(const StageEntry* __restrict__ stage, const unsigned* stage_count,
+                                                      unsigned stage_cap, const int* __restrict__ blk_off,
+                                                      Cand* __restrict__ cand) {
+    const unsigned n = min(*stage_count, stage_cap);
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const StageEntry e = stage[i];
+    Cand c;
+    c.key = e.key; c.unit = e.unit;
+    cand[blk_off[e.gb] + e.rank] = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Level table shared by the sparse kernels.
+// ---------------------------------------------------------------------------------------------
+struct LevelTable {
+    const float* gss[kMaxOct * kMaxG];
+    float scale[kMaxOct * kMaxG];  // (float)(2^(o+s/L) * sigma0), Src/cUtil.cc:209-210
+    int dims[kMaxOct][3];
+    int L;  // num_kp_levels
+    int G;  // L + 3
+};
+
+// Symmetric 3x3 eigen-decomposition in double (cyclic Jacobi), columns of V = unit eigenvectors.
+// Stands in for Eigen::EigenSolver<Matrix3d> (Src/cSIFT3D.cc:1016-1029): eigenvalues agree to
+// ~1e-15 relative, eigenvectors up to sign, and the reference fixes signs itself (:1089-1108).
+__device__ inline void eig3_jacobi(const double A[9], double val[3], double V[9]) {
+    double a[3][3] = {{A[0], A[1], A[2]}, {A[3], A[4], A[5]}, {A[6], A[7], A[8]}};
+    double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 64; sweep++) {
+        double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        double diag = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]);
+        if (off <= 1e-300 || off <= 1e-18 * diag) break;
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int q = p + 1; q < 3; q++) {
+                if (a[p][q] == 0.0) continue;
+                double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - s * akq;
+                    a[k][q] = s * akp + c * akq;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - s * aqk;
+                    a[q][k] = s * apk + c * aqk;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - s * vkq;
+                    v[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        val[i] = a[i][i];
+        double nn = sqrt(v[0][i] * v[0][i] + v[1][i] * v[1][i] + v[2][i] * v[2][i]);
+#pragma unroll
+        for (int k = 0; k < 3; k++) V[k * 3 + i] = v[k][i] / nn;
+    }
+}
+
+// Window bounds, Src/cSIFT3D.cc:939-955 and :1182-1198 (App. B Q23).
+__device__ __forceinline__ void window_bounds(float c, float r_over_u, int n, int& s, int& e) {
+    int a = (int)floorf(c - r_over_u);
+    s = a > 1 ? a : 1;
+    int b = (int)ceilf(c + r_over_u);
+    e = b < (n - 2) ? b : n - 1 - 1;
+}
+
+struct OrientSums {
+    float t00, t01, t02, t11, t12, t22, wx, wy, wz;
+};
+
+// One window voxel of Assign_Orientation_Imp, Src/cSIFT3D.cc:964-994 (same operation order).
+__device__ __forceinline__ void orient_voxel(const float* __restrict__ g, ll i, ll ys, ll zs, float dx, float dy, float dz,
+                                             float u, float sigma, float r2, OrientSums& S) {
+    const float sq = dx * dx + dy * dy + dz * dz;
+    if (sq > r2) return;
+    const float weight = s3d_expf_ref((float)(-0.5 * (double)sq / (double)(sigma * sigma)));
+    float vx = (float)(0.5 * (double)(g[i + 1] - g[i - 1]));
+    float vy = (float)(0.5 * (double)(g[i + ys] - g[i - ys]));
+    float vz = (float)(0.5 * (double)(g[i + zs] - g[i - zs]));
+    const float iu = 1.0f / u;
+    vx *= iu; vy *= iu; vz *= iu;
+    S.t00 += vx * vx * weight;
+    S.t01 += vx * vy * weight;
+    S.t02 += vx * vz * weight;
+    S.t11 += vy * vy * weight;
+    S.t12 += vy * vz * weight;
+    S.t22 += vz * vz * weight;
+    S.wx += vx * weight; S.wy += vy * weight; S.wz += vz * weight;
+}
+
+// Everything after the window loop of Assign_Orientation_Imp, Src/cSIFT3D.cc:1000-1137.
+// Fills kp (str_tensor, win, eigvalue, eigvector, Rotation) and returns 1 / -1 / -2 / -3.
+// margin_out (may be null) receives the smallest relative distance of any accept/reject test to
+// its threshold (used to pick candidates for the exact serial re-evaluation).
+__device__ inline int orient_finish(const OrientSums& S, s3d_keypoint& kp, float max_eig_ratio, float corner_thresh,
+                                    float* margin_out) {
+    float* T = kp.str_tensor;
+    T[0] = S.t00; T[1] = S.t01; T[2] = S.t02; T[4] = S.t11; T[5] = S.t12; T[8] = S.t22;
+    T[3] = T[1]; T[6] = T[2]; T[7] = T[5];
+    kp.win[0] = S.wx; kp.win[1] = S.wy; kp.win[2] = S.wz;
+    float margin = FLT_MAX;
+    const float wn2 = S.wx * S.wx + S.wy * S.wy + S.wz * S.wz;
+    margin = fminf(margin, fabsf(wn2 - 1E-10f) / 1E-10f);
+    if (wn2 < 1E-10f) {
+        if (margin_out) *margin_out = margin;
+        return -1;
+    }
+    double A[9], val[3], V[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) A[i] = (double)T[i];
+    eig3_jacobi(A, val, V);
+    float ev[3], evec[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        ev[i] = (float)val[i];
+#pragma unroll
+        for (int k = 0; k < 3; k++) evec[i][k] = (float)V[k * 3 + i];
+    }
+    // ascending by value (std::sort with cmp, :1050)
+#pragma unroll
+    for (int i = 1; i < 3; i++)
+#pragma unroll
+        for (int j = i; j > 0; j--)
+            if (ev[j] < ev[j - 1]) {
+                float tv = ev[j]; ev[j] = ev[j - 1]; ev[j - 1] = tv;
+#pragma unroll
+                for (int k = 0; k < 3; k++) { float tk = evec[j][k]; evec[j][k] = evec[j - 1][k]; evec[j - 1][k] = tk; }
+            }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        kp.eigvalue[i] = ev[i];
+#pragma unroll
+        for (int k = 0; k < 3; k++) kp.eigvector[i * 3 + k] = evec[i][k];
+    }
+    const float r01 = fabsf(ev[0] / ev[1]), r12 = fabsf(ev[1] / ev[2]);
+    margin = fminf(margin, fminf(fabsf(r01 - max_eig_ratio), fabsf(r12 - max_eig_ratio)));
+    int code = 1;
+    if (r01 > max_eig_ratio || r12 > max_eig_ratio) code = -2;
+    // DistinctEig, :1140-1150
+    if (code == 1 && (fabs((double)(ev[0] - ev[1])) < DBL_EPSILON || fabs((double)(ev[0] - ev[2])) < DBL_EPSILON ||
+                      fabs((double)(ev[2] - ev[1])) < DBL_EPSILON))
+        code = -2;
+    if (code != 1) {
+        if (margin_out) *margin_out = margin;
+        return code;
+    }
+    const float d_NORM = sqrtf(wn2);
+    float corner_score = FLT_MAX;
+#pragma unroll
+    for (int i = 2; i > 0; i--) {
+        const float ex = evec[i][0], ey = evec[i][1], ez = evec[i][2];
+        const float d = ex * S.wx + ey * S.wy + ez * S.wz;
+        const float q_NORM = sqrtf(ex * ex + ey * ey + ez * ez);
+        const float cos_ang = d / (d_NORM * q_NORM);
+        const float abs_cos_ang = fabsf(cos_ang);
+        corner_score = corner_score < abs_cos_ang ? corner_score : abs_cos_ang;
+        const float sgn = d > 0.0f ? 1.0f : -1.0f;
+        evec[i][0] *= sgn; evec[i][1] *= sgn; evec[i][2] *= sgn;
+    }
+    margin = fminf(margin, fabsf(corner_score - corner_thresh));
+    if (margin_out) *margin_out = margin;
+    if (corner_score < corner_thresh) return -3;
+    const float* v1 = evec[2];
+    const float* v2 = evec[1];
+    const float vr0 = v1[1] * v2[2] - v1[2] * v2[1];
+    const float vr1 = v1[2] * v2[0] - v1[0] * v2[2];
+    const float vr2 = v1[0] * v2[1] - v1[1] * v2[0];
+    float* R = kp.Rotation;
+    R[0] = v1[0]; R[1] = v2[0]; R[2] = vr0;
+    R[3] = v1[1]; R[4] = v2[1]; R[5] = vr1;
+    R[6] = v1[2]; R[7] = v2[2]; R[8] = vr2;
+    return 1;
+}
+
+__device__ __forceinline__ void cand_decode(const Cand c, const LevelTable& tab, int& o, int& lvl, int& x, int& y, int& z) {
+    o = (int)(c.unit / (uint32_t)tab.L);
+    lvl = (int)(c.unit % (uint32_t)tab.L) + 1;
+    const int nx = tab.dims[o][0], ny = tab.dims[o][1];
+    x = (int)(c.key % (uint32_t)nx);
+    y = (int)((c.key / (uint32_t)nx) % (uint32_t)ny);
+    z = (int)(c.key / ((uint32_t)nx * (uint32_t)ny));
+}
+
+__device__ __forceinline__ void kp_init(s3d_keypoint& kp, int o, int lvl, int x, int y, int z, float scale) {
+    // Detect_KeyPoints :401-408 + Initialize_Keypoint Src/cUtil.cc:449-463
+    kp.x = (float)x; kp.y = (float)y; kp.z = (float)z;
+    kp.scale = scale; kp.octave = o; kp.level = lvl;
+    kp.rx = kp.ry = kp.rz = -1.0f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { kp.win[i] = 0.f; kp.eigvalue[i] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < 9; i++) { kp.eigvector[i] = 0.f; kp.Rotation[i] = 0.f; kp.str_tensor[i] = 0.f; }
+    kp.desc = nullptr;
+}
+
+// K5  Orientation: one warp per detection.  Assign_Orientation Src/cSIFT3D.cc:427-482.
+//     Lanes stride over the (y,x) plane of each z slice, keep 9 partial sums, butterfly-reduce
+//     (fixed tree, so results are run-to-run deterministic), then finish redundantly per lane.
+//     The FP32 summation order differs from the reference's serial z,y,x order; detections whose
+//     tests land within `recheck_margin` of a threshold are flagged (margins[]) for the exact
+//     serial re-evaluation kernel below.
+__global__ void __launch_bounds__(256) orient_kernel(const Cand* __restrict__ cand, int ncand, LevelTable tab,
+                                                     s3d_keypoint* __restrict__ out, int* __restrict__ codes,
+                                                     int* __restrict__ xyz5, float* __restrict__ margins, float max_eig,
+                                                     float corner) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < ncand; ci += warps_per_grid) {
+        int o, lvl, x, y, z;
+        cand_decode(cand[ci], tab, o, lvl, x, y, z);
+        const int nx = tab.dims[o][0], ny = tab.dims[o][1], nz = tab.dims[o][2];
+        const float* g = tab.gss[o * tab.G + lvl];
+        const float scale = tab.scale[o * tab.G + lvl];
+        const float u = (float)(1 << o);
+        s3d_keypoint kp;
+        kp_init(kp, o, lvl, x, y, z, scale);
+        const float sigma = 1.5f * scale;          // ori_sig_fctr, :27,:442
+        const float win_radius = sigma * 3.0f;     // ori_rad_fctr, :28,:915
+        const float r2 = win_radius * win_radius;
+        int xs, xe, y0, y1, z0, z1;
+        window_bounds(kp.x, win_radius / u, nx, xs, xe);
+        window_bounds(kp.y, win_radius / u, ny, y0, y1);
+        window_bounds(kp.z, win_radius / u, nz, z0, z1);
+        const int wxn = xe - xs + 1, wyn = y1 - y0 + 1;
+        const int plane = wxn > 0 && wyn > 0 ? wxn * wyn : 0;
+        const ll ys = nx, zs = (ll)nx * ny;
+        OrientSums S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int zz = z0; zz <= z1; ++zz) {
+            const float dz = ((float)zz - kp.z) * u;
+            for (int tI = lane; tI < plane; tI += 32) {
+                const int yy = y0 + tI / wxn, xx = xs + tI % wxn;
+                const float dx = ((float)xx - kp.x) * u, dy = ((float)yy - kp.y) * u;
+                orient_voxel(g, (ll)xx + (ll)yy * ys + (ll)zz * zs, ys, zs, dx, dy, dz, u, sigma, r2, S);
+            }
+        }
+        float* sp = reinterpret_cast<float*>(&S);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            float v = sp[k];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            sp[k] = v;
+        }
+        float margin;
+        const int code = orient_finish(S, kp, max_eig, corner, &margin);
+        if (lane == 0) {
+            if (code < 1) kp.x = kp.y = kp.z = -1.0f;  // :446-450
+            out[ci] = kp;
+            codes[ci] = code;
+            margins[ci] = margin;
+            xyz5[5 * ci + 0] = x; xyz5[5 * ci + 1] = y; xyz5[5 * ci + 2] = z; xyz5[5 * ci + 3] = o; xyz5[5 * ci + 4] = lvl;
+        }
+    }
+}
+
+// Exact serial re-evaluation (one thread per flagged detection) in the reference's own loop order
+// z, y, x with FP32 accumulation (Src/cSIFT3D.cc:958-998), so near-threshold accept/reject
+// decisions follow the reference's rounding instead of the warp-parallel tree's.
+__global__ void __launch_bounds__(64) orient_exact_kernel(const Cand* __restrict__ cand, int ncand, LevelTable tab,
+                                                          s3d_keypoint* __restrict__ out, int* __restrict__ codes,
+                                                          const float* __restrict__ margins, float recheck_margin,
+                                                          float max_eig, float corner, int* n_rechecked, int* n_flipped) {
+    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ci >= ncand) return;
+    if (!(margins[ci] < recheck_margin)) return;
+    int o, lvl, x, y, z;
+    cand_decode(cand[ci], tab, o, lvl, x, y, z);
+    const int nx = tab.dims[o][0], ny = tab.dims[o][1], nz = tab.dims[o][2];
+    const float* g = tab.gss[o * tab.G + lvl];
+    const float scale = tab.scale[o * tab.G + lvl];
+    const float u = (float)(1 << o);
+    s3d_keypoint kp;
+    kp_init(kp, o, lvl, x, y, z, scale);
+    const float sigma = 1.5f * scale;
+    const float win_radius = sigma * 3.0f;
+    const float r2 = win_radius * win_radius;
+    int xs, xe, y0, y1, z0, z1;
+    window_bounds(kp.x, win_radius / u, nx, xs, xe);
+    window_bounds(kp.y, win_radius / u, ny, y0, y1);
+    window_bounds(kp.z, win_radius / u, nz, z0, z1);
+    const ll ys = nx, zs = (ll)nx * ny;
+    OrientSums S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int zz = z0; zz <= z1; ++zz)
+        for (int yy = y0; yy <= y1; ++yy)
+            for (int xx = xs; xx <= xe; ++xx) {
+                const float dx = ((float)xx - kp.x) * u, dy = ((float)yy - kp.y) * u, dz = ((float)zz - kp.z) * u;
+                orient_voxel(g, (ll)xx + (ll)yy * ys + (ll)zz * zs, ys, zs, dx, dy, dz, u, sigma, r2, S);
+            }
+    const int code = orient_finish(S, kp, max_eig, corner, nullptr);
+    if (code < 1) kp.x = kp.y = kp.z = -1.0f;
+    atomicAdd(n_rechecked, 1);
+    if (code != codes[ci]) atomicAdd(n_flipped, 1);
+    out[ci] = kp;
+    codes[ci] = code;
+}
+
+// Ordered compaction of the survivors (serial loop Src/cSIFT3D.cc:459-466): one CTA.
+__global__ void __launch_bounds__(1024) survivors_kernel(const int* __restrict__ codes, int n, int* __restrict__ surv,
+                                                         int* total_out) {
+    __shared__ int part[1024];
+    const int per = (n + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += codes[i] == 1;
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;
+    for (int i = b; i < e; ++i)
+        if (codes[i] == 1) surv[run++] = i;
+    if (threadIdx.x == 1023) *total_out = part[1023];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6  Descriptor.  Extract_Descriptor_Imp Src/cSIFT3D.cc:1152-1381 +
+//     Trilinear_interpolation_over_desc_debug :1450-1540 + Check_intersect_faces :1542-1573 +
+//     cart2bary :1592-1637 + normailize_desc :1639-1656.
+// ---------------------------------------------------------------------------------------------
+struct MeshConst {
+    float e1[20][3], e2[20][3], t[20][3], q[20][3];  // per face: V1-V0, V2-V0, -V0, t x e1
+    float qe2[20];                                   // q . e2
+    int idx[20][3];                                  // vertex ids (NOT swapped, App. B Q13)
+};
+
+// cart2bary for one face, Src/cSIFT3D.cc:1592-1637, with the face-only terms precomputed on the
+// host in the same FP32 arithmetic.  Returns false for |det| < bary_eps.
+__device__ __forceinline__ bool face_bary(const MeshConst& M, int f, float gx, float gy, float gz, float bary_eps,
+                                          float& b0, float& b1, float& b2, float& k) {
+    const float e2x = M.e2[f][0], e2y = M.e2[f][1], e2z = M.e2[f][2];
+    const float px = gy * e2z - gz * e2y;
+    const float py = gz * e2x - gx * e2z;
+    const float pz = gx * e2y - gy * e2x;
+    const float det = M.e1[f][0] * px + M.e1[f][1] * py + M.e1[f][2] * pz;
+    if (fabsf(det) < bary_eps) return false;
+    const float det_inv = (float)(1.0 / (double)det);
+    b1 = det_inv * (px * M.t[f][0] + py * M.t[f][1] + pz * M.t[f][2]);
+    b2 = det_inv * (gx * M.q[f][0] + gy * M.q[f][1] + gz * M.q[f][2]);
+    b0 = 1 - b1 - b2;
+    k = det_inv * M.qe2[f];
+    return true;
+}
+
+constexpr int kDescWarps = 8;
+
+__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_keypoint* __restrict__ extre,
+                                                                   const int* __restrict__ surv, int nkp, LevelTable tab,
+                                                                   const MeshConst* __restrict__ meshp,
+                                                                   s3d_keypoint* __restrict__ kps_out,
+                                                                   float* __restrict__ desc_out) {
+    __shared__ float hist[kDescWarps][S3D_DESC_LEN];
+    __shared__ MeshConst M;
+    __shared__ s3d_keypoint kp;
+    __shared__ float red[kDescWarps];
+    const int k = blockIdx.x;
+    if (k >= nkp) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    {
+        const int* src = reinterpret_cast<const int*>(extre + surv[k]);
+        int* dstp = reinterpret_cast<int*>(&kp);
+        for (int i = tid; i < (int)(sizeof(s3d_keypoint) / 4); i += blockDim.x) dstp[i] = src[i];
+        const int* ms = reinterpret_cast<const int*>(meshp);
+        int* md = reinterpret_cast<int*>(&M);
+        for (int i = tid; i < (int)(sizeof(MeshConst) / 4); i += blockDim.x) md[i] = ms[i];
+        for (int i = tid; i < kDescWarps * S3D_DESC_LEN; i += blockDim.x) (&hist[0][0])[i] = 0.0f;
+    }
+    __syncthreads();
+    const int o = kp.octave, lvl = kp.level;
+    const int nx = tab.dims[o][0], ny = tab.dims[o][1], nz = tab.dims[o][2];
+    const float* g = tab.gss[o * tab.G + lvl];
+    const float u = (float)(1 << o);
+    const float bary_eps = (float)(FLT_EPSILON * 1E1);          // :23
+    const float sigma = kp.scale * 7.071067812f;                // desc_sig_fctr :30,:1155
+    const float win_radius = 2.0f * sigma;                      // desc_rad_fctr :31,:1156
+    const float desc_hw = (float)((double)win_radius / sqrt(2.0));
+    const float desc_width = 2.0f * desc_hw;
+    const float desc_bin_fctr = 4.0f / desc_width;
+    const float r2 = win_radius * win_radius;
+    const float s2 = sigma * sigma;
+    const float cx = kp.x, cy = kp.y, cz = kp.z;
+    // Transpose_Matrix(kp.Rotation) :1214 — R below is the transpose (App. B Q11)
+    const float R0 = kp.Rotation[0], R1 = kp.Rotation[3], R2 = kp.Rotation[6];
+    const float R3 = kp.Rotation[1], R4 = kp.Rotation[4], R5 = kp.Rotation[7];
+    const float R6 = kp.Rotation[2], R7 = kp.Rotation[5], R8 = kp.Rotation[8];
+    int xs, xe, y0, y1, z0, z1;
+    window_bounds(cx, win_radius / u, nx, xs, xe);
+    window_bounds(cy, win_radius / u, ny, y0, y1);
+    window_bounds(cz, win_radius / u, nz, z0, z1);
+    const int wyn = y1 - y0 + 1, wzn = z1 - z0 + 1;
+    const int nrows = (wyn > 0 && wzn > 0) ? wyn * wzn : 0;
+    const ll ys = nx, zs = (ll)nx * ny;
+    float* myh = hist[wid];
+    const float iu = 1.0f / u;
+
+    for (int r = wid; r < nrows; r += kDescWarps) {
+        const int yy = y0 + r % wyn, zz = z0 + r / wyn;
+        const float dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
+        // fl(fl(dx^2+dy^2)+dz^2) >= fl(dy^2+dz^2) by monotonicity of rounding: safe row reject
+        if (dy * dy + dz * dz > r2) continue;
+        for (int xb = xs; xb <= xe; xb += 32) {
+            const int xx = xb + lane;
+            bool contrib = false;
+            float vb0 = 0.f, vb1 = 0.f, vb2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, mag = 0.f;
+            int face = -1;
+            if (xx <= xe) {
+                const float dx = ((float)xx - cx) * u;
+                const float sq = dx * dx + dy * dy + dz * dz;
+                if (!(sq > r2)) {
+                    vb0 = (R0 * dx + R1 * dy + R2 * dz + desc_hw) * desc_bin_fctr;
+                    vb1 = (R3 * dx + R4 * dy + R5 * dz + desc_hw) * desc_bin_fctr;
+                    vb2 = (R6 * dx + R7 * dy + R8 * dz + desc_hw) * desc_bin_fctr;
+                    vb0 -= 0.5f; vb1 -= 0.5f; vb2 -= 0.5f;
+                    if (!(vb0 <= -0.5f || vb1 <= -0.5f || vb2 <= -0.5f || vb0 >= 3.5f || vb1 >= 3.5f || vb2 >= 3.5f)) {
+                        const float weight = s3d_expf_ref(-0.5f * sq / s2);
+                        const ll i = (ll)xx + (ll)yy * ys + (ll)zz * zs;
+                        float gx = (float)(0.5 * (double)(g[i + 1] - g[i - 1]));
+                        float gy = (float)(0.5 * (double)(g[i + ys] - g[i - ys]));
+                        float gz = (float)(0.5 * (double)(g[i + zs] - g[i - zs]));
+                        gx *= iu; gy *= iu; gz *= iu;
+                        gx = gx * weight; gy = gy * weight; gz = gz * weight;  // SIFT3D_CVEC_SCALE :1322
+                        const float rx = R0 * gx + R1 * gy + R2 * gz;
+                        const float ry = R3 * gx + R4 * gy + R5 * gz;
+                        const float rz = R6 * gx + R7 * gy + R8 * gz;
+                        const float n2 = rx * rx + ry * ry + rz * rz;
+                        if (!(n2 < bary_eps)) {  // Check_intersect_faces :1544
+                            for (int f = 0; f < 20; ++f) {
+                                float c0, c1, c2, kk;
+                                if (!face_bary(M, f, rx, ry, rz, bary_eps, c0, c1, c2, kk)) continue;
+                                if (c0 < -bary_eps || c1 < -bary_eps || c2 < -bary_eps || kk < 0) continue;
+                                face = f; b0 = c0; b1 = c1; b2 = c2;
+                                break;
+                            }
+                            if (face >= 0) {
+                                mag = sqrtf(n2);
+                                contrib = true;
+                            }
+                        }
+                    }
+                }
+            }
+            // Phase B: the warp replays each contributing voxel; lane = cell*3 + vertex (24 lanes)
+            unsigned m = __ballot_sync(0xffffffffu, contrib);
+            const int cell = lane / 3, vtx = lane - cell * 3;
+            const int ddx = (cell >> 2) & 1, ddy = (cell >> 1) & 1, ddz = cell & 1;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const float a0 = __shfl_sync(0xffffffffu, vb0, j), a1 = __shfl_sync(0xffffffffu, vb1, j),
+                            a2 = __shfl_sync(0xffffffffu, vb2, j);
+                const float mg = __shfl_sync(0xffffffffu, mag, j);
+                const float c0 = __shfl_sync(0xffffffffu, b0, j), c1 = __shfl_sync(0xffffffffu, b1, j),
+                            c2 = __shfl_sync(0xffffffffu, b2, j);
+                const int f = __shfl_sync(0xffffffffu, face, j);
+                if (lane < 24) {
+                    const int bx = (int)a0 + ddx, by = (int)a1 + ddy, bz = (int)a2 + ddz;  // truncation, Q12
+                    if (!(bx < 0 || by < 0 || bz < 0 || bx >= 4 || by >= 4 || bz >= 4)) {
+                        const float dv0 = a0 - floorf(a0), dv1 = a1 - floorf(a1), dv2 = a2 - floorf(a2);
+                        const double w0 = ddx == 0 ? (1.0 - (double)dv0) : (double)dv0;
+                        const double w1 = ddy == 0 ? (1.0 - (double)dv1) : (double)dv1;
+                        const double w2 = ddz == 0 ? (1.0 - (double)dv2) : (double)dv2;
+                        const float wt = (float)(w0 * w1 * w2);
+                        const float bv = vtx == 0 ? c0 : (vtx == 1 ? c1 : c2);
+                        const int hidx = (bx + by * 4 + bz * 16) * 12 + M.idx[f][vtx];
+                        myh[hidx] += mg * wt * bv;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+    // fixed-order sum over the per-warp histograms, then normalise / clamp / normalise (:1350-1358)
+    float v[3];
+    float ss = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        const int i = tid + e * 256;
+        float a = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kDescWarps; ++w) a += hist[w][i];
+        v[e] = a;
+        ss += a * a;
+    }
+    auto block_sum = [&](float x) -> float {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        __syncthreads();
+        if (lane == 0) red[wid] = x;
+        __syncthreads();
+        float tsum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kDescWarps; ++w) tsum += red[w];
+        return tsum;
+    };
+    float norm = block_sum(ss);
+    norm = (float)((double)sqrtf(norm) + DBL_EPSILON);
+    float norm_inv = (float)(1.0 / (double)norm);
+    const float trunc_thresh = (float)(0.2 * 128 / S3D_DESC_LEN);
+    ss = 0.0f;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        v[e] *= norm_inv;
+        v[e] = v[e] < trunc_thresh ? v[e] : trunc_thresh;
+        ss += v[e] * v[e];
+    }
+    norm = block_sum(ss);
+    norm = (float)((double)sqrtf(norm) + DBL_EPSILON);
+    norm_inv = (float)(1.0 / (double)norm);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) desc_out[(size_t)k * S3D_DESC_LEN + tid + e * 256] = v[e] * norm_inv;
+    if (tid == 0) {
+        s3d_keypoint outk = kp;
+        outk.Rotation[0] = R0; outk.Rotation[1] = R1; outk.Rotation[2] = R2;
+        outk.Rotation[3] = R3; outk.Rotation[4] = R4; outk.Rotation[5] = R5;
+        outk.Rotation[6] = R6; outk.Rotation[7] = R7; outk.Rotation[8] = R8;
+        const float coord_factor = (float)(1 << o);  // pow(2.0, octave) :1161
+        outk.rx = kp.x * coord_factor; outk.ry = kp.y * coord_factor; outk.rz = kp.z * coord_factor;  // :1377-1379
+        outk.desc = nullptr;
+        kps_out[k] = outk;
+    }
+}
+
+// FP-contract self test: with -fmad=false, a*b+c must round twice.
+__global__ void selftest_kernel(float a, float b, float c, float d, float* out) {
+    out[0] = a * b + c;   // must equal fadd(fmul(a,b),c), not fma
+    out[1] = __fadd_rn(__fmul_rn(a, b), c);
+    out[2] = fmaf(a, b, c);
+    out[3] = a / d;
+    out[4] = __fdiv_rn(a, d);
+    out[5] = sqrtf(d);
+    out[6] = __fsqrt_rn(d);
+    out[7] = s3d_expf_ref(-d);
+}
+
+}  // namespace s3d

@@ -1,0 +1,430 @@
+// s3d_match.cu — brute-force descriptor matching (muBruteMatcher, /root/reference/3DSIFT/Src/cMatcher.cc).
+//
+// Exact path: for every query the best / second-best dot product over the database, where a dot
+// product is the reference's own  sum_{i=0..767} (double)(float)(a_i * b_i)  accumulated
+// sequentially in double (KP_squareSum, Src/cMatcher.cc:17-23).  The running top-2 uses the total
+// order (dot desc, index asc), which equals the reference's ascending-j strict-'>' scan
+// (Src/cMatcher.cc:54-70).
+#include <cfloat>
+#include <cstring>
+#include <vector>
+
+#include "s3d_common.h"
+
+namespace s3d {
+
+constexpr int kD = S3D_DESC_LEN;
+
+struct Top2 {
+    double d1, d2;
+    int i1, i2;
+};
+
+__device__ __forceinline__ void top2_init(Top2& t) {
+    t.d1 = (double)FLT_MIN; t.d2 = (double)FLT_MIN;  // Src/cMatcher.cc:54-55
+    t.i1 = -1; t.i2 = -1;
+}
+
+// is (da, ia) ahead of (db, ib) in (dot desc, index asc)?  index -1 = empty slot (never ahead)
+__device__ __forceinline__ bool ahead(double da, int ia, double db, int ib) {
+    if (ia < 0) return false;
+    if (ib < 0) return true;
+    return da > db || (da == db && ia < ib);
+}
+
+// Insert one candidate (s, j).  Candidates with s <= FLT_MIN never enter (strict '>' against the
+// FLT_MIN initial values, Src/cMatcher.cc:60,66).
+__device__ __forceinline__ void top2_push(Top2& t, double s, int j) {
+    if (!(s > (double)FLT_MIN)) return;
+    if (ahead(s, j, t.d1, t.i1)) {
+        t.d2 = t.d1; t.i2 = t.i1;
+        t.d1 = s; t.i1 = j;
+    } else if (ahead(s, j, t.d2, t.i2)) {
+        t.d2 = s; t.i2 = j;
+    }
+}
+
+__device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
+    if (b.i1 >= 0) top2_push(a, b.d1, b.i1);
+    if (b.i2 >= 0) top2_push(a, b.d2, b.i2);
+}
+
+// Exact tile kernel: CTA = 64 queries x 64 database rows per step, 256 threads, each thread owns a
+// 4x4 block of (query, db) pairs (db rows interleaved by 16 to keep shared reads conflict-free) and walks k = 0..767 in order with a k-chunked shared-memory
+// stage, so every pair sees the reference's accumulation order.  Database rows are swept in
+// `db_per_cta`-sized slices (gridDim.y) and merged by top2_merge_kernel.
+constexpr int kTQ = 64, kTD = 64, kTK = 32;
+
+__global__ void __launch_bounds__(256) top2_exact_kernel(const float* __restrict__ q, int nq, const float* __restrict__ db,
+                                                         int nd, int db_offset, const int* __restrict__ mask,
+                                                         int db_per_cta, Top2* __restrict__ part) {
+    __shared__ float sq[kTK][kTQ + 1];
+    __shared__ float sd[kTK][kTD + 1];
+    __shared__ Top2 red[kTQ][16 + 1];
+    const int tid = threadIdx.x;
+    const int tq = tid / 16, td = tid % 16;  // thread owns queries tq*4.., db rows td*4..
+    const int q0 = blockIdx.x * kTQ;
+    const int dbeg = blockIdx.y * db_per_cta, dend = min(nd, dbeg + db_per_cta);
+    Top2 best[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) top2_init(best[a]);
+    for (int d0 = dbeg; d0 < dend; d0 += kTD) {
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int k0 = 0; k0 < kD; k0 += kTK) {
+            __syncthreads();
+            // stage kTK columns of 64 query rows and 64 db rows (transposed: [k][row])
+            for (int e = tid; e < kTQ * kTK; e += 256) {
+                const int row = e / kTK, kk = e % kTK;
+                const int qi = q0 + row, di = d0 + row;
+                sq[kk][row] = qi < nq ? q[(size_t)qi * kD + k0 + kk] : 0.0f;
+                sd[kk][row] = di < dend ? db[(size_t)di * kD + k0 + kk] : 0.0f;
+            }
+            __syncthreads();
+#pragma unroll 4
+            for (int kk = 0; kk < kTK; ++kk) {
+                float av[4], bv[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) av[a] = sq[kk][tq * 4 + a];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) bv[b] = sd[kk][b * 16 + td];
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = __dadd_rn(acc[a][b], (double)__fmul_rn(av[a], bv[b]));
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int di = d0 + b * 16 + td;
+                if (di < dend) top2_push(best[a], acc[a][b], di + db_offset);
+            }
+    }
+    // merge the 16 db-lanes of every query
+#pragma unroll
+    for (int a = 0; a < 4; ++a) red[tq * 4 + a][td] = best[a];
+    __syncthreads();
+    if (tid < kTQ) {
+        Top2 r = red[tid][0];
+        for (int j = 1; j < 16; ++j) top2_merge(r, red[tid][j]);
+        const int qi = q0 + tid;
+        if (qi < nq) {
+            if (mask && mask[qi] == 0) top2_init(r);
+            part[(size_t)blockIdx.y * nq + qi] = r;
+        }
+    }
+}
+
+// Merge `parts` partial lists per query and emit calMatches' outputs (Src/cMatcher.cc:71-77);
+// masked-out queries get gIdx = -1 and nothing else (:48-52).
+__global__ void __launch_bounds__(256) top2_merge_kernel(int parts, int nq, const Top2* __restrict__ part,
+                                                         const int* __restrict__ mask, double* d1o, int* i1o, double* d2o,
+                                                         int* i2o, float* gDist, int* gIdx, float* sDist, int* sIdx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    if (mask && mask[i] == 0) {
+        if (gIdx) gIdx[i] = -1;
+        if (i1o) { i1o[i] = -1; i2o[i] = -1; d1o[i] = (double)FLT_MIN; d2o[i] = (double)FLT_MIN; }
+        return;
+    }
+    Top2 r = part[i];
+    for (int p = 1; p < parts; ++p) top2_merge(r, part[(size_t)p * nq + i]);
+    if (i1o) { d1o[i] = r.d1; i1o[i] = r.i1; d2o[i] = r.d2; i2o[i] = r.i2; }
+    if (gIdx) {
+        gDist[i] = (float)(2 - 2 * r.d1);
+        sDist[i] = (float)(2 - 2 * r.d2);
+        gIdx[i] = r.i1;
+        sIdx[i] = r.i2;
+    }
+}
+
+// Merge across shards given as separate arrays laid out [part][nq] (multi-GPU gather).
+__global__ void __launch_bounds__(256) top2_merge_arrays_kernel(int parts, int nq, const double* __restrict__ d1,
+                                                                const int* __restrict__ i1, const double* __restrict__ d2,
+                                                                const int* __restrict__ i2, const int* __restrict__ mask,
+                                                                float* gDist, int* gIdx, float* sDist, int* sIdx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    if (mask && mask[i] == 0) {
+        gIdx[i] = -1;
+        return;
+    }
+    Top2 r;
+    top2_init(r);
+    for (int p = 0; p < parts; ++p) {
+        const size_t o = (size_t)p * nq + i;
+        if (i1[o] >= 0) top2_push(r, d1[o], i1[o]);
+        if (i2[o] >= 0) top2_push(r, d2[o], i2[o]);
+    }
+    gDist[i] = (float)(2 - 2 * r.d1);
+    sDist[i] = (float)(2 - 2 * r.d2);
+    gIdx[i] = r.i1;
+    sIdx[i] = r.i2;
+}
+
+// filter, Src/cMatcher.cc:81-97: float quotient of squared distances vs double thr^2; idx *= -1
+// (so index 0 cannot be rejected, App. B Q19; NaN keeps the match, Q20).
+__global__ void ratio_filter_kernel(int* gIdx, const float* __restrict__ gDist, const float* __restrict__ sDist, int n,
+                                    double thresSquare) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (gIdx[i] < 0) return;
+    const float d1 = gDist[i], d2 = sDist[i];
+    if ((double)__fdiv_rn(d1, d2) >= thresSquare) gIdx[i] *= -1;
+}
+
+// countMatched, Src/cMatcher.cc:114-120
+__global__ void count_kernel(const int* __restrict__ gIdx, int n_ref, int* counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ref) return;
+    const int idx = gIdx[i];
+    if (idx >= 0) atomicAdd(&counts[idx], 1);
+}
+// toMask, Src/cMatcher.cc:122-131
+__global__ void mask_kernel(int* counts, int n_tar, int thres) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tar) return;
+    counts[i] = counts[i] > thres ? 1 : 0;
+}
+// bijectFilter, Src/cMatcher.cc:133-144
+__global__ void biject_kernel(int* gIdx, int n_ref, const int* __restrict__ mask, const int* __restrict__ gIdx2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ref) return;
+    const int m = gIdx[i];
+    if (m < 0 || mask[m] == 0) return;
+    if (gIdx2[m] != i) gIdx[i] *= -1;
+}
+// toCvec, Src/cMatcher.cc:99-112: ordered compaction of (i, gIdx[i]) for gIdx[i] >= 0 — one CTA.
+__global__ void __launch_bounds__(1024) pairs_kernel(const int* __restrict__ gIdx, int n, int* pair_ref, int* pair_tar,
+                                                     int* n_pairs) {
+    __shared__ int part[1024];
+    const int per = (n + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += gIdx[i] >= 0;
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;
+    for (int i = b; i < e; ++i)
+        if (gIdx[i] >= 0) {
+            pair_ref[run] = i;
+            pair_tar[run] = gIdx[i];
+            ++run;
+        }
+    if (threadIdx.x == 1023) *n_pairs = part[1023];
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// One search direction on device arrays: partial lists + merge.
+static int search_device(const float* d_q, int nq, const float* d_db, int nd, int db_offset, const int* d_mask,
+                         double* d1, int* i1, double* d2, int* i2, float* gDist, int* gIdx, float* sDist, int* sIdx,
+                         cudaStream_t st) {
+    if (nq <= 0) return S3D_OK;
+    // split the database so the grid fills the GPU: ~148*4 CTAs
+    const int qtiles = (nq + kTQ - 1) / kTQ;
+    int parts = std::max(1, std::min((nd + kTD - 1) / kTD, (148 * 4 + qtiles - 1) / qtiles));
+    int db_per_cta = ((nd + parts - 1) / parts + kTD - 1) / kTD * kTD;
+    if (db_per_cta < kTD) db_per_cta = kTD;
+    parts = std::max(1, (nd + db_per_cta - 1) / db_per_cta);
+    Top2* d_part = nullptr;
+    S3D_CUDA(cudaMallocAsync((void**)&d_part, sizeof(Top2) * (size_t)parts * nq, st));
+    dim3 grid(qtiles, parts);
+    S3D_LAUNCH(top2_exact_kernel, grid, 256, 0, st, d_q, nq, d_db, nd, db_offset, d_mask, db_per_cta, d_part);
+    S3D_LAUNCH(top2_merge_kernel, s3d_blocks(nq, 256), 256, 0, st, parts, nq, d_part, d_mask, d1, i1, d2, i2, gDist, gIdx,
+               sDist, sIdx);
+    S3D_CUDA(cudaGetLastError());
+    S3D_CUDA(cudaFreeAsync(d_part, st));
+    return S3D_OK;
+}
+
+}  // namespace s3d
+
+using namespace s3d;
+
+extern "C" {
+
+int s3d_top2_device(const float* d_q, int n_q, const float* d_db, int n_db, int db_offset, const int* d_mask,
+                    double* d_dot1, int* d_idx1, double* d_dot2, int* d_idx2, void* stream) {
+    clear_error();
+    if (!d_q || !d_dot1 || !d_idx1 || !d_dot2 || !d_idx2 || n_q < 0 || n_db < 0) return fail(S3D_ERR_ARG, "bad argument");
+    if (n_db > 0 && !d_db) return fail(S3D_ERR_ARG, "null database");
+    int dev;
+    S3D_TRY(use_device(-1, &dev));
+    return search_device(d_q, n_q, d_db, n_db, db_offset, d_mask, d_dot1, d_idx1, d_dot2, d_idx2, nullptr, nullptr, nullptr,
+                         nullptr, (cudaStream_t)stream);
+}
+
+int s3d_top2_merge_device(int parts, int n_q, const double* d_dot1, const int* d_idx1, const double* d_dot2,
+                          const int* d_idx2, const int* d_mask, float* d_gDist, int* d_gIdx, float* d_sDist, int* d_sIdx,
+                          void* stream) {
+    clear_error();
+    if (parts < 1 || n_q < 0 || !d_dot1 || !d_idx1 || !d_dot2 || !d_idx2 || !d_gDist || !d_gIdx || !d_sDist || !d_sIdx)
+        return fail(S3D_ERR_ARG, "bad argument");
+    if (n_q == 0) return S3D_OK;
+    S3D_LAUNCH(top2_merge_arrays_kernel, s3d_blocks(n_q, 256), 256, 0, (cudaStream_t)stream, parts, n_q, d_dot1, d_idx1,
+               d_dot2, d_idx2, d_mask, d_gDist, d_gIdx, d_sDist, d_sIdx);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+int s3d_ratio_filter_device(int* d_gIdx, const float* d_gDist, const float* d_sDist, int n, double thr, void* stream) {
+    clear_error();
+    if (n <= 0) return S3D_OK;
+    S3D_LAUNCH(ratio_filter_kernel, s3d_blocks(n, 256), 256, 0, (cudaStream_t)stream, d_gIdx, d_gDist, d_sDist, n, thr * thr);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+int s3d_count_mask_device(const int* d_gIdx, int n_ref, int* d_mask, int n_tar, int count_thres, void* stream) {
+    clear_error();
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_tar <= 0) return S3D_OK;
+    S3D_CUDA(cudaMemsetAsync(d_mask, 0, sizeof(int) * n_tar, st));
+    if (n_ref > 0) S3D_LAUNCH(count_kernel, s3d_blocks(n_ref, 256), 256, 0, st, d_gIdx, n_ref, d_mask);
+    S3D_LAUNCH(mask_kernel, s3d_blocks(n_tar, 256), 256, 0, st, d_mask, n_tar, count_thres);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+int s3d_biject_filter_device(int* d_gIdx, int n_ref, const int* d_mask, const int* d_gIdx2, void* stream) {
+    clear_error();
+    if (n_ref <= 0) return S3D_OK;
+    S3D_LAUNCH(biject_kernel, s3d_blocks(n_ref, 256), 256, 0, (cudaStream_t)stream, d_gIdx, n_ref, d_mask, d_gIdx2);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+int s3d_pairs_device(const int* d_gIdx, int n_ref, int* d_pair_ref, int* d_pair_tar, int* d_n_pairs, void* stream) {
+    clear_error();
+    S3D_LAUNCH(pairs_kernel, 1, 1024, 0, (cudaStream_t)stream, d_gIdx, n_ref, d_pair_ref, d_pair_tar, d_n_pairs);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+// bijectMatchBase, Src/cMatcher.cc:146-215, on device arrays.
+int s3d_match_device(int type, const float* d_ref, int n_ref, const float* d_tar, int n_tar, double thr, int* d_gIdx,
+                     float* d_gDist, int* d_sIdx, float* d_sDist, int* d_gIdx2, float* d_gDist2, int* d_sIdx2,
+                     float* d_sDist2, int* d_pair_ref, int* d_pair_tar, int* d_n_pairs, void* stream) {
+    clear_error();
+    if (type < 1 || type > 3) return fail(S3D_ERR_ARG, "match type %d (1 inject, 2 biject, 3 enhanced)", type);
+    if (n_ref < 0 || n_tar < 0) return fail(S3D_ERR_ARG, "negative size");
+    if (!d_gIdx || !d_gDist || !d_sIdx || !d_sDist) return fail(S3D_ERR_ARG, "forward outputs are required");
+    int dev;
+    S3D_TRY(use_device(-1, &dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    // glodenIdx/silverIdx start at -1 (:154-155)
+    if (n_ref > 0) {
+        S3D_LAUNCH(fill_int_kernel, s3d_blocks(n_ref, 256), 256, 0, st, d_gIdx, n_ref, -1);
+        S3D_LAUNCH(fill_int_kernel, s3d_blocks(n_ref, 256), 256, 0, st, d_sIdx, n_ref, -1);
+        S3D_CUDA(cudaMemsetAsync(d_gDist, 0, sizeof(float) * n_ref, st));
+        S3D_CUDA(cudaMemsetAsync(d_sDist, 0, sizeof(float) * n_ref, st));
+    }
+    S3D_TRY(search_device(d_ref, n_ref, d_tar, n_tar, 0, nullptr, nullptr, nullptr, nullptr, nullptr, d_gDist, d_gIdx,
+                          d_sDist, d_sIdx, st));
+    S3D_TRY(s3d_ratio_filter_device(d_gIdx, d_gDist, d_sDist, n_ref, thr, st));
+    if (type != 1) {
+        if (!d_gIdx2 || !d_gDist2 || !d_sIdx2 || !d_sDist2) return fail(S3D_ERR_ARG, "reverse outputs are required");
+        int* d_mask = nullptr;
+        S3D_CUDA(cudaMallocAsync((void**)&d_mask, sizeof(int) * std::max(n_tar, 1), st));
+        if (n_tar > 0) {
+            S3D_LAUNCH(fill_int_kernel, s3d_blocks(n_tar, 256), 256, 0, st, d_gIdx2, n_tar, -1);
+            S3D_LAUNCH(fill_int_kernel, s3d_blocks(n_tar, 256), 256, 0, st, d_sIdx2, n_tar, -1);
+            S3D_CUDA(cudaMemsetAsync(d_gDist2, 0, sizeof(float) * n_tar, st));
+            S3D_CUDA(cudaMemsetAsync(d_sDist2, 0, sizeof(float) * n_tar, st));
+        }
+        S3D_TRY(s3d_count_mask_device(d_gIdx, n_ref, d_mask, n_tar, type == 2 ? 0 : 1, st));
+        S3D_TRY(search_device(d_tar, n_tar, d_ref, n_ref, 0, d_mask, nullptr, nullptr, nullptr, nullptr, d_gDist2, d_gIdx2,
+                              d_sDist2, d_sIdx2, st));
+        S3D_TRY(s3d_ratio_filter_device(d_gIdx2, d_gDist2, d_sDist2, n_tar, thr, st));
+        S3D_TRY(s3d_biject_filter_device(d_gIdx, n_ref, d_mask, d_gIdx2, st));
+        S3D_CUDA(cudaFreeAsync(d_mask, st));
+    }
+    if (d_pair_ref && d_pair_tar && d_n_pairs) S3D_TRY(s3d_pairs_device(d_gIdx, n_ref, d_pair_ref, d_pair_tar, d_n_pairs, st));
+    return S3D_OK;
+}
+
+int s3d_match(int type, const float* ref_desc, int n_ref, const float* tar_desc, int n_tar, double thr, int* gIdx,
+              float* gDist, int* sIdx, float* sDist, int* gIdx2, float* gDist2, int* sIdx2, float* sDist2, int* pair_ref,
+              int* pair_tar, int* n_pairs, double* times3) {
+    clear_error();
+    if (type < 1 || type > 3) return fail(S3D_ERR_ARG, "match type %d (1 inject, 2 biject, 3 enhanced)", type);
+    if (n_ref < 0 || n_tar < 0 || (n_ref > 0 && !ref_desc) || (n_tar > 0 && !tar_desc)) return fail(S3D_ERR_ARG, "bad argument");
+    int dev;
+    S3D_TRY(use_device(-1, &dev));
+    cudaStream_t st;
+    S3D_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    const size_t nr = std::max(n_ref, 1), nt = std::max(n_tar, 1);
+    float *d_ref = nullptr, *d_tar = nullptr, *d_f = nullptr;
+    int* d_i = nullptr;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int rc = S3D_OK;
+    auto body = [&]() -> int {
+        S3D_CUDA(cudaMallocAsync((void**)&d_ref, sizeof(float) * kD * nr, st));
+        S3D_CUDA(cudaMallocAsync((void**)&d_tar, sizeof(float) * kD * nt, st));
+        S3D_CUDA(cudaMallocAsync((void**)&d_f, sizeof(float) * 2 * (nr + nt), st));
+        S3D_CUDA(cudaMallocAsync((void**)&d_i, sizeof(int) * (4 * nr + 2 * nt + 4), st));
+        if (n_ref) S3D_CUDA(cudaMemcpyAsync(d_ref, ref_desc, sizeof(float) * kD * (size_t)n_ref, cudaMemcpyHostToDevice, st));
+        if (n_tar) S3D_CUDA(cudaMemcpyAsync(d_tar, tar_desc, sizeof(float) * kD * (size_t)n_tar, cudaMemcpyHostToDevice, st));
+        float *dg = d_f, *ds = d_f + nr, *dg2 = d_f + 2 * nr, *ds2 = d_f + 2 * nr + nt;
+        int *ig = d_i, *is = d_i + nr, *pr = d_i + 2 * nr, *pt = d_i + 3 * nr, *ig2 = d_i + 4 * nr, *is2 = d_i + 4 * nr + nt,
+            *np = d_i + 4 * nr + 2 * nt;
+        S3D_CUDA(cudaMemsetAsync(np, 0, sizeof(int), st));
+        S3D_CUDA(cudaMemsetAsync(d_f, 0, sizeof(float) * 2 * (nr + nt), st));
+        S3D_CUDA(cudaEventRecord(e0, st));
+        S3D_TRY(s3d_match_device(type, d_ref, n_ref, d_tar, n_tar, thr, ig, dg, is, ds, ig2, dg2, is2, ds2, pr, pt, np, st));
+        S3D_CUDA(cudaEventRecord(e1, st));
+        int h_np = 0;
+        S3D_CUDA(cudaMemcpyAsync(&h_np, np, sizeof(int), cudaMemcpyDeviceToHost, st));
+        auto back = [&](void* h, const void* d, size_t bytes) -> cudaError_t {
+            return (h && bytes) ? cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+        };
+        S3D_CUDA(back(gIdx, ig, sizeof(int) * n_ref));
+        S3D_CUDA(back(sIdx, is, sizeof(int) * n_ref));
+        S3D_CUDA(back(gDist, dg, sizeof(float) * n_ref));
+        S3D_CUDA(back(sDist, ds, sizeof(float) * n_ref));
+        if (type != 1) {
+            S3D_CUDA(back(gIdx2, ig2, sizeof(int) * n_tar));
+            S3D_CUDA(back(sIdx2, is2, sizeof(int) * n_tar));
+            S3D_CUDA(back(gDist2, dg2, sizeof(float) * n_tar));
+            S3D_CUDA(back(sDist2, ds2, sizeof(float) * n_tar));
+        }
+        S3D_CUDA(back(pair_ref, pr, sizeof(int) * n_ref));
+        S3D_CUDA(back(pair_tar, pt, sizeof(int) * n_ref));
+        S3D_CUDA(cudaStreamSynchronize(st));
+        if (n_pairs) *n_pairs = h_np;
+        if (times3) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            times3[0] = times3[2] = ms * 1e-3;
+            times3[1] = 0;
+        }
+        return S3D_OK;
+    };
+    rc = body();
+    void* ptrs[] = {d_ref, d_tar, d_f, d_i};
+    for (void* p : ptrs) if (p) cudaFreeAsync(p, st);
+    cudaStreamSynchronize(st);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+}  // extern "C"

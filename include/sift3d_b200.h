@@ -1,0 +1,185 @@
+/* sift3d_b200.h — C ABI of the B200-native 3DSIFT hot path (libsift3d_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status returns (0 = ok, non-zero =
+ * error; s3d_last_error() gives the message), no exceptions, caller-allocated outputs, opaque
+ * handles.  The C++ façade (include/3dsift/cSIFT3D.h, cMatcher.h) and the Python host mirror
+ * (3dsift_b200/api.py) are thin callers of these entry points.  There is no CPU fallback: every
+ * compute entry point fails with S3D_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to
+ * /root/reference/3DSIFT/).
+ */
+#ifndef SIFT3D_B200_H
+#define SIFT3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define S3D_API __declspec(dllexport)
+#else
+#define S3D_API __attribute__((visibility("default")))
+#endif
+
+#define S3D_OK 0
+#define S3D_ERR_ARG 1       /* bad argument */
+#define S3D_ERR_CUDA 2      /* CUDA runtime / no device */
+#define S3D_ERR_CAPACITY 3  /* an internal candidate buffer overflowed */
+#define S3D_ERR_STATE 4     /* call order (e.g. get before run) */
+
+#define S3D_DESC_LEN 768    /* Include/cMatcher.h:8 DESC_LENGTH, Include/cSIFT3D.h:27 DESC_NUMEL */
+#define S3D_KP_BYTES 176    /* sizeof(CPUSIFT::Keypoint), Include/cSIFT3D.h:52-70 */
+
+/* Keypoint record written by s3d_get_keypoints / s3d_get_extrema: byte-identical to
+ * CPUSIFT::Keypoint (Include/cSIFT3D.h:52-70).  `desc` is written as NULL; the caller owns the
+ * descriptor buffer and patches the pointer (the façade does). */
+typedef struct s3d_keypoint {
+    float x, y, z;
+    float scale;
+    int octave, level;
+    float rx, ry, rz;
+    float win[3];
+    float eigvalue[3];
+    float eigvector[9];
+    float Rotation[9];
+    float str_tensor[9];
+    float* desc;
+} s3d_keypoint;
+
+/* Constructor parameters: the default arguments of CSIFT3DFactory::CreateCSIFT3D
+ * (Include/cSIFT3D.h:187-202; defaults Include/cSIFT3D.h:13-21). */
+typedef struct s3d_params {
+    int num_kp_levels;     /* 3    */
+    float sigma_default;   /* 1.6  */
+    float sigma_n_default; /* 1.15 */
+    float peak_thresh;     /* 0.1  */
+    float max_eig_thres;   /* 0.9  */
+    float corner_thresh;   /* 0.4  */
+    int device;            /* CUDA device ordinal; -1 = current device */
+    int keep_levels;       /* 1 = keep the pyramids after s3d_run (== building the reference with
+                              CHECK_ENABLE, Src/cSIFT3D.cc:223-225) so s3d_get_level works */
+    int exact_recheck;     /* 1 = re-evaluate orientation candidates whose accept/reject tests are
+                              within a small margin in the reference's serial FP32 order */
+    int reserved;
+} s3d_params;
+
+typedef struct s3d_ctx* s3d_handle;
+
+/* ---- library ------------------------------------------------------------------------------ */
+S3D_API int s3d_version(void);
+S3D_API const char* s3d_last_error(void);
+/* Number of usable sm_100 devices (0 when none: every compute call will fail). */
+S3D_API int s3d_device_count(void);
+/* Checks on the device that FP32 a*b+c is NOT contracted and that division/sqrt are IEEE
+ * (the bit-exact contract of the dense stages).  0 = ok. */
+S3D_API int s3d_selftest(int device);
+S3D_API void s3d_default_params(s3d_params* p);
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+S3D_API uint64_t s3d_launch_count(void);
+
+/* ---- extraction --------------------------------------------------------------------------- */
+/* CSIFT3DFactory::CreateCSIFT3D(float*, nx, ny, nz, ...)  Src/cSIFT3D.cc:103-110 → ctor :146-163
+ * (copy the caller's volume, divide by global max|v|: data_scale Src/cUtil.cc:536-564).
+ * `vol` is HOST memory, x fastest (xs=1, ys=nx, zs=nx*ny; Src/Util/cTexImage.cc:28-30); it is
+ * copied and never written.  Pinned host memory is copied asynchronously. */
+S3D_API int s3d_create(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out);
+/* Same, for a volume already resident in device memory (HBM-resident timing, chained pipelines). */
+S3D_API int s3d_create_device(const float* d_vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out);
+/* CSIFT3D::KpSiftAlgorithm()  Src/cSIFT3D.cc:165-235: Initialize, Gaussian scale space, DoG,
+ * detection, orientation, description.  Blocks until the results are on the host side of the
+ * handle (keypoint records + descriptors). */
+S3D_API int s3d_run(s3d_handle h);
+/* Asynchronous halves of s3d_run: enqueue everything on the handle's stream / wait for it. */
+S3D_API int s3d_run_async(s3d_handle h);
+S3D_API int s3d_wait(s3d_handle h);
+/* CSIFT3D::~CSIFT3D  Src/cSIFT3D.cc:140-144 */
+S3D_API void s3d_destroy(s3d_handle h);
+
+/* octave_num  Src/cSIFT3D.cc:254-255 */
+S3D_API int s3d_num_octaves(s3d_handle h, int* n);
+/* dims of an octave (n >> o, Src/cUtil.cc:219-221) */
+S3D_API int s3d_level_dims(s3d_handle h, int octave, int* dims3);
+/* CSIFT3D::GetKeypoints()  Src/cSIFT3D.cc:1686-1688: count, then records (+ K x 768 descriptors;
+ * either pointer may be NULL).  Order = (octave, level, z, y, x) of the surviving detections. */
+S3D_API int s3d_num_keypoints(s3d_handle h, int* n);
+S3D_API int s3d_get_keypoints(s3d_handle h, s3d_keypoint* kp, float* desc);
+/* The raw detections after orientation (`extre`, Src/cSIFT3D.cc:410,427-456): records carry
+ * str_tensor / win / eigvalue / eigvector, rejected ones x=y=z=-1; codes[i] in {1,-1,-2,-3}
+ * (RET, Src/cSIFT3D.cc:445).  xyz5 (may be NULL) receives the integer x,y,z,octave,level of every
+ * detection — the bit-exact detection mask (level_extrema, Src/cSIFT3D.cc:412,419). */
+S3D_API int s3d_num_extrema(s3d_handle h, int* n);
+S3D_API int s3d_get_extrema(s3d_handle h, s3d_keypoint* kp, int* codes, int* xyz5);
+/* GET_GSS() / GET_DOG()  Include/cSIFT3D.h:169-174.  which: 0 = Gaussian level idx (o*(L+3)+i),
+ * 1 = DoG level idx (o*(L+2)+i).  Needs keep_levels. */
+S3D_API int s3d_get_level(s3d_handle h, int which, int idx, float* out);
+/* The normalised input (Host_Im after data_scale, Src/cSIFT3D.cc:162). */
+S3D_API int s3d_get_input(s3d_handle h, float* out);
+/* Per-level detection thresholds peak_thresh*max|DoG| (Src/cSIFT3D.cc:384-385), o*L + (i-1). */
+S3D_API int s3d_get_thresholds(s3d_handle h, float* out, int n);
+/* SIFT_TimerPara m_timer  Include/Util/common.h:22-41, filled Src/cSIFT3D.cc:228-233:
+ * t[0]=alloc t[1]=gss t[2]=dog t[3]=detect t[4]=orient t[5]=describe t[6]=release t[7]=total
+ * (seconds, from CUDA events on the handle's stream; t[8]=h2d, t[9]=d2h). */
+S3D_API int s3d_get_timers(s3d_handle h, double* t10);
+
+/* ---- free kernels (parity hooks ≙ Include/cSIFT3D.h:208-239) ------------------------------- */
+/* GaussianSmooth_3D  Src/cSIFT3D.cc:535-622 (host buffers in/out). */
+S3D_API int s3d_gaussian_smooth(const float* src, int nx, int ny, int nz, float sigma, float* dst);
+/* One separable pass (GaussianSmooth_3D_Imp, Src/cSIFT3D.cc:624-790) along axis 0/1/2 with the
+ * given taps; variant 0 = generic kernel, 1 = fast (vector / marching) kernel when eligible. */
+S3D_API int s3d_blur_axis(const float* src, int nx, int ny, int nz, int axis, const float* w, int hw,
+                          int variant, float* dst);
+/* DownSample_3D  Src/cSIFT3D.cc:506-533 */
+S3D_API int s3d_downsample(const float* src, int nx, int ny, int nz, float* dst);
+
+/* ---- matching ------------------------------------------------------------------------------ */
+/* muBruteMatcher::injectMatch / bijectMatch / enhancedMatch  Src/cMatcher.cc:218-228 →
+ * bijectMatchBase :146-215.  type: 1 inject, 2 biject, 3 enhanced (Include/cMatcher.h:14-18).
+ * ref_desc / tar_desc: HOST, row-major n x 768 (the façade gathers Keypoint::desc).
+ * Outputs (HOST, caller-allocated, any may be NULL):
+ *   gIdx,gDist,sIdx,sDist   length n_ref: glodenIdx (post-filter: rejected = negated,
+ *                            Src/cMatcher.cc:92-94,141-142), glodenDistSquare, silverIdx,
+ *                            silverDistSquare (Src/cMatcher.cc:71-77)
+ *   gIdx2,gDist2,sIdx2,sDist2 length n_tar: the reverse (masked) search
+ *   pair_ref,pair_tar       length n_ref: matched index pairs in ascending ref order
+ *                            (toCvec, Src/cMatcher.cc:99-112); *n_pairs = count
+ *   times3                  matchTime, revMatchTime, totalTime (seconds)
+ */
+S3D_API int s3d_match(int type, const float* ref_desc, int n_ref, const float* tar_desc, int n_tar, double thr,
+                      int* gIdx, float* gDist, int* sIdx, float* sDist, int* gIdx2, float* gDist2, int* sIdx2,
+                      float* sDist2, int* pair_ref, int* pair_tar, int* n_pairs, double* times3);
+/* Same with DEVICE-resident descriptor sets and DEVICE outputs (HBM-resident timing; the
+ * extract→match handoff of SURVEY.md §8f-1).  stream is a cudaStream_t (0 = default). */
+S3D_API int s3d_match_device(int type, const float* d_ref, int n_ref, const float* d_tar, int n_tar, double thr,
+                             int* d_gIdx, float* d_gDist, int* d_sIdx, float* d_sDist, int* d_gIdx2,
+                             float* d_gDist2, int* d_sIdx2, float* d_sDist2, int* d_pair_ref, int* d_pair_tar,
+                             int* d_n_pairs, void* stream);
+/* calMatches (Src/cMatcher.cc:40-79) over ONE shard of the database: per query the best and
+ * second-best (dot, global index) over db rows [0, n_db) reported as index + db_offset; dots are
+ * the reference's double sums (KP_squareSum :17-23).  mask (may be NULL): queries with 0 are
+ * skipped (idx = -1).  All pointers DEVICE.  Used for multi-GPU sharding. */
+S3D_API int s3d_top2_device(const float* d_q, int n_q, const float* d_db, int n_db, int db_offset,
+                            const int* d_mask, double* d_dot1, int* d_idx1, double* d_dot2, int* d_idx2,
+                            void* stream);
+/* Merge `parts` partial top-2 lists (each n_q long, laid out [part][n_q]) under the total order
+ * (dot desc, index asc) — equal to the reference's sequential strict-'>' scan — and emit the
+ * distances 2-2*dot and indices of calMatches (Src/cMatcher.cc:71-77).  DEVICE pointers. */
+S3D_API int s3d_top2_merge_device(int parts, int n_q, const double* d_dot1, const int* d_idx1,
+                                  const double* d_dot2, const int* d_idx2, const int* d_mask, float* d_gDist,
+                                  int* d_gIdx, float* d_sDist, int* d_sIdx, void* stream);
+/* filter / countMatched+toMask / bijectFilter / toCvec (Src/cMatcher.cc:81-144) on DEVICE arrays. */
+S3D_API int s3d_ratio_filter_device(int* d_gIdx, const float* d_gDist, const float* d_sDist, int n, double thr,
+                                    void* stream);
+S3D_API int s3d_count_mask_device(const int* d_gIdx, int n_ref, int* d_mask, int n_tar, int count_thres,
+                                  void* stream);
+S3D_API int s3d_biject_filter_device(int* d_gIdx, int n_ref, const int* d_mask, const int* d_gIdx2, void* stream);
+S3D_API int s3d_pairs_device(const int* d_gIdx, int n_ref, int* d_pair_ref, int* d_pair_tar, int* d_n_pairs,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIFT3D_B200_H */
