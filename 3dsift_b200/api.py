@@ -41,7 +41,8 @@ class S3DError(RuntimeError):
 class s3d_params(C.Structure):
     _fields_ = [("num_kp_levels", C.c_int), ("sigma_default", C.c_float), ("sigma_n_default", C.c_float),
                 ("peak_thresh", C.c_float), ("max_eig_thres", C.c_float), ("corner_thresh", C.c_float),
-                ("device", C.c_int), ("keep_levels", C.c_int), ("exact_recheck", C.c_int), ("reserved", C.c_int)]
+                ("device", C.c_int), ("keep_levels", C.c_int), ("exact_recheck", C.c_int), ("profile", C.c_int),
+                ("stream", C.c_void_p)]
 
 
 _lib = None
@@ -77,6 +78,9 @@ def lib():
     L.s3d_get_input.argtypes = [vp, fp]
     L.s3d_get_thresholds.argtypes = [vp, fp, C.c_int]
     L.s3d_get_timers.argtypes = [vp, C.POINTER(C.c_double * 10)]
+    L.s3d_get_kernel_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_int), vp, vp, vp]
+    L.s3d_kernel_class_name.argtypes = [C.c_int]
+    L.s3d_kernel_class_name.restype = C.c_char_p
     L.s3d_gaussian_smooth.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_float, fp]
     L.s3d_blur_axis.argtypes = [fp, C.c_int, C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, fp]
     L.s3d_downsample.argtypes = [fp, C.c_int, C.c_int, C.c_int, fp]
@@ -133,7 +137,7 @@ class CSIFT3D:
     def __init__(self, volume, x_dim=None, y_dim=None, z_dim=None, num_kp_levels=NUM_KP_LEVELS,
                  sigma_default=SIGMA_DEFAULT, sigma_n_default=SIGMA_N_DEFAULT, peak_thresh=PEAK_THRESH,
                  max_eig_thres=EIG_THRES, corner_thresh=CORNER_THRESH, *, device=-1, keep_levels=False,
-                 exact_recheck=True):
+                 exact_recheck=True, profile=False, stream=None):
         L = lib()
         self._h = C.c_void_p()
         p = s3d_params()
@@ -141,6 +145,8 @@ class CSIFT3D:
         p.num_kp_levels, p.sigma_default, p.sigma_n_default = num_kp_levels, sigma_default, sigma_n_default
         p.peak_thresh, p.max_eig_thres, p.corner_thresh = peak_thresh, max_eig_thres, corner_thresh
         p.device, p.keep_levels, p.exact_recheck = device, int(keep_levels), int(exact_recheck)
+        p.profile = int(profile)
+        p.stream = C.c_void_p(int(stream)) if stream else None
         self.num_kp_levels = num_kp_levels
         on_device = hasattr(volume, "is_cuda") and volume.is_cuda
         if isinstance(volume, np.ndarray):
@@ -251,6 +257,15 @@ class CSIFT3D:
         names = ["d_Allocation", "d_BuildGSS", "d_BuildDOG", "d_Detect", "d_AssignOrientation", "d_Extraction",
                  "d_release", "d_TotalTime", "d_h2d", "d_d2h"]
         return dict(zip(names, list(t)))
+
+    def kernel_stats(self):
+        """{class name: dict(ms, launches, alg_bytes)} of the last run (needs profile=True)."""
+        cap = 32
+        n = C.c_int()
+        ms = np.zeros(cap, np.float64); cnt = np.zeros(cap, np.int64); by = np.zeros(cap, np.float64)
+        check(lib().s3d_get_kernel_stats(self._h, cap, C.byref(n), _ptr(ms), _ptr(cnt), _ptr(by)))
+        return {lib().s3d_kernel_class_name(i).decode(): dict(ms=float(ms[i]), launches=int(cnt[i]), alg_bytes=float(by[i]))
+                for i in range(n.value) if cnt[i]}
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -175,6 +175,45 @@ static void launch_march(const float* src, float* dst, int nx, int n, ll st_m, i
     }
 }
 
+// ---- per-kernel-class device timing (params.profile) ---------------------------------------
+enum KCls { K_MAXABS, K_NORMALIZE, K_BLUR_X, K_BLUR_Y, K_BLUR_Z_DOG, K_BLUR_GENERIC, K_DOWNSAMPLE, K_DETECT, K_COMPACT,
+            K_ORIENT, K_ORIENT_EXACT, K_SURVIVORS, K_DESCRIBE, K_NCLS };
+static const char* kClsName[K_NCLS] = {"maxabs", "normalize", "blur_x", "blur_y", "blur_z_dog", "blur_generic", "downsample",
+                                       "detect", "compact", "orient", "orient_exact", "survivors", "describe"};
+struct Prof {
+    bool on = false;
+    cudaStream_t st = nullptr;
+    struct Rec { int cls; cudaEvent_t a, b; double bytes; };
+    std::vector<Rec> recs;
+    double ms[K_NCLS] = {0};
+    long long cnt[K_NCLS] = {0};
+    double bytes[K_NCLS] = {0};
+    void begin(int cls, double by) {
+        if (!on) return;
+        Rec r; r.cls = cls; r.bytes = by;
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, st);
+        recs.push_back(r);
+    }
+    void end() {
+        if (!on) return;
+        cudaEventRecord(recs.back().b, st);
+    }
+    void resolve() {  // after the stream has been synchronised
+        for (auto& r : recs) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; cnt[r.cls]++; bytes[r.cls] += r.bytes; }
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        recs.clear();
+    }
+};
+struct ProfScope {
+    Prof* p;
+    ProfScope(Prof* p_, int cls, double by) : p(p_) { if (p) p->begin(cls, by); }
+    ~ProfScope() { if (p) p->end(); }
+};
+
 #define S3D_HW_SWITCH(hw, CALL)            \
     switch (hw) {                          \
         case 2: CALL(2); break;            \
@@ -189,11 +228,14 @@ static void launch_march(const float* src, float* dst, int nx, int n, ll st_m, i
 // One separable pass.  variant 0 = generic kernel; 1 = fast kernels when eligible.
 // prev/dog/slot non-null fuses the DoG subtraction + max|DoG| (only meaningful on the last pass).
 static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int axis, const Taps& t, int variant,
-                      const float* prev, float* dog, unsigned* slot, cudaStream_t st) {
+                      const float* prev, float* dog, unsigned* slot, cudaStream_t st, Prof* prof = nullptr) {
     const ll total = (ll)nx * ny * nz;
     const int n = axis == 0 ? nx : (axis == 1 ? ny : nz);
     const bool fast = variant == 1 && (nx % 4 == 0) && supported_fast_hw(t.hw) && n >= 2 * t.hw + 2 && total >= 4096 &&
                       !(axis == 0 && dog);
+    // algorithmic bytes: read src + write dst (+ read prev + write dog on the fused pass)
+    ProfScope ps(prof, !fast ? K_BLUR_GENERIC : (axis == 0 ? K_BLUR_X : (axis == 1 ? K_BLUR_Y : K_BLUR_Z_DOG)),
+                 (dog ? 16.0 : 8.0) * (double)total);
     if (!fast) {
         S3D_LAUNCH(blur_generic_kernel, s3d_blocks((size_t)total, 256), 256, 0, st, src, dst, nx, ny, nz, axis, t, prev,
                    dog, slot);
@@ -223,6 +265,8 @@ struct s3d_ctx {
     s3d_params prm;
     int device = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    Prof prof;
     int nx = 0, ny = 0, nz = 0;
     size_t n0 = 0;
     int noct = 0, G = 0, D = 0, L = 0;
@@ -270,7 +314,14 @@ static int ctx_common_init(s3d_ctx* c, int nx, int ny, int nz, const s3d_params*
     S3D_TRY(use_device(c->prm.device, &c->device));
     c->nx = nx; c->ny = ny; c->nz = nz;
     c->n0 = (size_t)nx * ny * nz;
-    S3D_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (c->prm.stream) {
+        c->stream = (cudaStream_t)c->prm.stream;
+    } else {
+        S3D_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    c->prof.on = c->prm.profile != 0;
+    c->prof.st = c->stream;
     for (int i = 0; i < 8; i++) S3D_CUDA(cudaEventCreate(&c->ev[i]));
     c->ev_ok = true;
     return S3D_OK;
@@ -282,8 +333,14 @@ static int ctx_normalize(s3d_ctx* c, const float* d_raw) {
     S3D_CUDA(cudaMallocAsync((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
     S3D_CUDA(cudaMemsetAsync(c->d_slots, 0, 256 * sizeof(unsigned), c->stream));
     const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks(c->n0 / 4 + 1, 256), 148 * 16);
-    S3D_LAUNCH(maxabs_kernel, grid, 256, 0, c->stream, d_raw, c->n0, c->d_slots);
-    S3D_LAUNCH(normalize_kernel, grid, 256, 0, c->stream, d_raw, c->d_input, c->n0, c->d_slots);
+    {
+        ProfScope ps(&c->prof, K_MAXABS, 4.0 * c->n0);
+        S3D_LAUNCH(maxabs_kernel, grid, 256, 0, c->stream, d_raw, c->n0, c->d_slots);
+    }
+    {
+        ProfScope ps(&c->prof, K_NORMALIZE, 8.0 * c->n0);
+        S3D_LAUNCH(normalize_kernel, grid, 256, 0, c->stream, d_raw, c->d_input, c->n0, c->d_slots);
+    }
     S3D_CUDA(cudaGetLastError());
     return S3D_OK;
 }
@@ -315,7 +372,8 @@ void s3d_default_params(s3d_params* p) {
     p->device = -1;
     p->keep_levels = 0;
     p->exact_recheck = 1;
-    p->reserved = 0;
+    p->profile = 0;
+    p->stream = nullptr;
 }
 
 int s3d_selftest(int device) {
@@ -390,8 +448,9 @@ void s3d_destroy(s3d_handle c) {
         void* ptrs[] = {c->d_input, c->d_slots, c->d_thres, c->d_mesh, c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc};
         for (void* q : ptrs) if (q) cudaFreeAsync(q, c->stream);
         cudaStreamSynchronize(c->stream);
+        c->prof.resolve();
         if (c->ev_ok) for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
-        cudaStreamDestroy(c->stream);
+        if (c->own_stream) cudaStreamDestroy(c->stream);
     }
     delete c;
 }
@@ -448,6 +507,7 @@ static int run_impl(s3d_ctx* c) {
             float* dst = c->gss[o * G + i];
             if (i == 0 && o > 0) {
                 // octave seed = even-index decimation of level L of the previous octave (:311)
+                ProfScope ps(&c->prof, K_DOWNSAMPLE, 8.0 * c->nvox[o]);
                 S3D_LAUNCH(downsample_kernel, s3d_blocks(c->nvox[o], 256), 256, 0, st, c->gss[(o - 1) * G + L],
                            c->dims[o - 1][0], c->dims[o - 1][1], dst, nx, ny, nz);
                 continue;
@@ -455,12 +515,13 @@ static int run_impl(s3d_ctx* c) {
             const float* src = (o == 0 && i == 0) ? c->d_input : c->gss[o * G + i - 1];
             const Taps& t = c->taps[i];
             // X -> Y -> Z (:609-617); the Z pass of level i >= 1 also emits DoG[i-1] = G[i-1] - G[i]
-            blur_pass(src, c->d_tmp[0], nx, ny, nz, 0, t, 1, nullptr, nullptr, nullptr, st);
-            blur_pass(c->d_tmp[0], c->d_tmp[1], nx, ny, nz, 1, t, 1, nullptr, nullptr, nullptr, st);
+            blur_pass(src, c->d_tmp[0], nx, ny, nz, 0, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
+            blur_pass(c->d_tmp[0], c->d_tmp[1], nx, ny, nz, 1, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
             if (i >= 1)
-                blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, src, c->dog[o * D + i - 1], c->d_slots + 1 + o * D + i - 1, st);
+                blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, src, c->dog[o * D + i - 1], c->d_slots + 1 + o * D + i - 1, st,
+                          &c->prof);
             else
-                blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, nullptr, nullptr, nullptr, st);
+                blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
         }
     }
     S3D_CUDA(cudaGetLastError());
@@ -487,12 +548,16 @@ static int run_impl(s3d_ctx* c) {
     for (int o = 0; o < c->noct; o++)
         for (int j = 1; j <= L; j++) {
             const int unit = o * L + (j - 1);
+            ProfScope ps(&c->prof, K_DETECT, 4.0 * c->nvox[o]);
             S3D_LAUNCH(detect_kernel, s3d_blocks(c->nvox[o], kDetectChunk), 256, 0, st, c->dog[o * D + j - 1],
                        c->dog[o * D + j], c->dog[o * D + j + 1], c->dims[o][0], c->dims[o][1], c->dims[o][2],
                        c->d_slots + 1 + o * D + j, c->prm.peak_thresh, (uint32_t)unit, gb_base[unit], d_blk_cnt, d_stage,
                        d_stage_count, stage_cap, c->d_thres + unit);
         }
-    S3D_LAUNCH(scan_kernel, 1, 1024, 0, st, d_blk_cnt, d_blk_off, nblk, d_total);
+    {
+        ProfScope ps(&c->prof, K_COMPACT, 8.0 * nblk);
+        S3D_LAUNCH(scan_kernel, 1, 1024, 0, st, d_blk_cnt, d_blk_off, nblk, d_total);
+    }
     unsigned h_stage = 0;
     int h_total[4] = {0, 0, 0, 0};
     S3D_CUDA(cudaMemcpyAsync(&h_stage, d_stage_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
@@ -504,6 +569,7 @@ static int run_impl(s3d_ctx* c) {
     const int ne = c->n_extre;
     if (ne > 0) {
         S3D_CUDA(cudaMallocAsync((void**)&d_cand, sizeof(Cand) * (size_t)ne, st));
+        ProfScope ps(&c->prof, K_COMPACT, 24.0 * ne);
         S3D_LAUNCH(scatter_kernel, s3d_blocks(ne, 256), 256, 0, st, d_stage, d_stage_count, stage_cap, d_blk_off, d_cand);
     }
     S3D_CUDA(cudaEventRecord(c->ev[3], st));
@@ -529,13 +595,20 @@ static int run_impl(s3d_ctx* c) {
     S3D_CUDA(cudaMallocAsync((void**)&d_surv, sizeof(int) * nea, st));
     if (ne > 0) {
         const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks((size_t)ne * 32, 256), 148 * 32);
-        S3D_LAUNCH(orient_kernel, grid, 256, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes, c->d_xyz5, d_margins,
-                   c->prm.max_eig_thres, c->prm.corner_thresh);
+        {
+            ProfScope ps(&c->prof, K_ORIENT, 200.0 * ne);
+            S3D_LAUNCH(orient_kernel, grid, 256, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes, c->d_xyz5, d_margins,
+                       c->prm.max_eig_thres, c->prm.corner_thresh);
+        }
+        ProfScope ps(&c->prof, K_ORIENT_EXACT, 0.0);
         if (c->prm.exact_recheck)
             S3D_LAUNCH(orient_exact_kernel, s3d_blocks(ne, 64), 64, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes,
                        d_margins, 2e-3f, c->prm.max_eig_thres, c->prm.corner_thresh, d_total + 1, d_total + 2);
     }
-    S3D_LAUNCH(survivors_kernel, 1, 1024, 0, st, c->d_codes, ne, d_surv, d_total + 3);
+    {
+        ProfScope ps(&c->prof, K_SURVIVORS, 8.0 * ne);
+        S3D_LAUNCH(survivors_kernel, 1, 1024, 0, st, c->d_codes, ne, d_surv, d_total + 3);
+    }
     S3D_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
     S3D_CUDA(cudaStreamSynchronize(st));
     c->n_rechecked = h_total[1];
@@ -547,9 +620,11 @@ static int run_impl(s3d_ctx* c) {
     const size_t nka = std::max(c->n_kps, 1);
     S3D_CUDA(cudaMallocAsync((void**)&c->d_kps, sizeof(s3d_keypoint) * nka, st));
     S3D_CUDA(cudaMallocAsync((void**)&c->d_desc, sizeof(float) * S3D_DESC_LEN * nka, st));
-    if (c->n_kps > 0)
+    if (c->n_kps > 0) {
+        ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
         S3D_LAUNCH(describe_kernel, c->n_kps, kDescWarps * 32, 0, st, c->d_extre, d_surv, c->n_kps, tab, c->d_mesh,
                    c->d_kps, c->d_desc);
+    }
     S3D_CUDA(cudaGetLastError());
     S3D_CUDA(cudaEventRecord(c->ev[5], st));
 
@@ -584,6 +659,7 @@ int s3d_wait(s3d_handle c) {
         c->timers[2] = 0.0;  // DoG is fused into the Z pass
         cudaEventElapsedTime(&ms, c->ev[0], c->ev[6]);
         c->timers[7] = ms * 1e-3;
+        c->prof.resolve();
         c->ran = true;
     }
     return S3D_OK;
@@ -692,6 +768,16 @@ int s3d_get_thresholds(s3d_handle c, float* out, int n) {
     S3D_CUDA(cudaStreamSynchronize(c->stream));
     return S3D_OK;
 }
+
+int s3d_get_kernel_stats(s3d_handle c, int cap, int* n_classes, double* ms, long long* launches, double* alg_bytes) {
+    if (!c || !n_classes || !ms || !launches || !alg_bytes) return fail(S3D_ERR_ARG, "null argument");
+    const int n = std::min(cap, (int)K_NCLS);
+    for (int i = 0; i < n; i++) { ms[i] = c->prof.ms[i]; launches[i] = c->prof.cnt[i]; alg_bytes[i] = c->prof.bytes[i]; }
+    *n_classes = n;
+    return S3D_OK;
+}
+
+const char* s3d_kernel_class_name(int cls) { return cls >= 0 && cls < K_NCLS ? kClsName[cls] : ""; }
 
 int s3d_get_timers(s3d_handle c, double* t) {
     if (!c || !t) return fail(S3D_ERR_ARG, "null argument");

@@ -64,7 +64,8 @@ typedef struct s3d_params {
                               CHECK_ENABLE, Src/cSIFT3D.cc:223-225) so s3d_get_level works */
     int exact_recheck;     /* 1 = re-evaluate orientation candidates whose accept/reject tests are
                               within a small margin in the reference's serial FP32 order */
-    int reserved;
+    int profile;           /* 1 = bracket every kernel launch with CUDA events (s3d_get_kernel_stats) */
+    void* stream;          /* cudaStream_t to run on (caller keeps it alive); NULL = a private stream */
 } s3d_params;
 
 typedef struct s3d_ctx* s3d_handle;
@@ -124,6 +125,13 @@ S3D_API int s3d_get_thresholds(s3d_handle h, float* out, int n);
  * t[0]=alloc t[1]=gss t[2]=dog t[3]=detect t[4]=orient t[5]=describe t[6]=release t[7]=total
  * (seconds, from CUDA events on the handle's stream; t[8]=h2d, t[9]=d2h). */
 S3D_API int s3d_get_timers(s3d_handle h, double* t10);
+
+/* Per-kernel-class device times of the last s3d_run (needs params.profile = 1): for class c <
+ * *n_classes, ms[c] = summed CUDA-event time, launches[c], alg_bytes[c] = algorithmic bytes moved
+ * (DESIGN.md states the per-voxel figures).  Arrays hold up to `cap` entries. */
+S3D_API int s3d_get_kernel_stats(s3d_handle h, int cap, int* n_classes, double* ms, long long* launches,
+                                 double* alg_bytes);
+S3D_API const char* s3d_kernel_class_name(int cls);
 
 /* ---- free kernels (parity hooks ≙ Include/cSIFT3D.h:208-239) ------------------------------- */
 /* GaussianSmooth_3D  Src/cSIFT3D.cc:535-622 (host buffers in/out). */
