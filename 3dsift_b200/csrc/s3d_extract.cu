@@ -138,6 +138,7 @@ static void host_mesh(MeshConst* M) {
         q[1] = sub(mul(t[2], e1[0]), mul(t[0], e1[2]));
         q[2] = sub(mul(t[0], e1[1]), mul(t[1], e1[0]));
         M->qe2[i] = add(add(mul(q[0], e2[0]), mul(q[1], e2[1])), mul(q[2], e2[2]));
+        for (int c = 0; c < 3; c++) M->cen[i][c] = v[0][c] + v[1][c] + v[2][c];
     }
 }
 
@@ -147,7 +148,7 @@ template <int HW>
 static void launch_x(const float* src, float* dst, int nx, ll nrows, const Taps& t, ll total, cudaStream_t st) {
     ll threads = nrows * (nx >> 2);
     auto kfn = blur_x_kernel<HW>;
-    S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 256), 256, 0, st, src, dst, nx, nrows, t, total);
+    S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 256), 256, 0, st, src, dst, nx, nrows, t);
 }
 
 static int pick_seg(int nx4, int n_other, int n) {
@@ -167,11 +168,11 @@ static void launch_march(const float* src, float* dst, int nx, int n, ll st_m, i
     if (dog) {
         auto kfn = blur_march_kernel<HW, true>;
         S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 128), 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
-                   total, prev, dog, slot);
+                   prev, dog, slot);
     } else {
         auto kfn = blur_march_kernel<HW, false>;
         S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 128), 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
-                   total, (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr);
+                   (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr);
     }
 }
 
@@ -622,7 +623,12 @@ static int run_impl(s3d_ctx* c) {
     S3D_CUDA(cudaMallocAsync((void**)&c->d_desc, sizeof(float) * S3D_DESC_LEN * nka, st));
     if (c->n_kps > 0) {
         ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
-        S3D_LAUNCH(describe_kernel, c->n_kps, kDescWarps * 32, 0, st, c->d_extre, d_surv, c->n_kps, tab, c->d_mesh,
+        static bool attr_set[64] = {false};
+        if (c->device < 64 && !attr_set[c->device]) {
+            S3D_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmem)));
+            attr_set[c->device] = true;
+        }
+        S3D_LAUNCH(describe_kernel, c->n_kps, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, c->n_kps, tab, c->d_mesh,
                    c->d_kps, c->d_desc);
     }
     S3D_CUDA(cudaGetLastError());

@@ -60,6 +60,43 @@ __device__ __forceinline__ float blur_boundary_one(const float* __restrict__ buf
 
 __device__ __forceinline__ bool blur_is_interior(int p, int n, int hw) { return p >= hw && p <= n - hw - 2; }
 
+// The sample the reference uses for tap coordinate c = q (an integer) of a BOUNDARY output
+// (Src/cSIFT3D.cc:747-764), as a function of q alone: q < 0 mirrors to in[-q] (frac = 0, so
+// 1.0f*in[-q] + 0.0f*in[-q+1] == in[-q]); q >= n-1 is the 0.1/0.9-style blend at
+// c' = 2(n-1) - q - 0.1f; otherwise in[q].  Interior outputs only ever touch 0 <= q <= n-2, where
+// this is in[q] as well, so with n >= 2*hw+2 EVERY output of a line is the plain ordered
+// correlation over this extended line — no divergent boundary path in the fast kernels.
+__device__ __forceinline__ void ext_coord(int q, int n, int& il, float& frac) {
+    if (q < 0) {
+        il = -q; frac = 0.0f;
+    } else if (q >= n - 1) {
+        float c = (float)(2 * (n - 1)) - (float)q - 0.1f;
+        il = (int)c;
+        frac = c - (float)il;
+    } else {
+        il = q; frac = 0.0f;
+    }
+}
+
+__device__ __forceinline__ float ext_sample1(const float* __restrict__ line, ll st, int n, int q) {
+    int il; float frac;
+    ext_coord(q, n, il, frac);
+    if (frac == 0.0f) return line[(ll)il * st];
+    return (1.0f - frac) * line[(ll)il * st] + frac * line[(ll)(il + 1) * st];
+}
+
+__device__ __forceinline__ float4 ext_sample4(const float* __restrict__ col, ll st, int n, int q) {
+    int il; float frac;
+    ext_coord(q, n, il, frac);
+    const float4 lo = *reinterpret_cast<const float4*>(col + (ll)il * st);
+    if (frac == 0.0f) return lo;
+    const float4 hi = *reinterpret_cast<const float4*>(col + (ll)(il + 1) * st);
+    float4 r;
+    r.x = (1.0f - frac) * lo.x + frac * hi.x; r.y = (1.0f - frac) * lo.y + frac * hi.y;
+    r.z = (1.0f - frac) * lo.z + frac * hi.z; r.w = (1.0f - frac) * lo.w + frac * hi.w;
+    return r;
+}
+
 __device__ __forceinline__ void atomic_max_abs(unsigned* slot, float m) {
     // non-negative floats order like their bit patterns
     atomicMax(slot, __float_as_uint(m));
@@ -147,10 +184,10 @@ __global__ void __launch_bounds__(256) blur_generic_kernel(const float* __restri
     }
 }
 
-// X pass, 4 outputs per thread (float4 store).  Requires nx % 4 == 0.
+// X pass, 4 outputs per thread (float4 store).  Requires nx % 4 == 0 and nx >= 2*HW+2.
 template <int HW>
 __global__ void __launch_bounds__(256) blur_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
-                                                     ll nrows, Taps t, ll total) {
+                                                     ll nrows, Taps t) {
     constexpr int PAD = (HW + 3) / 4 * 4;
     constexpr int NV = (2 * PAD + 4) / 4;
     const int nx4 = nx >> 2;
@@ -163,36 +200,41 @@ __global__ void __launch_bounds__(256) blur_x_kernel(const float* __restrict__ s
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
         const int xx = x0 - PAD + 4 * q;
-        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (xx >= 0 && xx < nx) f = *reinterpret_cast<const float4*>(r + xx);
-        v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        if (xx >= 0 && xx + 3 <= nx - 2) {
+            const float4 f = *reinterpret_cast<const float4*>(r + xx);
+            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        } else {
+            // row ends: mirrored / blended samples of the extended line (only the edge threads);
+            // positions farther than HW from the row are never used by any tap
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int qq = xx + e;
+                v[4 * q + e] = (qq >= -HW && qq <= nx - 1 + HW) ? ext_sample1(r, 1, nx, qq) : 0.0f;
+            }
+        }
     }
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const int x = x0 + j;
-        if (blur_is_interior(x, nx, HW)) {
-            float acc = 0.0f;
+        float acc = 0.0f;
 #pragma unroll
-            for (int k = 0; k <= 2 * HW; ++k) acc += t.w[k] * v[PAD + j + HW - k];
-            o[j] = acc;
-        } else {
-            o[j] = blur_boundary_one(src, row * nx, 1, nx, x, t, total);
-        }
+        for (int k = 0; k <= 2 * HW; ++k) acc += t.w[k] * v[PAD + j + HW - k];
+        o[j] = acc;
     }
     *reinterpret_cast<float4*>(dst + row * nx + x0) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // Y / Z pass: each thread owns a float4 column (4 consecutive x) and marches along the axis over
 // a segment, keeping the 2*HW+1 most recent inputs in a register ring (static indices through a
-// (2*HW+1)-way unrolled loop), so every input is loaded once per segment.
-// Requires nx % 4 == 0.  n = length of the marched axis, st = its stride, n_other / st_other =
+// (2*HW+1)-way unrolled loop), so every input is loaded once per segment.  Line ends use the
+// extended-line samples (ext_sample4), so there is no separate boundary path.
+// Requires nx % 4 == 0 and n >= 2*HW+2.  n = length of the marched axis, st = its stride, n_other / st_other =
 // the remaining non-x axis.
 template <int HW, bool DOG>
 __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
                                                          int n, ll st, int n_other, ll st_other, int seg, Taps t,
-                                                         ll total, const float* __restrict__ prev,
-                                                         float* __restrict__ dog, unsigned* maxslot) {
+                                                         const float* __restrict__ prev, float* __restrict__ dog,
+                                                         unsigned* maxslot) {
     constexpr int W = 2 * HW + 1;
     const int nx4 = nx >> 2;
     const int nseg = (n + seg - 1) / seg;
@@ -212,7 +254,7 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict
 #pragma unroll
         for (int r = 0; r < 2 * HW; ++r) {
             const int q = p0 - HW + r;
-            win[r] = (q >= 0 && q < n) ? *reinterpret_cast<const float4*>(col + (ll)q * st) : make_float4(0.f, 0.f, 0.f, 0.f);
+            win[r] = (q >= -HW && q <= n - 1 + HW) ? ext_sample4(col, st, n, q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         win[2 * HW] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int ib = 0; p0 + ib < p1; ib += W) {
@@ -222,22 +264,13 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict
                 if (p < p1) {
                     // newest input p+HW goes to the slot of the oldest one (relative r = ib+j+2HW)
                     const int q = p + HW;
-                    win[(j + 2 * HW) % W] = (q < n) ? *reinterpret_cast<const float4*>(col + (ll)q * st)
-                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 acc;
-                    if (blur_is_interior(p, n, HW)) {
-                        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    win[(j + 2 * HW) % W] = ext_sample4(col, st, n, q);  // q <= n-1+HW always
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                        for (int k = 0; k <= 2 * HW; ++k) {
-                            const float4 v = win[(j + 2 * HW - k) % W];  // input p+HW-k
-                            const float w = t.w[k];
-                            acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
-                        }
-                    } else {
-                        acc.x = blur_boundary_one(src, line0 + 0, st, n, p, t, total);
-                        acc.y = blur_boundary_one(src, line0 + 1, st, n, p, t, total);
-                        acc.z = blur_boundary_one(src, line0 + 2, st, n, p, t, total);
-                        acc.w = blur_boundary_one(src, line0 + 3, st, n, p, t, total);
+                    for (int k = 0; k <= 2 * HW; ++k) {
+                        const float4 v = win[(j + 2 * HW - k) % W];  // extended-line sample p+HW-k
+                        const float w = t.w[k];
+                        acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
                     }
                     const ll oidx = line0 + (ll)p * st;
                     *reinterpret_cast<float4*>(dst + oidx) = acc;
@@ -311,12 +344,26 @@ __global__ void __launch_bounds__(256) detect_kernel(const float* __restrict__ D
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = (base + j < total) ? D0[base + j] : 0.0f;
         }
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) any |= (v[j] > thres || v[j] < -thres);
+        // total < 2^32 (checked at create): 32-bit divisions, once per thread
+        uint32_t x0 = 0, y0 = 0, z0 = 0;
+        if (any) {
+            const uint32_t b = (uint32_t)base, unx = (uint32_t)nx, uny = (uint32_t)ny;
+            const uint32_t tq = b / unx;
+            x0 = b - tq * unx; z0 = tq / uny; y0 = tq - z0 * uny;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const ll i = base + j;
             const float val = v[j];
-            if (i < total && (val > thres || val < -thres)) {
-                const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / zs);
+            if (any && i < total && (val > thres || val < -thres)) {
+                int x = (int)x0 + j, y = (int)y0, z = (int)z0;
+                if (x >= nx) {  // only when nx % 4 != 0: the group straddles a row
+                    x -= nx;
+                    if (++y >= ny) { y = 0; ++z; }
+                }
                 if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
                     const float t0 = Dm[i], t1 = D0[i - 1], t2 = D0[i + 1], t3 = D0[i + ys], t4 = D0[i - ys],
                                 t5 = D0[i + zs], t6 = D0[i - zs], t7 = Dp[i];
@@ -733,6 +780,7 @@ __global__ void __launch_bounds__(1024) survivors_kernel(const int* __restrict__
 struct MeshConst {
     float e1[20][3], e2[20][3], t[20][3], q[20][3];  // per face: V1-V0, V2-V0, -V0, t x e1
     float qe2[20];                                   // q . e2
+    float cen[20][3];                                // V0+V1+V2 (all faces have the same |cen|)
     int idx[20][3];                                  // vertex ids (NOT swapped, App. B Q13)
 };
 
@@ -754,30 +802,79 @@ __device__ __forceinline__ bool face_bary(const MeshConst& M, int f, float gx, f
     return true;
 }
 
-constexpr int kDescWarps = 8;
+// Check_intersect_faces, Src/cSIFT3D.cc:1542-1573: the FIRST face (index order) whose barycentric
+// coordinates are all >= -bary_eps with k >= 0 wins (App. B Q14).
+// Fast path: the faces of a regular icosahedron are the spherical Voronoi cells of their
+// centroids, so the face hit by a direction is argmax_f <cen_f, g>.  If that face's barycentric
+// coordinates are all comfortably positive, no other face can pass the reference's tolerance test
+// and the result (face, bary) is exactly what the sequential scan returns (same FP32 formula for
+// the same face).  Directions within `margin` of an edge/vertex take the reference's scan.
+__device__ __forceinline__ int find_face(const MeshConst& M, float gx, float gy, float gz, float bary_eps, float& b0,
+                                         float& b1, float& b2) {
+    int fs = 0;
+    float best = -FLT_MAX;
+#pragma unroll
+    for (int f = 0; f < 20; ++f) {
+        const float d = M.cen[f][0] * gx + M.cen[f][1] * gy + M.cen[f][2] * gz;
+        if (d > best) { best = d; fs = f; }
+    }
+    float k;
+    const float margin = 1e-4f;
+    if (face_bary(M, fs, gx, gy, gz, bary_eps, b0, b1, b2, k) && b0 > margin && b1 > margin && b2 > margin && k > 0.0f)
+        return fs;
+    for (int f = 0; f < 20; ++f) {
+        float c0, c1, c2, kk;
+        if (!face_bary(M, f, gx, gy, gz, bary_eps, c0, c1, c2, kk)) continue;
+        if (c0 < -bary_eps || c1 < -bary_eps || c2 < -bary_eps || kk < 0) continue;
+        b0 = c0; b1 = c1; b2 = c2;
+        return f;
+    }
+    return -1;
+}
 
+constexpr int kDescWarps = 8;
+constexpr int kHistStride = 776;  // 768 bins + a dump slot for out-of-grid cells, padded
+constexpr int kStagePad = 33;
+
+struct DescSmem {
+    float hist[kDescWarps][kHistStride];
+    float sval[kDescWarps][24][kStagePad];
+    unsigned short saddr[kDescWarps][24][kStagePad];
+    MeshConst M;
+    s3d_keypoint kp;
+    float red[kDescWarps];
+};
+
+// One CTA per surviving keypoint, 8 warps.  Rows (y,z) of the window are dealt round-robin to
+// the warps (static assignment => run-to-run deterministic sums).  Per row the x range is clipped
+// to the sphere chord and the rotated 4x4x4 grid (conservatively, +-1 voxel; the reference's exact
+// per-voxel tests still decide).  Phase A: one lane per voxel computes the reference's per-voxel
+// quantities and stages its 24 (bin, value) contributions (8 trilinear cells x 3 face vertices)
+// in shared memory.  Phase B: the warp replays the contributing voxels one at a time, lane l < 24
+// adding contribution l into the warp-private histogram — plain LDS/FADD/STS, no atomics (shared
+// FP32 atomics are CAS loops on sm_100).  Warp histograms are summed in fixed order at the end.
 __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_keypoint* __restrict__ extre,
                                                                    const int* __restrict__ surv, int nkp, LevelTable tab,
                                                                    const MeshConst* __restrict__ meshp,
                                                                    s3d_keypoint* __restrict__ kps_out,
                                                                    float* __restrict__ desc_out) {
-    __shared__ float hist[kDescWarps][S3D_DESC_LEN];
-    __shared__ MeshConst M;
-    __shared__ s3d_keypoint kp;
-    __shared__ float red[kDescWarps];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DescSmem& S = *reinterpret_cast<DescSmem*>(smem_raw);
     const int k = blockIdx.x;
     if (k >= nkp) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     {
         const int* src = reinterpret_cast<const int*>(extre + surv[k]);
-        int* dstp = reinterpret_cast<int*>(&kp);
+        int* dstp = reinterpret_cast<int*>(&S.kp);
         for (int i = tid; i < (int)(sizeof(s3d_keypoint) / 4); i += blockDim.x) dstp[i] = src[i];
         const int* ms = reinterpret_cast<const int*>(meshp);
-        int* md = reinterpret_cast<int*>(&M);
+        int* md = reinterpret_cast<int*>(&S.M);
         for (int i = tid; i < (int)(sizeof(MeshConst) / 4); i += blockDim.x) md[i] = ms[i];
-        for (int i = tid; i < kDescWarps * S3D_DESC_LEN; i += blockDim.x) (&hist[0][0])[i] = 0.0f;
+        for (int i = tid; i < kDescWarps * kHistStride; i += blockDim.x) (&S.hist[0][0])[i] = 0.0f;
     }
     __syncthreads();
+    const MeshConst& M = S.M;
+    const s3d_keypoint& kp = S.kp;
     const int o = kp.octave, lvl = kp.level;
     const int nx = tab.dims[o][0], ny = tab.dims[o][1], nz = tab.dims[o][2];
     const float* g = tab.gss[o * tab.G + lvl];
@@ -802,26 +899,48 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
     const int wyn = y1 - y0 + 1, wzn = z1 - z0 + 1;
     const int nrows = (wyn > 0 && wzn > 0) ? wyn * wzn : 0;
     const ll ys = nx, zs = (ll)nx * ny;
-    float* myh = hist[wid];
+    float* myh = S.hist[wid];
+    float(*sv)[kStagePad] = S.sval[wid];
+    unsigned short(*sa)[kStagePad] = S.saddr[wid];
     const float iu = 1.0f / u;
+    const float slab = desc_hw * 1.0009765625f + 1e-3f;  // conservative half-width of the rotated grid
 
     for (int r = wid; r < nrows; r += kDescWarps) {
         const int yy = y0 + r % wyn, zz = z0 + r / wyn;
         const float dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
         // fl(fl(dx^2+dy^2)+dz^2) >= fl(dy^2+dz^2) by monotonicity of rounding: safe row reject
-        if (dy * dy + dz * dz > r2) continue;
-        for (int xb = xs; xb <= xe; xb += 32) {
+        const float dyz2 = dy * dy + dz * dz;
+        if (dyz2 > r2) continue;
+        // conservative x interval (in voxels about cx): sphere chord ...
+        float lo = -(sqrtf(r2 - dyz2) * iu), hi = -lo;
+        // ... intersected with the three slabs |R_k . disp| < desc_hw of the rotated grid
+        bool empty = false;
+        {
+            const float a[3] = {R0 * u, R3 * u, R6 * u};
+            const float c[3] = {R1 * dy + R2 * dz, R4 * dy + R5 * dz, R7 * dy + R8 * dz};
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) {
+                if (fabsf(a[kk]) > 1e-6f) {
+                    float t0 = (-slab - c[kk]) / a[kk], t1 = (slab - c[kk]) / a[kk];
+                    if (t0 > t1) { const float tt = t0; t0 = t1; t1 = tt; }
+                    lo = fmaxf(lo, t0); hi = fminf(hi, t1);
+                } else if (fabsf(c[kk]) > slab + 1e-3f * desc_hw) {
+                    empty = true;
+                }
+            }
+        }
+        if (empty || lo > hi + 2.0f) continue;
+        const int xlo = max(xs, (int)floorf(cx + lo) - 1), xhi = min(xe, (int)ceilf(cx + hi) + 1);
+        for (int xb = xlo; xb <= xhi; xb += 32) {
             const int xx = xb + lane;
             bool contrib = false;
-            float vb0 = 0.f, vb1 = 0.f, vb2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, mag = 0.f;
-            int face = -1;
-            if (xx <= xe) {
+            if (xx <= xhi) {
                 const float dx = ((float)xx - cx) * u;
                 const float sq = dx * dx + dy * dy + dz * dz;
                 if (!(sq > r2)) {
-                    vb0 = (R0 * dx + R1 * dy + R2 * dz + desc_hw) * desc_bin_fctr;
-                    vb1 = (R3 * dx + R4 * dy + R5 * dz + desc_hw) * desc_bin_fctr;
-                    vb2 = (R6 * dx + R7 * dy + R8 * dz + desc_hw) * desc_bin_fctr;
+                    float vb0 = (R0 * dx + R1 * dy + R2 * dz + desc_hw) * desc_bin_fctr;
+                    float vb1 = (R3 * dx + R4 * dy + R5 * dz + desc_hw) * desc_bin_fctr;
+                    float vb2 = (R6 * dx + R7 * dy + R8 * dz + desc_hw) * desc_bin_fctr;
                     vb0 -= 0.5f; vb1 -= 0.5f; vb2 -= 0.5f;
                     if (!(vb0 <= -0.5f || vb1 <= -0.5f || vb2 <= -0.5f || vb0 >= 3.5f || vb1 >= 3.5f || vb2 >= 3.5f)) {
                         const float weight = s3d_expf_ref(-0.5f * sq / s2);
@@ -836,46 +955,46 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
                         const float rz = R6 * gx + R7 * gy + R8 * gz;
                         const float n2 = rx * rx + ry * ry + rz * rz;
                         if (!(n2 < bary_eps)) {  // Check_intersect_faces :1544
-                            for (int f = 0; f < 20; ++f) {
-                                float c0, c1, c2, kk;
-                                if (!face_bary(M, f, rx, ry, rz, bary_eps, c0, c1, c2, kk)) continue;
-                                if (c0 < -bary_eps || c1 < -bary_eps || c2 < -bary_eps || kk < 0) continue;
-                                face = f; b0 = c0; b1 = c1; b2 = c2;
-                                break;
-                            }
+                            float b[3];
+                            const int face = find_face(M, rx, ry, rz, bary_eps, b[0], b[1], b[2]);
                             if (face >= 0) {
-                                mag = sqrtf(n2);
                                 contrib = true;
+                                const float mag = sqrtf(n2);
+                                // Trilinear_interpolation_over_desc_debug :1466-1522
+                                const int ib0 = (int)vb0, ib1 = (int)vb1, ib2 = (int)vb2;  // truncation, Q12
+                                const float dv0 = vb0 - floorf(vb0), dv1 = vb1 - floorf(vb1), dv2 = vb2 - floorf(vb2);
+                                const double wx[2] = {1.0 - (double)dv0, (double)dv0};
+                                const double wy[2] = {1.0 - (double)dv1, (double)dv1};
+                                const double wz[2] = {1.0 - (double)dv2, (double)dv2};
+                                const int i0 = M.idx[face][0], i1 = M.idx[face][1], i2 = M.idx[face][2];
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    const int ddx = (c >> 2) & 1, ddy = (c >> 1) & 1, ddz = c & 1;
+                                    const int bx = ib0 + ddx, by = ib1 + ddy, bz = ib2 + ddz;
+                                    const bool ok = !(bx < 0 || by < 0 || bz < 0 || bx >= 4 || by >= 4 || bz >= 4);
+                                    const float wt = (float)(wx[ddx] * wy[ddy] * wz[ddz]);
+                                    const float mw = mag * wt;
+                                    const int base = (bx + by * 4 + bz * 16) * 12;
+                                    sv[c * 3 + 0][lane] = mw * b[0];
+                                    sv[c * 3 + 1][lane] = mw * b[1];
+                                    sv[c * 3 + 2][lane] = mw * b[2];
+                                    sa[c * 3 + 0][lane] = (unsigned short)(ok ? base + i0 : S3D_DESC_LEN);
+                                    sa[c * 3 + 1][lane] = (unsigned short)(ok ? base + i1 : S3D_DESC_LEN);
+                                    sa[c * 3 + 2][lane] = (unsigned short)(ok ? base + i2 : S3D_DESC_LEN);
+                                }
                             }
                         }
                     }
                 }
             }
-            // Phase B: the warp replays each contributing voxel; lane = cell*3 + vertex (24 lanes)
-            unsigned m = __ballot_sync(0xffffffffu, contrib);
-            const int cell = lane / 3, vtx = lane - cell * 3;
-            const int ddx = (cell >> 2) & 1, ddy = (cell >> 1) & 1, ddz = cell & 1;
+            unsigned m = __ballot_sync(0xffffffffu, contrib);  // also orders the staging writes
+            const int l24 = lane < 24 ? lane : 0;
             while (m) {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
-                const float a0 = __shfl_sync(0xffffffffu, vb0, j), a1 = __shfl_sync(0xffffffffu, vb1, j),
-                            a2 = __shfl_sync(0xffffffffu, vb2, j);
-                const float mg = __shfl_sync(0xffffffffu, mag, j);
-                const float c0 = __shfl_sync(0xffffffffu, b0, j), c1 = __shfl_sync(0xffffffffu, b1, j),
-                            c2 = __shfl_sync(0xffffffffu, b2, j);
-                const int f = __shfl_sync(0xffffffffu, face, j);
                 if (lane < 24) {
-                    const int bx = (int)a0 + ddx, by = (int)a1 + ddy, bz = (int)a2 + ddz;  // truncation, Q12
-                    if (!(bx < 0 || by < 0 || bz < 0 || bx >= 4 || by >= 4 || bz >= 4)) {
-                        const float dv0 = a0 - floorf(a0), dv1 = a1 - floorf(a1), dv2 = a2 - floorf(a2);
-                        const double w0 = ddx == 0 ? (1.0 - (double)dv0) : (double)dv0;
-                        const double w1 = ddy == 0 ? (1.0 - (double)dv1) : (double)dv1;
-                        const double w2 = ddz == 0 ? (1.0 - (double)dv2) : (double)dv2;
-                        const float wt = (float)(w0 * w1 * w2);
-                        const float bv = vtx == 0 ? c0 : (vtx == 1 ? c1 : c2);
-                        const int hidx = (bx + by * 4 + bz * 16) * 12 + M.idx[f][vtx];
-                        myh[hidx] += mg * wt * bv;
-                    }
+                    const int a = sa[l24][j];
+                    myh[a] += sv[l24][j];
                 }
                 __syncwarp();
             }
@@ -890,7 +1009,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
         const int i = tid + e * 256;
         float a = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kDescWarps; ++w) a += hist[w][i];
+        for (int w = 0; w < kDescWarps; ++w) a += S.hist[w][i];
         v[e] = a;
         ss += a * a;
     }
@@ -898,11 +1017,11 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
         __syncthreads();
-        if (lane == 0) red[wid] = x;
+        if (lane == 0) S.red[wid] = x;
         __syncthreads();
         float tsum = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kDescWarps; ++w) tsum += red[w];
+        for (int w = 0; w < kDescWarps; ++w) tsum += S.red[w];
         return tsum;
     };
     float norm = block_sum(ss);

@@ -62,7 +62,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -84,7 +84,7 @@ class ClockSampler:
     def summary(self, windows):
         sm, mx, reasons = [], [], set()
         for t, line in self.rows:
-            if not any(a <= t <= b for a, b in windows):
+            if not any(a - 0.05 <= t <= b + 0.05 for a, b in windows):
                 continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
