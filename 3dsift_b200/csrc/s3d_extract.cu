@@ -110,6 +110,7 @@ static void host_mesh(MeshConst* M) {
     auto mul = [](float a, float b) { volatile float r = a * b; return (float)r; };
     auto add = [](float a, float b) { volatile float r = a + b; return (float)r; };
     auto sub = [](float a, float b) { volatile float r = a - b; return (float)r; };
+    float cen[20][3];
     for (int i = 0; i < 20; i++) {
         float v[3][3];
         for (int j = 0; j < 3; j++) {
@@ -138,8 +139,40 @@ static void host_mesh(MeshConst* M) {
         q[1] = sub(mul(t[2], e1[0]), mul(t[0], e1[2]));
         q[2] = sub(mul(t[0], e1[1]), mul(t[1], e1[0]));
         M->qe2[i] = add(add(mul(q[0], e2[0]), mul(q[1], e2[1])), mul(q[2], e2[2]));
-        for (int c = 0; c < 3; c++) M->cen[i][c] = v[0][c] + v[1][c] + v[2][c];
+        for (int c = 0; c < 3; c++) cen[i][c] = v[0][c] + v[1][c] + v[2][c];
     }
+    // antipodal face pairs (the icosahedron is centrally symmetric): 10 centroids decide 20 faces
+    bool used[20] = {false};
+    int np = 0;
+    for (int i = 0; i < 20; i++) {
+        if (used[i]) continue;
+        int opp = -1;
+        for (int j = i + 1; j < 20; j++)
+            if (!used[j] && fabsf(cen[i][0] + cen[j][0]) + fabsf(cen[i][1] + cen[j][1]) + fabsf(cen[i][2] + cen[j][2]) < 1e-4f) opp = j;
+        used[i] = true;
+        if (opp >= 0) used[opp] = true;
+        for (int c = 0; c < 3; c++) M->cen10[np][c] = cen[i][c];
+        M->pos[np] = i;
+        M->neg[np] = opp >= 0 ? opp : i;
+        np++;
+    }
+}
+
+// Extended-line table of a pass along an axis of length n (Src/cSIFT3D.cc:751-760): for tap
+// coordinate c = q = n-1+e the reference samples at c' = 2(n-1) - c - 0.1f, lo = (int)c',
+// frac = c' - lo.  Same FP32 operations as the reference (volatile: no wider evaluation).
+static Taps with_ext(const Taps& t0, int n) {
+    Taps t = t0;
+    for (int e = 0; e <= kMaxHW; e++) {
+        volatile float c = (float)(2 * (n - 1));
+        c = c - (float)(n - 1 + e);
+        c = c - 0.1f;
+        int il = (int)c;
+        volatile float fr = c - (float)il;
+        t.ext_il[e] = il;
+        t.ext_frac[e] = fr;
+    }
+    return t;
 }
 
 static bool supported_fast_hw(int hw) { return hw == 2 || hw == 3 || hw == 4 || hw == 5 || hw == 6 || hw == 8; }
@@ -148,7 +181,7 @@ template <int HW>
 static void launch_x(const float* src, float* dst, int nx, ll nrows, const Taps& t, ll total, cudaStream_t st) {
     ll threads = nrows * (nx >> 2);
     auto kfn = blur_x_kernel<HW>;
-    S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 256), 256, 0, st, src, dst, nx, nrows, t);
+    S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 256), 256, 0, st, src, dst, nx, (unsigned)threads, t);
 }
 
 static int pick_seg(int nx4, int n_other, int n) {
@@ -228,10 +261,11 @@ struct ProfScope {
 
 // One separable pass.  variant 0 = generic kernel; 1 = fast kernels when eligible.
 // prev/dog/slot non-null fuses the DoG subtraction + max|DoG| (only meaningful on the last pass).
-static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int axis, const Taps& t, int variant,
+static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int axis, const Taps& t0, int variant,
                       const float* prev, float* dog, unsigned* slot, cudaStream_t st, Prof* prof = nullptr) {
     const ll total = (ll)nx * ny * nz;
     const int n = axis == 0 ? nx : (axis == 1 ? ny : nz);
+    const Taps t = with_ext(t0, n);
     const bool fast = variant == 1 && (nx % 4 == 0) && supported_fast_hw(t.hw) && n >= 2 * t.hw + 2 && total >= 4096 &&
                       !(axis == 0 && dog);
     // algorithmic bytes: read src + write dst (+ read prev + write dog on the fused pass)
@@ -603,7 +637,7 @@ static int run_impl(s3d_ctx* c) {
         }
         ProfScope ps(&c->prof, K_ORIENT_EXACT, 0.0);
         if (c->prm.exact_recheck)
-            S3D_LAUNCH(orient_exact_kernel, s3d_blocks(ne, 64), 64, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes,
+            S3D_LAUNCH(orient_exact_kernel, (unsigned)std::min<size_t>(s3d_blocks((size_t)ne * 32, 256), 148 * 8), 256, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes,
                        d_margins, 2e-3f, c->prm.max_eig_thres, c->prm.corner_thresh, d_total + 1, d_total + 2);
     }
     {

@@ -24,6 +24,10 @@ constexpr int kMaxG = 12;    // num_kp_levels + 3 <= 12
 struct Taps {
     int hw;
     float w[2 * kMaxHW + 1];
+    // extended-line table for the axis this pass runs along (length n): sample q = n-1+e,
+    // e = 0..hw, is (1-frac)*in[il] + frac*in[il+1]  (filled on the host by fill_ext)
+    int ext_il[kMaxHW + 1];
+    float ext_frac[kMaxHW + 1];
 };
 
 typedef long long ll;
@@ -66,30 +70,23 @@ __device__ __forceinline__ bool blur_is_interior(int p, int n, int hw) { return 
 // c' = 2(n-1) - q - 0.1f; otherwise in[q].  Interior outputs only ever touch 0 <= q <= n-2, where
 // this is in[q] as well, so with n >= 2*hw+2 EVERY output of a line is the plain ordered
 // correlation over this extended line — no divergent boundary path in the fast kernels.
-__device__ __forceinline__ void ext_coord(int q, int n, int& il, float& frac) {
-    if (q < 0) {
-        il = -q; frac = 0.0f;
-    } else if (q >= n - 1) {
-        float c = (float)(2 * (n - 1)) - (float)q - 0.1f;
-        il = (int)c;
-        frac = c - (float)il;
-    } else {
-        il = q; frac = 0.0f;
-    }
+// (il, frac) for q >= n-1 come from Taps::ext_il / ext_frac, computed on the host with the same
+// FP32 operations.
+__device__ __forceinline__ float ext_sample1(const float* __restrict__ line, int n, int q, const Taps& t) {
+    if (q < 0) return line[-q];
+    if (q < n - 1) return line[q];
+    const int e = q - (n - 1);
+    const int il = t.ext_il[e];
+    const float frac = t.ext_frac[e];
+    return (1.0f - frac) * line[il] + frac * line[il + 1];
 }
 
-__device__ __forceinline__ float ext_sample1(const float* __restrict__ line, ll st, int n, int q) {
-    int il; float frac;
-    ext_coord(q, n, il, frac);
-    if (frac == 0.0f) return line[(ll)il * st];
-    return (1.0f - frac) * line[(ll)il * st] + frac * line[(ll)(il + 1) * st];
-}
-
-__device__ __forceinline__ float4 ext_sample4(const float* __restrict__ col, ll st, int n, int q) {
-    int il; float frac;
-    ext_coord(q, n, il, frac);
+__device__ __forceinline__ float4 ext_sample4(const float* __restrict__ col, ll st, int n, int q, const Taps& t) {
+    if (q < n - 1) return *reinterpret_cast<const float4*>(col + (ll)(q < 0 ? -q : q) * st);
+    const int e = q - (n - 1);
+    const int il = t.ext_il[e];
+    const float frac = t.ext_frac[e];
     const float4 lo = *reinterpret_cast<const float4*>(col + (ll)il * st);
-    if (frac == 0.0f) return lo;
     const float4 hi = *reinterpret_cast<const float4*>(col + (ll)(il + 1) * st);
     float4 r;
     r.x = (1.0f - frac) * lo.x + frac * hi.x; r.y = (1.0f - frac) * lo.y + frac * hi.y;
@@ -187,15 +184,15 @@ __global__ void __launch_bounds__(256) blur_generic_kernel(const float* __restri
 // X pass, 4 outputs per thread (float4 store).  Requires nx % 4 == 0 and nx >= 2*HW+2.
 template <int HW>
 __global__ void __launch_bounds__(256) blur_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
-                                                     ll nrows, Taps t) {
+                                                     unsigned nthreads, Taps t) {
     constexpr int PAD = (HW + 3) / 4 * 4;
     constexpr int NV = (2 * PAD + 4) / 4;
-    const int nx4 = nx >> 2;
-    const ll gid = (ll)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= nrows * nx4) return;
-    const ll row = gid / nx4;
+    const unsigned nx4 = (unsigned)nx >> 2;
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= nthreads) return;
+    const unsigned row = gid / nx4;
     const int x0 = (int)(gid - row * nx4) * 4;
-    const float* r = src + row * nx;
+    const float* r = src + (size_t)row * nx;
     float v[2 * PAD + 4];
 #pragma unroll
     for (int q = 0; q < NV; ++q) {
@@ -209,7 +206,7 @@ __global__ void __launch_bounds__(256) blur_x_kernel(const float* __restrict__ s
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int qq = xx + e;
-                v[4 * q + e] = (qq >= -HW && qq <= nx - 1 + HW) ? ext_sample1(r, 1, nx, qq) : 0.0f;
+                v[4 * q + e] = (qq >= -HW && qq <= nx - 1 + HW) ? ext_sample1(r, nx, qq, t) : 0.0f;
             }
         }
     }
@@ -221,7 +218,7 @@ __global__ void __launch_bounds__(256) blur_x_kernel(const float* __restrict__ s
         for (int k = 0; k <= 2 * HW; ++k) acc += t.w[k] * v[PAD + j + HW - k];
         o[j] = acc;
     }
-    *reinterpret_cast<float4*>(dst + row * nx + x0) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(dst + (size_t)row * nx + x0) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // Y / Z pass: each thread owns a float4 column (4 consecutive x) and marches along the axis over
@@ -235,52 +232,58 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict
                                                          int n, ll st, int n_other, ll st_other, int seg, Taps t,
                                                          const float* __restrict__ prev, float* __restrict__ dog,
                                                          unsigned* maxslot) {
-    constexpr int W = 2 * HW + 1;
-    const int nx4 = nx >> 2;
+    constexpr int PF = HW >= 5 ? 2 : 4;       // loads are issued PF steps ahead of their first use
+    constexpr int WR = 2 * HW + 1 + PF;       // ring size == unroll factor (static slot indices)
+    const unsigned nx4 = (unsigned)nx >> 2;
     const int nseg = (n + seg - 1) / seg;
-    const ll gid = (ll)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.0f;
-    if (gid < (ll)nx4 * n_other * nseg) {
-        const int x4 = (int)(gid % nx4);
-        const ll tt = gid / nx4;
-        const int other = (int)(tt % n_other);
-        const int s = (int)(tt / n_other);
+    if (gid < nx4 * (unsigned)n_other * (unsigned)nseg) {
+        const unsigned tt = gid / nx4;
+        const int x4 = (int)(gid - tt * nx4);
+        const int s = (int)(tt / (unsigned)n_other);
+        const int other = (int)(tt - (unsigned)s * (unsigned)n_other);
         const int p0 = s * seg;
         const int p1 = min(n, p0 + seg);
+        const int qmax = p1 - 1 + HW;  // last extended-line sample this segment needs (<= n-1+HW)
         const ll line0 = (ll)x4 * 4 + (ll)other * st_other;  // flat index of coordinate 0 on this line
         const float* col = src + line0;
-        float4 win[W];
-        // prologue: ring slots for inputs p0-HW .. p0+HW-1 (relative r = 0 .. 2HW-1)
+        float4 win[WR];
+        // prologue: samples p0-HW .. p0+HW+PF-1  (relative r = 0 .. 2HW+PF-1)
 #pragma unroll
-        for (int r = 0; r < 2 * HW; ++r) {
+        for (int r = 0; r < 2 * HW + PF; ++r) {
             const int q = p0 - HW + r;
-            win[r] = (q >= -HW && q <= n - 1 + HW) ? ext_sample4(col, st, n, q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            win[r] = (q <= qmax) ? ext_sample4(col, st, n, q, t) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        win[2 * HW] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ib = 0; p0 + ib < p1; ib += W) {
+        win[2 * HW + PF] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (DOG) pv = *reinterpret_cast<const float4*>(prev + line0 + (ll)p0 * st);
+        for (int ib = 0; p0 + ib < p1; ib += WR) {
 #pragma unroll
-            for (int j = 0; j < W; ++j) {
+            for (int j = 0; j < WR; ++j) {
                 const int p = p0 + ib + j;
                 if (p < p1) {
-                    // newest input p+HW goes to the slot of the oldest one (relative r = ib+j+2HW)
-                    const int q = p + HW;
-                    win[(j + 2 * HW) % W] = ext_sample4(col, st, n, q);  // q <= n-1+HW always
+                    // prefetch sample p+HW+PF into the slot of the oldest one (relative r = ib+j+2HW+PF)
+                    const int q = p + HW + PF;
+                    if (q <= qmax) win[(j + 2 * HW + PF) % WR] = ext_sample4(col, st, n, q, t);
+                    float4 pvn = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (DOG && p + 1 < p1) pvn = *reinterpret_cast<const float4*>(prev + line0 + (ll)(p + 1) * st);
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int k = 0; k <= 2 * HW; ++k) {
-                        const float4 v = win[(j + 2 * HW - k) % W];  // extended-line sample p+HW-k
+                        const float4 v = win[(j + 2 * HW - k) % WR];  // extended-line sample p+HW-k
                         const float w = t.w[k];
                         acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
                     }
                     const ll oidx = line0 + (ll)p * st;
                     *reinterpret_cast<float4*>(dst + oidx) = acc;
                     if (DOG) {
-                        const float4 pv = *reinterpret_cast<const float4*>(prev + oidx);
                         float4 dv;
                         dv.x = (acc.x - pv.x) * (-1); dv.y = (acc.y - pv.y) * (-1);
                         dv.z = (acc.z - pv.z) * (-1); dv.w = (acc.w - pv.w) * (-1);
                         *reinterpret_cast<float4*>(dog + oidx) = dv;
                         m = fmaxf(m, fmaxf(fmaxf(fabsf(dv.x), fabsf(dv.y)), fmaxf(fabsf(dv.z), fabsf(dv.w))));
+                        pv = pvn;
                     }
                 }
             }
@@ -709,45 +712,83 @@ __global__ void __launch_bounds__(256) orient_kernel(const Cand* __restrict__ ca
     }
 }
 
-// Exact serial re-evaluation (one thread per flagged detection) in the reference's own loop order
-// z, y, x with FP32 accumulation (Src/cSIFT3D.cc:958-998), so near-threshold accept/reject
-// decisions follow the reference's rounding instead of the warp-parallel tree's.
-__global__ void __launch_bounds__(64) orient_exact_kernel(const Cand* __restrict__ cand, int ncand, LevelTable tab,
-                                                          s3d_keypoint* __restrict__ out, int* __restrict__ codes,
-                                                          const float* __restrict__ margins, float recheck_margin,
-                                                          float max_eig, float corner, int* n_rechecked, int* n_flipped) {
-    const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ci >= ncand) return;
-    if (!(margins[ci] < recheck_margin)) return;
-    int o, lvl, x, y, z;
-    cand_decode(cand[ci], tab, o, lvl, x, y, z);
-    const int nx = tab.dims[o][0], ny = tab.dims[o][1], nz = tab.dims[o][2];
-    const float* g = tab.gss[o * tab.G + lvl];
-    const float scale = tab.scale[o * tab.G + lvl];
-    const float u = (float)(1 << o);
-    s3d_keypoint kp;
-    kp_init(kp, o, lvl, x, y, z, scale);
-    const float sigma = 1.5f * scale;
-    const float win_radius = sigma * 3.0f;
-    const float r2 = win_radius * win_radius;
-    int xs, xe, y0, y1, z0, z1;
-    window_bounds(kp.x, win_radius / u, nx, xs, xe);
-    window_bounds(kp.y, win_radius / u, ny, y0, y1);
-    window_bounds(kp.z, win_radius / u, nz, z0, z1);
-    const ll ys = nx, zs = (ll)nx * ny;
-    OrientSums S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int zz = z0; zz <= z1; ++zz)
-        for (int yy = y0; yy <= y1; ++yy)
-            for (int xx = xs; xx <= xe; ++xx) {
-                const float dx = ((float)xx - kp.x) * u, dy = ((float)yy - kp.y) * u, dz = ((float)zz - kp.z) * u;
-                orient_voxel(g, (ll)xx + (ll)yy * ys + (ll)zz * zs, ys, zs, dx, dy, dz, u, sigma, r2, S);
+// One window voxel's nine addends (no accumulation), same arithmetic as orient_voxel.
+__device__ __forceinline__ bool orient_terms(const float* __restrict__ g, ll i, ll ys, ll zs, float dx, float dy, float dz,
+                                             float u, float sigma, float r2, float tm[9]) {
+    const float sq = dx * dx + dy * dy + dz * dz;
+    if (sq > r2) return false;
+    const float weight = s3d_expf_ref((float)(-0.5 * (double)sq / (double)(sigma * sigma)));
+    float vx = (float)(0.5 * (double)(g[i + 1] - g[i - 1]));
+    float vy = (float)(0.5 * (double)(g[i + ys] - g[i - ys]));
+    float vz = (float)(0.5 * (double)(g[i + zs] - g[i - zs]));
+    const float iu = 1.0f / u;
+    vx *= iu; vy *= iu; vz *= iu;
+    tm[0] = vx * vx * weight; tm[1] = vx * vy * weight; tm[2] = vx * vz * weight;
+    tm[3] = vy * vy * weight; tm[4] = vy * vz * weight; tm[5] = vz * vz * weight;
+    tm[6] = vx * weight; tm[7] = vy * weight; tm[8] = vz * weight;
+    return true;
+}
+
+// Exact re-evaluation of the flagged detections in the reference's own summation order
+// (z, y, x serial FP32 accumulation, Src/cSIFT3D.cc:958-998), so near-threshold accept/reject
+// decisions follow the reference's rounding instead of the warp-parallel tree's.  One warp per
+// flagged detection: lanes compute the addends of 32 consecutive voxels of a row in parallel,
+// then every lane accumulates them IN ORDER (broadcast by shuffle), which reproduces the serial
+// sum bit for bit at 1/32 of the serial latency.
+__global__ void __launch_bounds__(256) orient_exact_kernel(const Cand* __restrict__ cand, int ncand, LevelTable tab,
+                                                           s3d_keypoint* __restrict__ out, int* __restrict__ codes,
+                                                           const float* __restrict__ margins, float recheck_margin,
+                                                           float max_eig, float corner, int* n_rechecked, int* n_flipped) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < ncand; ci += warps_per_grid) {
+        if (!(margins[ci] < recheck_margin)) continue;
+        int o, lvl, x, y, z;
+        cand_decode(cand[ci], tab, o, lvl, x, y, z);
+        const int nx = tab.dims[o][0], ny = tab.dims[o][1], nz = tab.dims[o][2];
+        const float* g = tab.gss[o * tab.G + lvl];
+        const float scale = tab.scale[o * tab.G + lvl];
+        const float u = (float)(1 << o);
+        s3d_keypoint kp;
+        kp_init(kp, o, lvl, x, y, z, scale);
+        const float sigma = 1.5f * scale;
+        const float win_radius = sigma * 3.0f;
+        const float r2 = win_radius * win_radius;
+        int xs, xe, y0, y1, z0, z1;
+        window_bounds(kp.x, win_radius / u, nx, xs, xe);
+        window_bounds(kp.y, win_radius / u, ny, y0, y1);
+        window_bounds(kp.z, win_radius / u, nz, z0, z1);
+        const ll ys = nx, zs = (ll)nx * ny;
+        float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int zz = z0; zz <= z1; ++zz)
+            for (int yy = y0; yy <= y1; ++yy) {
+                const float dy = ((float)yy - kp.y) * u, dz = ((float)zz - kp.z) * u;
+                for (int xb = xs; xb <= xe; xb += 32) {
+                    const int xx = xb + lane;
+                    float tm[9];
+                    bool in = false;
+                    if (xx <= xe) in = orient_terms(g, (ll)xx + (ll)yy * ys + (ll)zz * zs, ys, zs, ((float)xx - kp.x) * u, dy, dz, u, sigma, r2, tm);
+                    unsigned m = __ballot_sync(0xffffffffu, in);
+                    while (m) {
+                        const int j = __ffs(m) - 1;
+                        m &= m - 1;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) acc[k] += __shfl_sync(0xffffffffu, tm[k], j);
+                    }
+                }
             }
-    const int code = orient_finish(S, kp, max_eig, corner, nullptr);
-    if (code < 1) kp.x = kp.y = kp.z = -1.0f;
-    atomicAdd(n_rechecked, 1);
-    if (code != codes[ci]) atomicAdd(n_flipped, 1);
-    out[ci] = kp;
-    codes[ci] = code;
+        OrientSums S;
+        S.t00 = acc[0]; S.t01 = acc[1]; S.t02 = acc[2]; S.t11 = acc[3]; S.t12 = acc[4]; S.t22 = acc[5];
+        S.wx = acc[6]; S.wy = acc[7]; S.wz = acc[8];
+        const int code = orient_finish(S, kp, max_eig, corner, nullptr);
+        if (lane == 0) {
+            if (code < 1) kp.x = kp.y = kp.z = -1.0f;
+            atomicAdd(n_rechecked, 1);
+            if (code != codes[ci]) atomicAdd(n_flipped, 1);
+            out[ci] = kp;
+            codes[ci] = code;
+        }
+    }
 }
 
 // Ordered compaction of the survivors (serial loop Src/cSIFT3D.cc:459-466): one CTA.
@@ -780,7 +821,8 @@ __global__ void __launch_bounds__(1024) survivors_kernel(const int* __restrict__
 struct MeshConst {
     float e1[20][3], e2[20][3], t[20][3], q[20][3];  // per face: V1-V0, V2-V0, -V0, t x e1
     float qe2[20];                                   // q . e2
-    float cen[20][3];                                // V0+V1+V2 (all faces have the same |cen|)
+    float cen10[10][3];                              // centroid of one face of each antipodal pair
+    int pos[10], neg[10];                            // face with centroid +cen10[i] / -cen10[i]
     int idx[20][3];                                  // vertex ids (NOT swapped, App. B Q13)
 };
 
@@ -805,19 +847,23 @@ __device__ __forceinline__ bool face_bary(const MeshConst& M, int f, float gx, f
 // Check_intersect_faces, Src/cSIFT3D.cc:1542-1573: the FIRST face (index order) whose barycentric
 // coordinates are all >= -bary_eps with k >= 0 wins (App. B Q14).
 // Fast path: the faces of a regular icosahedron are the spherical Voronoi cells of their
-// centroids, so the face hit by a direction is argmax_f <cen_f, g>.  If that face's barycentric
-// coordinates are all comfortably positive, no other face can pass the reference's tolerance test
-// and the result (face, bary) is exactly what the sequential scan returns (same FP32 formula for
-// the same face).  Directions within `margin` of an edge/vertex take the reference's scan.
+// centroids, so the face hit by a direction is argmax_f <cen_f, g>; faces come in antipodal
+// pairs, so 10 dot products (fused: this is only a pre-selection) decide among 20 faces.  If the
+// selected face's barycentric coordinates are all comfortably positive, no other face can pass
+// the reference's tolerance test and (face, bary) is exactly what the sequential scan returns
+// (same FP32 formula for the same face).  Directions within `margin` of an edge/vertex take the
+// reference's scan.
 __device__ __forceinline__ int find_face(const MeshConst& M, float gx, float gy, float gz, float bary_eps, float& b0,
                                          float& b1, float& b2) {
-    int fs = 0;
-    float best = -FLT_MAX;
+    int fi = 0;
+    float best = -1.0f, bestd = 0.0f;
 #pragma unroll
-    for (int f = 0; f < 20; ++f) {
-        const float d = M.cen[f][0] * gx + M.cen[f][1] * gy + M.cen[f][2] * gz;
-        if (d > best) { best = d; fs = f; }
+    for (int i = 0; i < 10; ++i) {
+        const float d = __fmaf_rn(M.cen10[i][0], gx, __fmaf_rn(M.cen10[i][1], gy, __fmul_rn(M.cen10[i][2], gz)));
+        const float ad = fabsf(d);
+        if (ad > best) { best = ad; bestd = d; fi = i; }
     }
+    const int fs = bestd >= 0.0f ? M.pos[fi] : M.neg[fi];
     float k;
     const float margin = 1e-4f;
     if (face_bary(M, fs, gx, gy, gz, bary_eps, b0, b1, b2, k) && b0 > margin && b1 > margin && b2 > margin && k > 0.0f)
@@ -833,26 +879,30 @@ __device__ __forceinline__ int find_face(const MeshConst& M, float gx, float gy,
 }
 
 constexpr int kDescWarps = 8;
-constexpr int kHistStride = 776;  // 768 bins + a dump slot for out-of-grid cells, padded
+// Histogram bin (x,y,z,v) lives at (x + 4y)*12 + z*kHistZ + v: the z stride is padded from 192 to
+// 200 words so the 8 trilinear cells of a voxel fall into 8 different bank groups.
+constexpr int kHistZ = 200;
+constexpr int kHistDump = 3 * kHistZ + 192;      // slot for out-of-grid cells
+constexpr int kHistStride = kHistDump + 8;
 constexpr int kStagePad = 33;
 
 struct DescSmem {
     float hist[kDescWarps][kHistStride];
-    float sval[kDescWarps][24][kStagePad];
-    unsigned short saddr[kDescWarps][24][kStagePad];
+    uint2 stage[kDescWarps][24][kStagePad];          // (bin address, value bits) per contribution
     MeshConst M;
     s3d_keypoint kp;
     float red[kDescWarps];
 };
 
-// One CTA per surviving keypoint, 8 warps.  Rows (y,z) of the window are dealt round-robin to
-// the warps (static assignment => run-to-run deterministic sums).  Per row the x range is clipped
-// to the sphere chord and the rotated 4x4x4 grid (conservatively, +-1 voxel; the reference's exact
-// per-voxel tests still decide).  Phase A: one lane per voxel computes the reference's per-voxel
-// quantities and stages its 24 (bin, value) contributions (8 trilinear cells x 3 face vertices)
-// in shared memory.  Phase B: the warp replays the contributing voxels one at a time, lane l < 24
-// adding contribution l into the warp-private histogram — plain LDS/FADD/STS, no atomics (shared
-// FP32 atomics are CAS loops on sm_100).  Warp histograms are summed in fixed order at the end.
+// One CTA per surviving keypoint, 8 warps.  Pairs of adjacent rows (y, y+1 at fixed z) of the
+// window are dealt round-robin to the warps, one row per half-warp (static assignment =>
+// run-to-run deterministic sums).  Per row the x range is clipped to the sphere chord and the
+// rotated 4x4x4 grid (conservatively, +-1 voxel; the reference's exact per-voxel tests still
+// decide).  Phase A: one lane per voxel computes the reference's per-voxel quantities and stages
+// its 24 (bin, value) contributions (8 trilinear cells x 3 face vertices) in shared memory.
+// Phase B: the warp replays the contributing voxels one at a time, lane l < 24 adding
+// contribution l into the warp-private histogram — plain LDS/FADD/STS, no atomics (shared FP32
+// atomics are CAS loops on sm_100).  Warp histograms are summed in fixed order at the end.
 __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_keypoint* __restrict__ extre,
                                                                    const int* __restrict__ surv, int nkp, LevelTable tab,
                                                                    const MeshConst* __restrict__ meshp,
@@ -897,42 +947,52 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
     window_bounds(cy, win_radius / u, ny, y0, y1);
     window_bounds(cz, win_radius / u, nz, z0, z1);
     const int wyn = y1 - y0 + 1, wzn = z1 - z0 + 1;
-    const int nrows = (wyn > 0 && wzn > 0) ? wyn * wzn : 0;
+    const int wyp = (wyn + 1) >> 1;  // row pairs per z slice
+    const int npairs = (wyn > 0 && wzn > 0) ? wyp * wzn : 0;
     const ll ys = nx, zs = (ll)nx * ny;
     float* myh = S.hist[wid];
-    float(*sv)[kStagePad] = S.sval[wid];
-    unsigned short(*sa)[kStagePad] = S.saddr[wid];
+    uint2(*stg)[kStagePad] = S.stage[wid];
     const float iu = 1.0f / u;
-    const float slab = desc_hw * 1.0009765625f + 1e-3f;  // conservative half-width of the rotated grid
+    // conservative clip of a row to the rotated grid: |R_k . disp| < slab for k = 0..2, with
+    // R_k . disp = a_k * (x - cx) + (R_k1*dy + R_k2*dz); the reciprocals are per keypoint
+    const float slab = desc_hw * 1.001f + 1e-3f;
+    const float a0 = R0 * u, a1 = R3 * u, a2 = R6 * u;
+    const bool f0 = fabsf(a0) > 1e-6f, f1 = fabsf(a1) > 1e-6f, f2 = fabsf(a2) > 1e-6f;
+    const float ia0 = f0 ? 1.0f / a0 : 0.0f, ia1 = f1 ? 1.0f / a1 : 0.0f, ia2 = f2 ? 1.0f / a2 : 0.0f;
+    const int half = lane >> 4, hl = lane & 15;
+    // row-pair cursor, advanced incrementally (no division in the loop)
+    const int wypg = wyp > 0 ? wyp : 1;
+    int py = wid % wypg, pz = wid / wypg;
 
-    for (int r = wid; r < nrows; r += kDescWarps) {
-        const int yy = y0 + r % wyn, zz = z0 + r / wyn;
+    for (int rp = wid; rp < npairs; rp += kDescWarps) {
+        const int yy = y0 + 2 * py + half, zz = z0 + pz;
+        py += kDescWarps;
+        while (py >= wyp) { py -= wyp; ++pz; }
         const float dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
         // fl(fl(dx^2+dy^2)+dz^2) >= fl(dy^2+dz^2) by monotonicity of rounding: safe row reject
         const float dyz2 = dy * dy + dz * dz;
-        if (dyz2 > r2) continue;
-        // conservative x interval (in voxels about cx): sphere chord ...
-        float lo = -(sqrtf(r2 - dyz2) * iu), hi = -lo;
-        // ... intersected with the three slabs |R_k . disp| < desc_hw of the rotated grid
-        bool empty = false;
-        {
-            const float a[3] = {R0 * u, R3 * u, R6 * u};
-            const float c[3] = {R1 * dy + R2 * dz, R4 * dy + R5 * dz, R7 * dy + R8 * dz};
-#pragma unroll
-            for (int kk = 0; kk < 3; ++kk) {
-                if (fabsf(a[kk]) > 1e-6f) {
-                    float t0 = (-slab - c[kk]) / a[kk], t1 = (slab - c[kk]) / a[kk];
-                    if (t0 > t1) { const float tt = t0; t0 = t1; t1 = tt; }
-                    lo = fmaxf(lo, t0); hi = fminf(hi, t1);
-                } else if (fabsf(c[kk]) > slab + 1e-3f * desc_hw) {
-                    empty = true;
-                }
+        int xlo = 1, xhi = 0;  // empty
+        if (yy <= y1 && !(dyz2 > r2)) {
+            float lo = -(sqrtf(r2 - dyz2) * iu), hi = -lo;  // sphere chord, in voxels about cx
+            bool empty = false;
+            const float c0 = R1 * dy + R2 * dz, c1 = R4 * dy + R5 * dz, c2 = R7 * dy + R8 * dz;
+#define S3D_CLIP(fk, ck, iak)                                                    \
+            if (fk) {                                                            \
+                const float t0 = (-slab - ck) * iak, t1 = (slab - ck) * iak;     \
+                lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));    \
+            } else if (fabsf(ck) > slab) empty = true;
+            S3D_CLIP(f0, c0, ia0) S3D_CLIP(f1, c1, ia1) S3D_CLIP(f2, c2, ia2)
+#undef S3D_CLIP
+            if (!empty && !(lo > hi + 2.0f)) {
+                xlo = max(xs, (int)floorf(cx + lo) - 1);
+                xhi = min(xe, (int)ceilf(cx + hi) + 1);
             }
         }
-        if (empty || lo > hi + 2.0f) continue;
-        const int xlo = max(xs, (int)floorf(cx + lo) - 1), xhi = min(xe, (int)ceilf(cx + hi) + 1);
-        for (int xb = xlo; xb <= xhi; xb += 32) {
-            const int xx = xb + lane;
+        const int len = xhi - xlo + 1;
+        const int len_other = __shfl_xor_sync(0xffffffffu, len, 16);
+        const int iters = (max(len, len_other) + 15) >> 4;
+        for (int it = 0; it < iters; ++it) {
+            const int xx = xlo + it * 16 + hl;
             bool contrib = false;
             if (xx <= xhi) {
                 const float dx = ((float)xx - cx) * u;
@@ -974,13 +1034,10 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
                                     const bool ok = !(bx < 0 || by < 0 || bz < 0 || bx >= 4 || by >= 4 || bz >= 4);
                                     const float wt = (float)(wx[ddx] * wy[ddy] * wz[ddz]);
                                     const float mw = mag * wt;
-                                    const int base = (bx + by * 4 + bz * 16) * 12;
-                                    sv[c * 3 + 0][lane] = mw * b[0];
-                                    sv[c * 3 + 1][lane] = mw * b[1];
-                                    sv[c * 3 + 2][lane] = mw * b[2];
-                                    sa[c * 3 + 0][lane] = (unsigned short)(ok ? base + i0 : S3D_DESC_LEN);
-                                    sa[c * 3 + 1][lane] = (unsigned short)(ok ? base + i1 : S3D_DESC_LEN);
-                                    sa[c * 3 + 2][lane] = (unsigned short)(ok ? base + i2 : S3D_DESC_LEN);
+                                    const int base = (bx + by * 4) * 12 + bz * kHistZ;
+                                    stg[c * 3 + 0][lane] = make_uint2(ok ? base + i0 : kHistDump, __float_as_uint(mw * b[0]));
+                                    stg[c * 3 + 1][lane] = make_uint2(ok ? base + i1 : kHistDump, __float_as_uint(mw * b[1]));
+                                    stg[c * 3 + 2][lane] = make_uint2(ok ? base + i2 : kHistDump, __float_as_uint(mw * b[2]));
                                 }
                             }
                         }
@@ -988,15 +1045,16 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
                 }
             }
             unsigned m = __ballot_sync(0xffffffffu, contrib);  // also orders the staging writes
-            const int l24 = lane < 24 ? lane : 0;
-            while (m) {
-                const int j = __ffs(m) - 1;
-                m &= m - 1;
-                if (lane < 24) {
-                    const int a = sa[l24][j];
-                    myh[a] += sv[l24][j];
+            if (m) {
+                const int l24 = lane < 24 ? lane : 0;
+                uint2 cur = stg[l24][__ffs(m) - 1];
+                while (m) {
+                    m &= m - 1;
+                    const uint2 nxt = stg[l24][m ? __ffs(m) - 1 : 0];  // prefetch the next voxel's entry
+                    if (lane < 24) myh[cur.x] += __uint_as_float(cur.y);
+                    __syncwarp();
+                    cur = nxt;
                 }
-                __syncwarp();
             }
         }
     }
@@ -1006,10 +1064,11 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
     float ss = 0.0f;
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
-        const int i = tid + e * 256;
+        const int i = tid + e * 256;                 // output index (x + 4y + 16z)*12 + v
+        const int hz = i / 192, hr = i - hz * 192;   // -> padded histogram address
         float a = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kDescWarps; ++w) a += S.hist[w][i];
+        for (int w = 0; w < kDescWarps; ++w) a += S.hist[w][hz * kHistZ + hr];
         v[e] = a;
         ss += a * a;
     }
