@@ -855,15 +855,17 @@ __device__ __forceinline__ bool face_bary(const MeshConst& M, int f, float gx, f
 // reference's scan.
 __device__ __forceinline__ int find_face(const MeshConst& M, float gx, float gy, float gz, float bary_eps, float& b0,
                                          float& b1, float& b2) {
-    int fi = 0;
-    float best = -1.0f, bestd = 0.0f;
+    // key = |d| bits with the low 5 mantissa bits replaced by (pair index << 1 | sign): one max
+    // per pair instead of compare + three selects (a pre-selection only; see the margin test)
+    unsigned key = 0;
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
         const float d = __fmaf_rn(M.cen10[i][0], gx, __fmaf_rn(M.cen10[i][1], gy, __fmul_rn(M.cen10[i][2], gz)));
-        const float ad = fabsf(d);
-        if (ad > best) { best = ad; bestd = d; fi = i; }
+        const unsigned u = __float_as_uint(d);
+        key = max(key, ((u & 0x7fffffe0u) | (unsigned)(i << 1)) | (u >> 31));
     }
-    const int fs = bestd >= 0.0f ? M.pos[fi] : M.neg[fi];
+    const int fi = (int)((key >> 1) & 15u);
+    const int fs = (key & 1u) ? M.neg[fi] : M.pos[fi];
     float k;
     const float margin = 1e-4f;
     if (face_bary(M, fs, gx, gy, gz, bary_eps, b0, b1, b2, k) && b0 > margin && b1 > margin && b2 > margin && k > 0.0f)
@@ -878,32 +880,36 @@ __device__ __forceinline__ int find_face(const MeshConst& M, float gx, float gy,
     return -1;
 }
 
-constexpr int kDescWarps = 8;
+constexpr int kDescWarps = 7;
+constexpr int kDescThreads = kDescWarps * 32;
 // Histogram bin (x,y,z,v) lives at (x + 4y)*12 + z*kHistZ + v: the z stride is padded from 192 to
 // 200 words so the 8 trilinear cells of a voxel fall into 8 different bank groups.
 constexpr int kHistZ = 200;
 constexpr int kHistDump = 3 * kHistZ + 192;      // slot for out-of-grid cells
 constexpr int kHistStride = kHistDump + 8;
-constexpr int kStagePad = 33;
 
 struct DescSmem {
     float hist[kDescWarps][kHistStride];
-    uint2 stage[kDescWarps][24][kStagePad];          // (bin address, value bits) per contribution
+    uint2 stage[kDescWarps][24][32];                 // (bin address, value bits); column = rank ^ entry
+    uint32_t queue[kDescWarps][64];                  // per-warp ring of voxels that passed the cheap tests
     MeshConst M;
     s3d_keypoint kp;
-    float red[kDescWarps];
+    float red[kDescWarps + 1];
 };
 
-// One CTA per surviving keypoint, 8 warps.  Pairs of adjacent rows (y, y+1 at fixed z) of the
-// window are dealt round-robin to the warps, one row per half-warp (static assignment =>
-// run-to-run deterministic sums).  Per row the x range is clipped to the sphere chord and the
-// rotated 4x4x4 grid (conservatively, +-1 voxel; the reference's exact per-voxel tests still
-// decide).  Phase A: one lane per voxel computes the reference's per-voxel quantities and stages
-// its 24 (bin, value) contributions (8 trilinear cells x 3 face vertices) in shared memory.
-// Phase B: the warp replays the contributing voxels one at a time, lane l < 24 adding
-// contribution l into the warp-private histogram — plain LDS/FADD/STS, no atomics (shared FP32
-// atomics are CAS loops on sm_100).  Warp histograms are summed in fixed order at the end.
-__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_keypoint* __restrict__ extre,
+// One CTA per surviving keypoint, 7 warps, 3 CTAs per SM.
+//  * Pairs of adjacent rows (y, y+1 at fixed z) of the window are dealt round-robin to the warps,
+//    one row per half-warp (static assignment => run-to-run deterministic sums).  Per row the x
+//    range is clipped to the sphere chord and the rotated 4x4x4 grid (conservatively, +-1 voxel).
+//  * Cheap phase: one lane per voxel applies the reference's exact inclusion tests (sphere
+//    :1270, grid :1300-1302) and pushes survivors onto a per-warp ring (ballot/popc ranks).
+//  * Heavy phase, whenever 32 voxels are queued (full warps): the reference's per-voxel
+//    arithmetic (:1312-1327, :1450-1522) and staging of the 24 (bin, value) contributions
+//    (8 trilinear cells x 3 face vertices) in shared memory, rank-compacted.
+//  * Replay: the warp walks the staged voxels in order, lane l < 24 adding contribution l into
+//    the warp-private histogram — plain LDS/FADD/STS, no atomics (shared FP32 atomics are CAS
+//    loops on sm_100).  Warp histograms are summed in fixed order at the end.
+__global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_keypoint* __restrict__ extre,
                                                                    const int* __restrict__ surv, int nkp, LevelTable tab,
                                                                    const MeshConst* __restrict__ meshp,
                                                                    s3d_keypoint* __restrict__ kps_out,
@@ -916,11 +922,11 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
     {
         const int* src = reinterpret_cast<const int*>(extre + surv[k]);
         int* dstp = reinterpret_cast<int*>(&S.kp);
-        for (int i = tid; i < (int)(sizeof(s3d_keypoint) / 4); i += blockDim.x) dstp[i] = src[i];
+        for (int i = tid; i < (int)(sizeof(s3d_keypoint) / 4); i += kDescThreads) dstp[i] = src[i];
         const int* ms = reinterpret_cast<const int*>(meshp);
         int* md = reinterpret_cast<int*>(&S.M);
-        for (int i = tid; i < (int)(sizeof(MeshConst) / 4); i += blockDim.x) md[i] = ms[i];
-        for (int i = tid; i < kDescWarps * kHistStride; i += blockDim.x) (&S.hist[0][0])[i] = 0.0f;
+        for (int i = tid; i < (int)(sizeof(MeshConst) / 4); i += kDescThreads) md[i] = ms[i];
+        for (int i = tid; i < kDescWarps * kHistStride; i += kDescThreads) (&S.hist[0][0])[i] = 0.0f;
     }
     __syncthreads();
     const MeshConst& M = S.M;
@@ -951,7 +957,8 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
     const int npairs = (wyn > 0 && wzn > 0) ? wyp * wzn : 0;
     const ll ys = nx, zs = (ll)nx * ny;
     float* myh = S.hist[wid];
-    uint2(*stg)[kStagePad] = S.stage[wid];
+    uint2(*stg)[32] = S.stage[wid];
+    uint32_t* que = S.queue[wid];
     const float iu = 1.0f / u;
     // conservative clip of a row to the rotated grid: |R_k . disp| < slab for k = 0..2, with
     // R_k . disp = a_k * (x - cx) + (R_k1*dy + R_k2*dz); the reciprocals are per keypoint
@@ -960,10 +967,83 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
     const bool f0 = fabsf(a0) > 1e-6f, f1 = fabsf(a1) > 1e-6f, f2 = fabsf(a2) > 1e-6f;
     const float ia0 = f0 ? 1.0f / a0 : 0.0f, ia1 = f1 ? 1.0f / a1 : 0.0f, ia2 = f2 ? 1.0f / a2 : 0.0f;
     const int half = lane >> 4, hl = lane & 15;
-    // row-pair cursor, advanced incrementally (no division in the loop)
-    const int wypg = wyp > 0 ? wyp : 1;
-    int py = wid % wypg, pz = wid / wypg;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int l24 = lane < 24 ? lane : 0;
 
+    // ---- heavy phase + replay for up to 32 queued voxels (packed = dx | dy<<10 | dz<<20 offsets) ----
+    auto heavy = [&](uint32_t packed, bool valid) {
+        bool contrib = false;
+        float vb0 = 0.f, vb1 = 0.f, vb2 = 0.f, mag = 0.f, b[3] = {0.f, 0.f, 0.f};
+        int face = 0;
+        if (valid) {
+            const int xx = xs + (int)(packed & 1023u), yy = y0 + (int)((packed >> 10) & 1023u), zz = z0 + (int)(packed >> 20);
+            const float dx = ((float)xx - cx) * u, dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
+            const float sq = dx * dx + dy * dy + dz * dz;
+            vb0 = (R0 * dx + R1 * dy + R2 * dz + desc_hw) * desc_bin_fctr;
+            vb1 = (R3 * dx + R4 * dy + R5 * dz + desc_hw) * desc_bin_fctr;
+            vb2 = (R6 * dx + R7 * dy + R8 * dz + desc_hw) * desc_bin_fctr;
+            vb0 -= 0.5f; vb1 -= 0.5f; vb2 -= 0.5f;
+            const float weight = s3d_expf_ref(-0.5f * sq / s2);
+            const ll i = (ll)xx + (ll)yy * ys + (ll)zz * zs;
+            float gx = (float)(0.5 * (double)(g[i + 1] - g[i - 1]));
+            float gy = (float)(0.5 * (double)(g[i + ys] - g[i - ys]));
+            float gz = (float)(0.5 * (double)(g[i + zs] - g[i - zs]));
+            gx *= iu; gy *= iu; gz *= iu;
+            gx = gx * weight; gy = gy * weight; gz = gz * weight;  // SIFT3D_CVEC_SCALE :1322
+            const float rx = R0 * gx + R1 * gy + R2 * gz;
+            const float ry = R3 * gx + R4 * gy + R5 * gz;
+            const float rz = R6 * gx + R7 * gy + R8 * gz;
+            const float n2 = rx * rx + ry * ry + rz * rz;
+            if (!(n2 < bary_eps)) {  // Check_intersect_faces :1544
+                face = find_face(M, rx, ry, rz, bary_eps, b[0], b[1], b[2]);
+                if (face >= 0) {
+                    contrib = true;
+                    mag = sqrtf(n2);
+                }
+            }
+        }
+        const unsigned mc = __ballot_sync(0xffffffffu, contrib);
+        if (contrib) {
+            // Trilinear_interpolation_over_desc_debug :1466-1522
+            const int rr = __popc(mc & lt_mask);  // rank among the contributing lanes = stage column
+            const int ib0 = (int)vb0, ib1 = (int)vb1, ib2 = (int)vb2;  // truncation, Q12
+            const float dv0 = vb0 - floorf(vb0), dv1 = vb1 - floorf(vb1), dv2 = vb2 - floorf(vb2);
+            const double wx[2] = {1.0 - (double)dv0, (double)dv0};
+            const double wy[2] = {1.0 - (double)dv1, (double)dv1};
+            const double wz[2] = {1.0 - (double)dv2, (double)dv2};
+            // cell (ib+dd) is inside the 4x4x4 grid iff 0 <= ib+dd <= 3, per axis
+            const bool okx[2] = {ib0 >= 0 && ib0 <= 3, ib0 >= -1 && ib0 <= 2};
+            const bool oky[2] = {ib1 >= 0 && ib1 <= 3, ib1 >= -1 && ib1 <= 2};
+            const bool okz[2] = {ib2 >= 0 && ib2 <= 3, ib2 >= -1 && ib2 <= 2};
+            const int ax[2] = {ib0 * 12, ib0 * 12 + 12}, ay[2] = {ib1 * 48, ib1 * 48 + 48}, az[2] = {ib2 * kHistZ, ib2 * kHistZ + kHistZ};
+            const int i0 = M.idx[face][0], i1 = M.idx[face][1], i2 = M.idx[face][2];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int ddx = (c >> 2) & 1, ddy = (c >> 1) & 1, ddz = c & 1;
+                const bool ok = okx[ddx] && oky[ddy] && okz[ddz];
+                const float wt = (float)(wx[ddx] * wy[ddy] * wz[ddz]);
+                const float mw = mag * wt;
+                const int base = ax[ddx] + ay[ddy] + az[ddz];
+                stg[c * 3 + 0][rr ^ (c * 3 + 0)] = make_uint2(ok ? base + i0 : kHistDump, __float_as_uint(mw * b[0]));
+                stg[c * 3 + 1][rr ^ (c * 3 + 1)] = make_uint2(ok ? base + i1 : kHistDump, __float_as_uint(mw * b[1]));
+                stg[c * 3 + 2][rr ^ (c * 3 + 2)] = make_uint2(ok ? base + i2 : kHistDump, __float_as_uint(mw * b[2]));
+            }
+        }
+        __syncwarp();
+        const int cnt = __popc(mc);
+        if (cnt) {
+            uint2 cur = stg[l24][l24];  // column 0 ^ l24
+            for (int j = 0; j < cnt; ++j) {
+                const uint2 nxt = stg[l24][((j + 1) & 31) ^ l24];  // prefetch the next voxel's entry
+                if (lane < 24) myh[cur.x] += __uint_as_float(cur.y);
+                __syncwarp();
+                cur = nxt;
+            }
+        }
+    };
+
+    int qhead = 0, qn = 0;  // warp-uniform ring state
+    int py = wid % (wyp > 0 ? wyp : 1), pz = wid / (wyp > 0 ? wyp : 1);  // row-pair cursor (no division in the loop)
     for (int rp = wid; rp < npairs; rp += kDescWarps) {
         const int yy = y0 + 2 * py + half, zz = z0 + pz;
         py += kDescWarps;
@@ -991,84 +1071,47 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
         const int len = xhi - xlo + 1;
         const int len_other = __shfl_xor_sync(0xffffffffu, len, 16);
         const int iters = (max(len, len_other) + 15) >> 4;
+        const uint32_t pyz = ((uint32_t)(yy - y0) << 10) | ((uint32_t)(zz - z0) << 20);
         for (int it = 0; it < iters; ++it) {
             const int xx = xlo + it * 16 + hl;
-            bool contrib = false;
+            bool pass = false;
             if (xx <= xhi) {
                 const float dx = ((float)xx - cx) * u;
                 const float sq = dx * dx + dy * dy + dz * dz;
-                if (!(sq > r2)) {
+                if (!(sq > r2)) {  // :1270
                     float vb0 = (R0 * dx + R1 * dy + R2 * dz + desc_hw) * desc_bin_fctr;
                     float vb1 = (R3 * dx + R4 * dy + R5 * dz + desc_hw) * desc_bin_fctr;
                     float vb2 = (R6 * dx + R7 * dy + R8 * dz + desc_hw) * desc_bin_fctr;
                     vb0 -= 0.5f; vb1 -= 0.5f; vb2 -= 0.5f;
-                    if (!(vb0 <= -0.5f || vb1 <= -0.5f || vb2 <= -0.5f || vb0 >= 3.5f || vb1 >= 3.5f || vb2 >= 3.5f)) {
-                        const float weight = s3d_expf_ref(-0.5f * sq / s2);
-                        const ll i = (ll)xx + (ll)yy * ys + (ll)zz * zs;
-                        float gx = (float)(0.5 * (double)(g[i + 1] - g[i - 1]));
-                        float gy = (float)(0.5 * (double)(g[i + ys] - g[i - ys]));
-                        float gz = (float)(0.5 * (double)(g[i + zs] - g[i - zs]));
-                        gx *= iu; gy *= iu; gz *= iu;
-                        gx = gx * weight; gy = gy * weight; gz = gz * weight;  // SIFT3D_CVEC_SCALE :1322
-                        const float rx = R0 * gx + R1 * gy + R2 * gz;
-                        const float ry = R3 * gx + R4 * gy + R5 * gz;
-                        const float rz = R6 * gx + R7 * gy + R8 * gz;
-                        const float n2 = rx * rx + ry * ry + rz * rz;
-                        if (!(n2 < bary_eps)) {  // Check_intersect_faces :1544
-                            float b[3];
-                            const int face = find_face(M, rx, ry, rz, bary_eps, b[0], b[1], b[2]);
-                            if (face >= 0) {
-                                contrib = true;
-                                const float mag = sqrtf(n2);
-                                // Trilinear_interpolation_over_desc_debug :1466-1522
-                                const int ib0 = (int)vb0, ib1 = (int)vb1, ib2 = (int)vb2;  // truncation, Q12
-                                const float dv0 = vb0 - floorf(vb0), dv1 = vb1 - floorf(vb1), dv2 = vb2 - floorf(vb2);
-                                const double wx[2] = {1.0 - (double)dv0, (double)dv0};
-                                const double wy[2] = {1.0 - (double)dv1, (double)dv1};
-                                const double wz[2] = {1.0 - (double)dv2, (double)dv2};
-                                const int i0 = M.idx[face][0], i1 = M.idx[face][1], i2 = M.idx[face][2];
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) {
-                                    const int ddx = (c >> 2) & 1, ddy = (c >> 1) & 1, ddz = c & 1;
-                                    const int bx = ib0 + ddx, by = ib1 + ddy, bz = ib2 + ddz;
-                                    const bool ok = !(bx < 0 || by < 0 || bz < 0 || bx >= 4 || by >= 4 || bz >= 4);
-                                    const float wt = (float)(wx[ddx] * wy[ddy] * wz[ddz]);
-                                    const float mw = mag * wt;
-                                    const int base = (bx + by * 4) * 12 + bz * kHistZ;
-                                    stg[c * 3 + 0][lane] = make_uint2(ok ? base + i0 : kHistDump, __float_as_uint(mw * b[0]));
-                                    stg[c * 3 + 1][lane] = make_uint2(ok ? base + i1 : kHistDump, __float_as_uint(mw * b[1]));
-                                    stg[c * 3 + 2][lane] = make_uint2(ok ? base + i2 : kHistDump, __float_as_uint(mw * b[2]));
-                                }
-                            }
-                        }
-                    }
+                    pass = !(vb0 <= -0.5f || vb1 <= -0.5f || vb2 <= -0.5f || vb0 >= 3.5f || vb1 >= 3.5f || vb2 >= 3.5f);  // :1300
                 }
             }
-            unsigned m = __ballot_sync(0xffffffffu, contrib);  // also orders the staging writes
-            if (m) {
-                const int l24 = lane < 24 ? lane : 0;
-                uint2 cur = stg[l24][__ffs(m) - 1];
-                while (m) {
-                    m &= m - 1;
-                    const uint2 nxt = stg[l24][m ? __ffs(m) - 1 : 0];  // prefetch the next voxel's entry
-                    if (lane < 24) myh[cur.x] += __uint_as_float(cur.y);
-                    __syncwarp();
-                    cur = nxt;
-                }
+            const unsigned mp = __ballot_sync(0xffffffffu, pass);
+            if (pass) que[(qhead + qn + __popc(mp & lt_mask)) & 63] = (uint32_t)(xx - xs) | pyz;
+            qn += __popc(mp);
+            __syncwarp();
+            if (qn >= 32) {
+                heavy(que[(qhead + lane) & 63], true);
+                qhead = (qhead + 32) & 63;
+                qn -= 32;
             }
         }
     }
+    if (qn > 0) heavy(que[(qhead + lane) & 63], lane < qn);
     __syncthreads();
     // fixed-order sum over the per-warp histograms, then normalise / clamp / normalise (:1350-1358)
-    float v[3];
+    constexpr int kPer = (S3D_DESC_LEN + kDescThreads - 1) / kDescThreads;
+    float v[kPer];
     float ss = 0.0f;
 #pragma unroll
-    for (int e = 0; e < 3; ++e) {
-        const int i = tid + e * 256;                 // output index (x + 4y + 16z)*12 + v
-        const int hz = i / 192, hr = i - hz * 192;   // -> padded histogram address
+    for (int e = 0; e < kPer; ++e) {
+        const int i = tid + e * kDescThreads;        // output index (x + 4y + 16z)*12 + v
         float a = 0.0f;
+        if (i < S3D_DESC_LEN) {
+            const int hz = i / 192, hr = i - hz * 192;  // -> padded histogram address
 #pragma unroll
-        for (int w = 0; w < kDescWarps; ++w) a += S.hist[w][hz * kHistZ + hr];
+            for (int w = 0; w < kDescWarps; ++w) a += S.hist[w][hz * kHistZ + hr];
+        }
         v[e] = a;
         ss += a * a;
     }
@@ -1089,7 +1132,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
     const float trunc_thresh = (float)(0.2 * 128 / S3D_DESC_LEN);
     ss = 0.0f;
 #pragma unroll
-    for (int e = 0; e < 3; ++e) {
+    for (int e = 0; e < kPer; ++e) {
         v[e] *= norm_inv;
         v[e] = v[e] < trunc_thresh ? v[e] : trunc_thresh;
         ss += v[e] * v[e];
@@ -1098,7 +1141,10 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const s3d_key
     norm = (float)((double)sqrtf(norm) + DBL_EPSILON);
     norm_inv = (float)(1.0 / (double)norm);
 #pragma unroll
-    for (int e = 0; e < 3; ++e) desc_out[(size_t)k * S3D_DESC_LEN + tid + e * 256] = v[e] * norm_inv;
+    for (int e = 0; e < kPer; ++e) {
+        const int i = tid + e * kDescThreads;
+        if (i < S3D_DESC_LEN) desc_out[(size_t)k * S3D_DESC_LEN + i] = v[e] * norm_inv;
+    }
     if (tid == 0) {
         s3d_keypoint outk = kp;
         outk.Rotation[0] = R0; outk.Rotation[1] = R1; outk.Rotation[2] = R2;
