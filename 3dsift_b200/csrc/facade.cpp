@@ -1,0 +1,369 @@
+// facade.cpp — the reference's C++ classes (include/3dsift/cSIFT3D.h, cMatcher.h) as a thin host
+// layer over the C ABI (include/sift3d_b200.h).  No arithmetic of the hot path lives here.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <string>
+
+#include "3dsift/cMatcher.h"
+#include "3dsift/cSIFT3D.h"
+#include "sift3d_b200.h"
+
+namespace {
+
+// Host descriptor blocks of live extractors -> their device copies.  Lets muBruteMatcher skip the
+// host round trip when it is handed keypoints straight from GetKeypoints().
+struct Resident {
+    const float* d_desc;
+    int n;
+};
+std::mutex g_reg_mu;
+std::map<const float*, Resident> g_registry;
+
+bool quiet() {
+    static int q = -1;
+    if (q < 0) {
+        const char* e = getenv("SIFT3D_B200_VERBOSE");
+        q = (e && e[0] && e[0] != '0') ? 0 : 1;
+    }
+    return q != 0;
+}
+
+}  // namespace
+
+// ---- Util/common.h printers (reference: Src/Util/common.cpp:5-36) ---------------------------------
+std::ostream& operator<<(std::ostream& os, const SIFT_TimerPara& st) {
+    os << "\tTotal Time:" << st.d_TotalTime << "\n\tAllocation time:" << st.d_Allocation << "\n\tBuild-GSS time:" << st.d_BuildGSS
+       << "\n\tBuild-DOG time:" << st.d_BuildDOG << "\n\tDetection time:" << st.d_Detect
+       << "\n\tOrientation time:" << st.d_AssignOrientation << "\n\tExtract time:" << st.d_Extraction
+       << "\n\tRelease time:" << st.d_release << "\n\tMemory ovhead time:" << st.d_memoryOverhead << std::endl;
+    if (st.vD_octaveTime.size() == st.vD_octaveCompute.size())
+        for (size_t i = 0; i < st.vD_octaveTime.size(); ++i)
+            os << "\t----Octave " << i << "\ttime:" << st.vD_octaveTime[i] << "\tcompute-time:" << st.vD_octaveCompute[i] << std::endl;
+    return os;
+}
+
+std::ostream& operator<<(std::ostream& os, const SIFT_PROCESS& sp) {
+    os << "Reference:\n" << sp.REF << std::endl << "Target:\n" << sp.TAR << std::endl << "Match:\n" << sp.d_RegTime;
+    return os;
+}
+
+namespace CPUSIFT {
+
+int sift_thread_num = 1;
+
+// lexicographic (z, y, x) orders, Src/cSIFT3D.cc:40-75
+bool cmp_kp(const Keypoint& a, const Keypoint& b) {
+    if (a.rz != b.rz) return a.rz < b.rz;
+    if (a.ry != b.ry) return a.ry < b.ry;
+    return a.rx < b.rx;
+}
+bool cmp_kp_orig(const Keypoint& a, const Keypoint& b) {
+    if (a.z != b.z) return a.z < b.z;
+    if (a.y != b.y) return a.y < b.y;
+    return a.x < b.x;
+}
+
+struct CSIFT3D::Impl {
+    s3d_handle h = nullptr;
+    s3d_params prm;
+    int status = S3D_OK;
+    std::string err;
+    bool ran = false, keep = false;
+    int nx = 0, ny = 0, nz = 0;
+    std::vector<float> volume;        // kept only until KpSiftAlgorithm when KeepLevels() may still change
+    std::vector<Keypoint> filter;
+    float* global_descriptor = nullptr;   // K x 768 host block the Keypoint::desc pointers borrow from
+    std::vector<TexImage> gss, dog;
+    std::vector<std::vector<Keypoint> > level_extrema;
+    bool levels_fetched = false;
+
+    void fail(int rc) {
+        status = rc;
+        err = s3d_last_error();
+        std::cerr << "[sift3d_b200] " << err << std::endl;
+    }
+    void create() {
+        if (h || volume.empty()) return;
+        prm.keep_levels = keep ? 1 : 0;
+        int rc = s3d_create(volume.data(), nx, ny, nz, &prm, &h);
+        if (rc != S3D_OK) { h = nullptr; fail(rc); }
+        std::vector<float>().swap(volume);
+    }
+};
+
+CSIFT3D::CSIFT3D() : impl(new Impl) { s3d_default_params(&impl->prm); }
+
+CSIFT3D::CSIFT3D(float* volume, int x_dim, int y_dim, int z_dim, int num_kp_levels_, float sigma_default_,
+                 float sigma_n_default_, float peak_thresh_, float max_eig_thres_, float corner_thresh_)
+    : impl(new Impl) {
+    s3d_default_params(&impl->prm);
+    impl->prm.num_kp_levels = num_kp_levels_;
+    impl->prm.sigma_default = sigma_default_;
+    impl->prm.sigma_n_default = sigma_n_default_;
+    impl->prm.peak_thresh = peak_thresh_;
+    impl->prm.max_eig_thres = max_eig_thres_;
+    impl->prm.corner_thresh = corner_thresh_;
+    const char* dev = getenv("SIFT3D_B200_DEVICE");
+    if (dev && dev[0]) impl->prm.device = atoi(dev);
+    const char* keep = getenv("SIFT3D_B200_KEEP_LEVELS");
+    impl->keep = keep && keep[0] && keep[0] != '0';
+    impl->nx = x_dim; impl->ny = y_dim; impl->nz = z_dim;
+    // the reference's ctor copies the caller's buffer (Src/cSIFT3D.cc:161); the device copy is made
+    // at the first use so that KeepLevels() can still be set between construction and the run
+    if (volume && x_dim > 0 && y_dim > 0 && z_dim > 0) impl->volume.assign(volume, volume + (size_t)x_dim * y_dim * z_dim);
+}
+
+CSIFT3D::~CSIFT3D() {
+    if (impl->global_descriptor) {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        g_registry.erase(impl->global_descriptor);
+    }
+    if (impl->h) s3d_destroy(impl->h);
+    free(impl->global_descriptor);
+    delete impl;
+}
+
+void CSIFT3D::KeepLevels(bool keep) { impl->keep = keep; }
+int CSIFT3D::LastStatus() const { return impl->status; }
+const char* CSIFT3D::LastError() const { return impl->err.c_str(); }
+
+void CSIFT3D::KpSiftAlgorithm() {
+    if (impl->ran) return;  // single-shot
+    impl->ran = true;
+    impl->create();
+    if (!impl->h) return;
+    int rc = s3d_run(impl->h);
+    if (rc != S3D_OK) return impl->fail(rc);
+    int n = 0;
+    s3d_num_keypoints(impl->h, &n);
+    impl->filter.resize(n);
+    impl->global_descriptor = (float*)calloc((size_t)std::max(n, 1) * DESC_NUMEL, sizeof(float));
+    static_assert(sizeof(Keypoint) == sizeof(s3d_keypoint), "record layouts must agree");
+    rc = s3d_get_keypoints(impl->h, reinterpret_cast<s3d_keypoint*>(impl->filter.data()), impl->global_descriptor);
+    if (rc != S3D_OK) return impl->fail(rc);
+    for (int i = 0; i < n; ++i) impl->filter[i].desc = impl->global_descriptor + (size_t)i * DESC_NUMEL;  // Src/cSIFT3D.cc:495
+    const float* dd = nullptr;
+    int dn = 0;
+    if (n > 0 && s3d_device_descriptors(impl->h, &dd, &dn) == S3D_OK && dd) {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        g_registry[impl->global_descriptor] = Resident{dd, dn};
+    }
+    double t[10];
+    s3d_get_timers(impl->h, t);
+    m_timer.d_Allocation = t[0]; m_timer.d_BuildGSS = t[1]; m_timer.d_BuildDOG = t[2]; m_timer.d_Detect = t[3];
+    m_timer.d_AssignOrientation = t[4]; m_timer.d_Extraction = t[5]; m_timer.d_release = t[6]; m_timer.d_TotalTime = t[7];
+    m_timer.d_memoryOverhead = t[8] + t[9];
+    if (!quiet()) {
+        int ne = 0;
+        s3d_num_extrema(impl->h, &ne);
+        std::cout << "After detecting keypoints, kp size is : " << ne << "\nAfter Orientation, kp size is : " << n << std::endl;
+    }
+}
+
+void CSIFT3D::SetNumThreads(int t_num) { if (t_num > 0) sift_thread_num = t_num; }
+std::vector<Keypoint> CSIFT3D::GetKeypoints() { return impl->filter; }
+const float* CSIFT3D::DeviceDescriptors() const {
+    const float* dd = nullptr;
+    int n = 0;
+    return (impl->h && s3d_device_descriptors(impl->h, &dd, &n) == S3D_OK) ? dd : nullptr;
+}
+
+void CSIFT3D::Initialize() { impl->create(); }
+void CSIFT3D::Build_Gaussian_Scale_Space() { KpSiftAlgorithm(); }
+void CSIFT3D::Build_DOG_Scale_Space() { KpSiftAlgorithm(); }
+void CSIFT3D::Detect_KeyPoints() { KpSiftAlgorithm(); }
+void CSIFT3D::Assign_Orientation() { KpSiftAlgorithm(); }
+void CSIFT3D::Extract_Description() { KpSiftAlgorithm(); }
+void CSIFT3D::Release_SIFT() {}
+
+static void fetch_levels(s3d_handle h, int which, std::vector<TexImage>& out) {
+    out.clear();
+    for (int idx = 0;; ++idx) {
+        int d[3];
+        float meta[4];
+        if (s3d_level_info(h, which, idx, d, meta) != S3D_OK) break;
+        TexImage t(d[0], d[1], d[2]);
+        t.SetImageScale(meta[0]);
+        t.SetImageUnit(meta[1], meta[2], meta[3]);
+        t.MallocArrayMemory();
+        if (s3d_get_level(h, which, idx, t._Data) != S3D_OK) break;
+        out.push_back(t);
+    }
+}
+
+std::vector<TexImage>* CSIFT3D::GET_GSS() {
+    if (impl->h && impl->ran && impl->gss.empty()) fetch_levels(impl->h, 0, impl->gss);
+    return &impl->gss;
+}
+std::vector<TexImage>* CSIFT3D::GET_DOG() {
+    if (impl->h && impl->ran && impl->dog.empty()) fetch_levels(impl->h, 1, impl->dog);
+    return &impl->dog;
+}
+std::vector<std::vector<Keypoint> >* CSIFT3D::GET_LEVEL() {
+    // per (octave, level) raw detections in raster order (Src/cSIFT3D.cc:412,419)
+    if (impl->h && impl->ran && impl->level_extrema.empty()) {
+        int ne = 0, noct = 0;
+        s3d_num_extrema(impl->h, &ne);
+        s3d_num_octaves(impl->h, &noct);
+        std::vector<s3d_keypoint> kp(std::max(ne, 1));
+        std::vector<int> codes(std::max(ne, 1)), xyz5(5 * (size_t)std::max(ne, 1));
+        if (s3d_get_extrema(impl->h, kp.data(), codes.data(), xyz5.data()) == S3D_OK) {
+            const int L = impl->prm.num_kp_levels;
+            impl->level_extrema.assign((size_t)noct * L, std::vector<Keypoint>());
+            for (int i = 0; i < ne; ++i) {
+                Keypoint k;
+                memcpy(&k, &kp[i], sizeof(k));
+                k.x = (float)xyz5[5 * i]; k.y = (float)xyz5[5 * i + 1]; k.z = (float)xyz5[5 * i + 2];
+                k.desc = nullptr;
+                impl->level_extrema[(size_t)xyz5[5 * i + 3] * L + (xyz5[5 * i + 4] - 1)].push_back(k);
+            }
+        }
+    }
+    return &impl->level_extrema;
+}
+
+CSIFT3D* CSIFT3DFactory::CreateCSIFT3D(float* volume, int x_dim, int y_dim, int z_dim, int num_kp_levels, float sigma_default,
+                                       float sigma_n_default, float peak_thresh, float max_eig_thres, float corner_thresh) {
+    return new CSIFT3D(volume, x_dim, y_dim, z_dim, num_kp_levels, sigma_default, sigma_n_default, peak_thresh,
+                       max_eig_thres, corner_thresh);
+}
+
+CSIFT3D* CSIFT3DFactory::CreateCSIFT3D(std::string path_, int num_kp_levels, float sigma_default, float sigma_n_default,
+                                       float peak_thresh, float max_eig_thres, float corner_thresh) {
+    // ReadMatrixFromDisk<float> (Include/Util/matrixIO3D.h:22-64): int m, n, p then m*n*p floats
+    int dims[3] = {0, 0, 0};
+    std::vector<float> vol;
+    FILE* f = fopen(path_.c_str(), "rb");
+    if (!f) {
+        printf("Can't open input matrix file: %s.\n", path_.c_str());
+    } else {
+        if (fread(dims, sizeof(int), 3, f) == 3 && dims[0] > 0 && dims[1] > 0 && dims[2] > 0) {
+            vol.resize((size_t)dims[0] * dims[1] * dims[2]);
+            if (fread(vol.data(), sizeof(float), vol.size(), f) != vol.size()) {
+                printf("Error reading matrix from disk file: %s.\n", path_.c_str());
+                vol.clear();
+            }
+        } else {
+            printf("Error reading matrix header from disk file: %s.\n", path_.c_str());
+        }
+        fclose(f);
+    }
+    std::cout << dims[0] << " " << dims[1] << " " << dims[2] << std::endl;  // Src/cSIFT3D.cc:118
+    return new CSIFT3D(vol.empty() ? nullptr : vol.data(), dims[0], dims[1], dims[2], num_kp_levels, sigma_default,
+                       sigma_n_default, peak_thresh, max_eig_thres, corner_thresh);
+}
+
+void DownSample_3D(TexImage* src, TexImage* dst) {
+    dst->SetImageSize(src->_nx / 2, src->_ny / 2, src->_nz / 2);
+    dst->MallocArrayMemory();
+    if (s3d_downsample(src->_Data, src->_nx, src->_ny, src->_nz, dst->_Data) != S3D_OK)
+        std::cerr << "[sift3d_b200] " << s3d_last_error() << std::endl;
+}
+
+void GaussianSmooth_3D(TexImage* src, TexImage* dst, float sigma) {
+    dst->SetImageSize(src->_nx, src->_ny, src->_nz);
+    dst->SetImageUnit(src->_ux, src->_uy, src->_uz);
+    dst->MallocArrayMemory();
+    if (s3d_gaussian_smooth(src->_Data, src->_nx, src->_ny, src->_nz, sigma, dst->_Data) != S3D_OK)
+        std::cerr << "[sift3d_b200] " << s3d_last_error() << std::endl;
+}
+
+// ---- matcher ------------------------------------------------------------------------------------
+
+muBruteMatcher::muBruteMatcher() {}
+float muBruteMatcher::getCalculationTime() { return totalTime; }
+std::vector<float> muBruteMatcher::getGlodenDistSquare() { return gDist; }
+std::vector<float> muBruteMatcher::getSilverDistSquare() { return sDist; }
+std::vector<int> muBruteMatcher::getGlodenIdx() { return gIdx; }
+std::vector<int> muBruteMatcher::getSilverIdx() { return sIdx; }
+
+// Keypoint::desc pointers (Src/cMatcher.cc:20) -> one n x 768 block.  Returns the block and whether
+// it lives on the device (descriptors of a live extractor, no copy) — else a host pointer, which
+// is the caller's own memory when the pointers already form base + 768*i, or `scratch`.
+static const float* gather(const std::vector<Keypoint>& kp, std::vector<float>& scratch, int* on_device) {
+    *on_device = 0;
+    const size_t n = kp.size();
+    if (n == 0) return nullptr;
+    bool contiguous = kp[0].desc != nullptr;
+    for (size_t i = 1; i < n && contiguous; ++i) contiguous = kp[i].desc == kp[0].desc + i * DESC_LENGTH;
+    if (contiguous) {
+        std::lock_guard<std::mutex> lk(g_reg_mu);
+        auto it = g_registry.find(kp[0].desc);
+        if (it != g_registry.end() && (size_t)it->second.n == n) {
+            *on_device = 1;
+            return it->second.d_desc;
+        }
+        return kp[0].desc;
+    }
+    scratch.assign(n * DESC_LENGTH, 0.0f);
+    for (size_t i = 0; i < n; ++i)
+        if (kp[i].desc) memcpy(&scratch[i * DESC_LENGTH], kp[i].desc, sizeof(float) * DESC_LENGTH);
+    return scratch.data();
+}
+
+void muBruteMatcher::run(int type, std::vector<Cvec>& refMatch, std::vector<Cvec>& tarMatch, const std::vector<Keypoint>& ref_kp,
+                         const std::vector<Keypoint>& tar_kp, double thr) {
+    const int n_ref = (int)ref_kp.size(), n_tar = (int)tar_kp.size();
+    std::vector<float> s_ref, s_tar;
+    int ref_dev = 0, tar_dev = 0;
+    const float* p_ref = gather(ref_kp, s_ref, &ref_dev);
+    const float* p_tar = gather(tar_kp, s_tar, &tar_dev);
+    // the reference (re)initialises its work vectors on every call (Src/cMatcher.cc:152-161)
+    gDist.assign(n_ref, 0.0f); sDist.assign(n_ref, 0.0f); gIdx.assign(n_ref, -1); sIdx.assign(n_ref, -1);
+    gDist2.assign(n_tar, 0.0f); sDist2.assign(n_tar, 0.0f); gIdx2.assign(n_tar, -1); sIdx2.assign(n_tar, -1);
+    std::vector<int> pr(std::max(n_ref, 1)), pt(std::max(n_ref, 1));
+    int np = 0;
+    double times[3] = {0, 0, 0};
+    status = s3d_match_ex(type, p_ref, n_ref, ref_dev, p_tar, n_tar, tar_dev, thr, gIdx.data(), gDist.data(), sIdx.data(),
+                          sDist.data(), gIdx2.data(), gDist2.data(), sIdx2.data(), sDist2.data(), pr.data(), pt.data(), &np, times);
+    if (status != S3D_OK) {
+        std::cerr << "[sift3d_b200] " << s3d_last_error() << std::endl;
+        return;
+    }
+    for (int i = 0; i < np; ++i) {  // toCvec, Src/cMatcher.cc:99-112 (append)
+        const Keypoint& a = ref_kp[pr[i]];
+        const Keypoint& b = tar_kp[pt[i]];
+        refMatch.push_back(Cvec(a.rx, a.ry, a.rz));
+        tarMatch.push_back(Cvec(b.rx, b.ry, b.rz));
+    }
+    matchTime = (float)times[0]; revMatchTime = (float)times[1]; totalTime = (float)times[2];
+}
+
+void muBruteMatcher::injectMatch(std::vector<Cvec>& r, std::vector<Cvec>& t, const std::vector<Keypoint>& rk,
+                                 const std::vector<Keypoint>& tk, const double thr) { run(1, r, t, rk, tk, thr); }
+void muBruteMatcher::bijectMatch(std::vector<Cvec>& r, std::vector<Cvec>& t, const std::vector<Keypoint>& rk,
+                                 const std::vector<Keypoint>& tk, const double thr) { run(2, r, t, rk, tk, thr); }
+void muBruteMatcher::enhancedMatch(std::vector<Cvec>& r, std::vector<Cvec>& t, const std::vector<Keypoint>& rk,
+                                   const std::vector<Keypoint>& tk, const double thr) { run(3, r, t, rk, tk, thr); }
+
+// "%.5lf,%.5lf,%.5lf\n" per point (Src/cUtil.cc:938-954)
+void write_sift_kp(std::vector<Cvec>& kp, const char* file_name) {
+    FILE* f = fopen(file_name, "w");
+    if (!f) return;
+    for (const Cvec& c : kp) fprintf(f, "%.5lf,%.5lf,%.5lf\n", c.x, c.y, c.z);
+    printf("sift keypoint size:%zd\n", kp.size());
+    fclose(f);
+}
+
+void read_sift_kp(const char* file_name, std::vector<Cvec>& kp) {
+    std::ifstream in(file_name);
+    std::string line;
+    int n = 0;
+    while (std::getline(in, line)) {
+        float v[3] = {0, 0, 0};
+        std::stringstream ss(line);
+        std::string tok;
+        for (int k = 0; k < 3 && std::getline(ss, tok, ','); ++k) v[k] = (float)atof(tok.c_str());
+        kp.push_back(Cvec(v[0], v[1], v[2]));
+        ++n;
+    }
+    std::cout << "File:" << file_name << ", number of points:" << n << std::endl;
+}
+
+}  // namespace CPUSIFT

@@ -789,6 +789,26 @@ int s3d_get_level(s3d_handle c, int which, int idx, float* out) {
     return S3D_OK;
 }
 
+int s3d_level_info(s3d_handle c, int which, int idx, int* dims3, float* meta4) {
+    if (!c || !dims3 || !meta4) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    const int per = which == 0 ? c->G : c->D;
+    if (which < 0 || which > 1 || idx < 0 || idx >= c->noct * per) return fail(S3D_ERR_ARG, "level index out of range");
+    const int o = idx / per, s = idx % per;
+    for (int k = 0; k < 3; k++) dims3[k] = c->dims[o][k];
+    meta4[0] = host_level_scale(o, s, c->L, c->prm.sigma_default);
+    meta4[1] = meta4[2] = meta4[3] = (float)(1 << o);
+    return S3D_OK;
+}
+
+int s3d_device_descriptors(s3d_handle c, const float** d_desc, int* n) {
+    if (!c || !d_desc || !n) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    *d_desc = c->d_desc;
+    *n = c->n_kps;
+    return S3D_OK;
+}
+
 int s3d_get_input(s3d_handle c, float* out) {
     clear_error();
     if (!c || !out) return fail(S3D_ERR_ARG, "null argument");

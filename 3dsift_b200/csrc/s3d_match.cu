@@ -361,6 +361,13 @@ int s3d_match_device(int type, const float* d_ref, int n_ref, const float* d_tar
 int s3d_match(int type, const float* ref_desc, int n_ref, const float* tar_desc, int n_tar, double thr, int* gIdx,
               float* gDist, int* sIdx, float* sDist, int* gIdx2, float* gDist2, int* sIdx2, float* sDist2, int* pair_ref,
               int* pair_tar, int* n_pairs, double* times3) {
+    return s3d_match_ex(type, ref_desc, n_ref, 0, tar_desc, n_tar, 0, thr, gIdx, gDist, sIdx, sDist, gIdx2, gDist2, sIdx2,
+                        sDist2, pair_ref, pair_tar, n_pairs, times3);
+}
+
+int s3d_match_ex(int type, const float* ref_desc, int n_ref, int ref_on_device, const float* tar_desc, int n_tar,
+                 int tar_on_device, double thr, int* gIdx, float* gDist, int* sIdx, float* sDist, int* gIdx2,
+                 float* gDist2, int* sIdx2, float* sDist2, int* pair_ref, int* pair_tar, int* n_pairs, double* times3) {
     clear_error();
     if (type < 1 || type > 3) return fail(S3D_ERR_ARG, "match type %d (1 inject, 2 biject, 3 enhanced)", type);
     if (n_ref < 0 || n_tar < 0 || (n_ref > 0 && !ref_desc) || (n_tar > 0 && !tar_desc)) return fail(S3D_ERR_ARG, "bad argument");
@@ -376,19 +383,23 @@ int s3d_match(int type, const float* ref_desc, int n_ref, const float* tar_desc,
     cudaEventCreate(&e1);
     int rc = S3D_OK;
     auto body = [&]() -> int {
-        S3D_CUDA(cudaMallocAsync((void**)&d_ref, sizeof(float) * kD * nr, st));
-        S3D_CUDA(cudaMallocAsync((void**)&d_tar, sizeof(float) * kD * nt, st));
+        if (!(ref_on_device && n_ref)) S3D_CUDA(cudaMallocAsync((void**)&d_ref, sizeof(float) * kD * nr, st));
+        if (!(tar_on_device && n_tar)) S3D_CUDA(cudaMallocAsync((void**)&d_tar, sizeof(float) * kD * nt, st));
         S3D_CUDA(cudaMallocAsync((void**)&d_f, sizeof(float) * 2 * (nr + nt), st));
         S3D_CUDA(cudaMallocAsync((void**)&d_i, sizeof(int) * (4 * nr + 2 * nt + 4), st));
-        if (n_ref) S3D_CUDA(cudaMemcpyAsync(d_ref, ref_desc, sizeof(float) * kD * (size_t)n_ref, cudaMemcpyHostToDevice, st));
-        if (n_tar) S3D_CUDA(cudaMemcpyAsync(d_tar, tar_desc, sizeof(float) * kD * (size_t)n_tar, cudaMemcpyHostToDevice, st));
+        const float* q_ref = d_ref;
+        const float* q_tar = d_tar;
+        if (ref_on_device && n_ref) q_ref = ref_desc;
+        else if (n_ref) S3D_CUDA(cudaMemcpyAsync(d_ref, ref_desc, sizeof(float) * kD * (size_t)n_ref, cudaMemcpyHostToDevice, st));
+        if (tar_on_device && n_tar) q_tar = tar_desc;
+        else if (n_tar) S3D_CUDA(cudaMemcpyAsync(d_tar, tar_desc, sizeof(float) * kD * (size_t)n_tar, cudaMemcpyHostToDevice, st));
         float *dg = d_f, *ds = d_f + nr, *dg2 = d_f + 2 * nr, *ds2 = d_f + 2 * nr + nt;
         int *ig = d_i, *is = d_i + nr, *pr = d_i + 2 * nr, *pt = d_i + 3 * nr, *ig2 = d_i + 4 * nr, *is2 = d_i + 4 * nr + nt,
             *np = d_i + 4 * nr + 2 * nt;
         S3D_CUDA(cudaMemsetAsync(np, 0, sizeof(int), st));
         S3D_CUDA(cudaMemsetAsync(d_f, 0, sizeof(float) * 2 * (nr + nt), st));
         S3D_CUDA(cudaEventRecord(e0, st));
-        S3D_TRY(s3d_match_device(type, d_ref, n_ref, d_tar, n_tar, thr, ig, dg, is, ds, ig2, dg2, is2, ds2, pr, pt, np, st));
+        S3D_TRY(s3d_match_device(type, q_ref, n_ref, q_tar, n_tar, thr, ig, dg, is, ds, ig2, dg2, is2, ds2, pr, pt, np, st));
         S3D_CUDA(cudaEventRecord(e1, st));
         int h_np = 0;
         S3D_CUDA(cudaMemcpyAsync(&h_np, np, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -117,6 +117,12 @@ S3D_API int s3d_get_extrema(s3d_handle h, s3d_keypoint* kp, int* codes, int* xyz
 /* GET_GSS() / GET_DOG()  Include/cSIFT3D.h:169-174.  which: 0 = Gaussian level idx (o*(L+3)+i),
  * 1 = DoG level idx (o*(L+2)+i).  Needs keep_levels. */
 S3D_API int s3d_get_level(s3d_handle h, int which, int idx, float* out);
+/* Level metadata as TexImage carries it (Include/Util/cTexImage.h:13-25): dims3 = nx,ny,nz;
+ * meta4 = scale, ux, uy, uz (Src/cUtil.cc:209-224). */
+S3D_API int s3d_level_info(s3d_handle h, int which, int idx, int* dims3, float* meta4);
+/* Device address of the K x 768 descriptor block of a finished extraction (valid until
+ * s3d_destroy): lets a matcher consume descriptors without the host round trip. */
+S3D_API int s3d_device_descriptors(s3d_handle h, const float** d_desc, int* n);
 /* The normalised input (Host_Im after data_scale, Src/cSIFT3D.cc:162). */
 S3D_API int s3d_get_input(s3d_handle h, float* out);
 /* Per-level detection thresholds peak_thresh*max|DoG| (Src/cSIFT3D.cc:384-385), o*L + (i-1). */
@@ -159,6 +165,12 @@ S3D_API int s3d_downsample(const float* src, int nx, int ny, int nz, float* dst)
 S3D_API int s3d_match(int type, const float* ref_desc, int n_ref, const float* tar_desc, int n_tar, double thr,
                       int* gIdx, float* gDist, int* sIdx, float* sDist, int* gIdx2, float* gDist2, int* sIdx2,
                       float* sDist2, int* pair_ref, int* pair_tar, int* n_pairs, double* times3);
+/* s3d_match where either descriptor set may already live in device memory (ref_on_device /
+ * tar_on_device != 0); outputs are HOST arrays as in s3d_match. */
+S3D_API int s3d_match_ex(int type, const float* ref_desc, int n_ref, int ref_on_device, const float* tar_desc, int n_tar,
+                         int tar_on_device, double thr, int* gIdx, float* gDist, int* sIdx, float* sDist, int* gIdx2,
+                         float* gDist2, int* sIdx2, float* sDist2, int* pair_ref, int* pair_tar, int* n_pairs,
+                         double* times3);
 /* Same with DEVICE-resident descriptor sets and DEVICE outputs (HBM-resident timing; the
  * extract→match handoff of SURVEY.md §8f-1).  stream is a cudaStream_t (0 = default). */
 S3D_API int s3d_match_device(int type, const float* d_ref, int n_ref, const float* d_tar, int n_tar, double thr,

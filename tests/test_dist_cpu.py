@@ -1,0 +1,139 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU orchestration in 3dsift_b200/dist.py: shard
+bounds, global index offsets, all-gather layout, the (dot desc, index asc) merge contract and the
+replicated filters — driven with a checker-backed ops object (the CUDA primitives need a GPU and are
+covered by tests/test_gpu_match.py::test_sharded_database_merge_equals_unsharded)."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FLT_MIN = float(np.finfo(np.float32).tiny)
+
+
+class NumpyOps:
+    """Reference semantics of the primitives (Src/cMatcher.cc), numpy only — test side."""
+
+    def to_device(self, a):
+        return np.ascontiguousarray(a, dtype=np.float32)
+
+    def top2(self, q, db, offset, mask):
+        nq = len(q)
+        d1 = np.full(nq, FLT_MIN, np.float64); d2 = np.full(nq, FLT_MIN, np.float64)
+        i1 = np.full(nq, -1, np.int32); i2 = np.full(nq, -1, np.int32)
+        for i in range(nq):
+            if mask is not None and mask[i] == 0:
+                continue
+            for j in range(len(db)):
+                s = float(np.add.accumulate((q[i] * db[j]).astype(np.float64))[-1])   # float product, sequential double sum
+                if s > d1[i]:
+                    d2[i], i2[i], d1[i], i1[i] = d1[i], i1[i], s, j + offset
+                elif s > d2[i]:
+                    d2[i], i2[i] = s, j + offset
+        return d1, i1, d2, i2
+
+    def merge(self, D1, I1, D2, I2, mask):
+        parts, nq = D1.shape
+        gD = np.zeros(nq, np.float32); sD = np.zeros(nq, np.float32)
+        gI = np.full(nq, -1, np.int32); sI = np.full(nq, -1, np.int32)
+        for i in range(nq):
+            if mask is not None and mask[i] == 0:
+                continue
+            c = [(D1[p, i], I1[p, i]) for p in range(parts) if I1[p, i] >= 0] + [(D2[p, i], I2[p, i]) for p in range(parts) if I2[p, i] >= 0]
+            c.sort(key=lambda t: (-t[0], t[1]))
+            b1 = c[0] if len(c) > 0 else (FLT_MIN, -1)
+            b2 = c[1] if len(c) > 1 else (FLT_MIN, -1)
+            gD[i], gI[i], sD[i], sI[i] = np.float32(2 - 2 * b1[0]), b1[1], np.float32(2 - 2 * b2[0]), b2[1]
+        return gD, gI, sD, sI
+
+    def ratio_filter(self, gI, gD, sD, thr):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rej = (gI >= 0) & ((gD / sD).astype(np.float64) >= thr * thr)
+        gI[rej] *= -1
+
+    def count_mask(self, gI, n_tar, count_thres):
+        cnt = np.bincount(gI[gI >= 0], minlength=n_tar)
+        return (cnt > count_thres).astype(np.int32)
+
+    def biject_filter(self, gI, mask, gI2):
+        for i in range(len(gI)):
+            m = gI[i]
+            if m < 0 or mask[m] == 0:
+                continue
+            if gI2[m] != i:
+                gI[i] *= -1
+
+    def all_gather(self, x, group=None):
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        outs = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(outs, t, group=group)
+        return np.stack([o.numpy() for o in outs])
+
+    def to_numpy(self, x):
+        return np.asarray(x)
+
+
+def _worker(rank, world, port, ref, tar, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("3dsift_b200.dist")
+    res = {t: d.match_sharded(t, ref, tar, 0.85, ops=NumpyOps()) for t in (1, 2, 3)}
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds():
+    d = importlib.import_module("3dsift_b200.dist")
+    assert d.shard_bounds(10, 3) == [0, 4, 7, 10]
+    assert d.shard_bounds(2, 4) == [0, 1, 2, 2, 2]
+    assert d.shard_bounds(0, 2) == [0, 0, 0]
+    for n in (1, 7, 64, 1000):
+        for w in (1, 2, 4, 8):
+            b = d.shard_bounds(n, w)
+            assert b[0] == 0 and b[-1] == n and all(0 <= b[i + 1] - b[i] <= -(-n // w) for i in range(w))
+
+
+@pytest.mark.timeout(300)
+def test_sharded_match_world2_gloo_equals_oracle(port, synth):
+    import torch.multiprocessing as mp
+    ref, tar, _ = synth.d_synth_pair(36, seed=8, k_tar=41)
+    tar[30] = tar[5]     # a tie whose two members land in different shards (bounds [0,21,41])
+    ref[4] = 0.0         # never matches
+    want = {t: port.match(t, ref, tar, 0.85) for t in (1, 2, 3)}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port_no, ref, tar, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        for t in (1, 2, 3):
+            for k in ("gIdx", "sIdx", "gDist", "sDist", "pairs"):
+                assert np.array_equal(got[rank][t][k], want[t][k]), (rank, t, k)
+            if t != 1:
+                searched = want[t]["gIdx2"] != -1
+                assert np.array_equal(got[rank][t]["gIdx2"], want[t]["gIdx2"])
+                assert np.array_equal(got[rank][t]["gDist2"][searched], want[t]["gDist2"][searched])
+    assert want[1]["gIdx"][4] == -1 and abs(want[1]["gIdx"]).max() > 21   # both shards contribute winners
+
+
+def test_single_process_path_equals_oracle(port, synth):
+    d = importlib.import_module("3dsift_b200.dist")
+    ref, tar, _ = synth.d_synth_pair(20, seed=9, k_tar=17)
+    for t in (1, 3):
+        got = d.match_sharded(t, ref, tar, 0.85, ops=NumpyOps())
+        want = port.match(t, ref, tar, 0.85)
+        assert np.array_equal(got["gIdx"], want["gIdx"]) and np.array_equal(got["pairs"], want["pairs"])

@@ -127,3 +127,49 @@ def test_sharded_database_merge_equals_unsharded(s3d, synth, port):
         assert np.array_equal(gI.cpu().numpy(), want["gIdx"]), shards
         assert np.array_equal(sI.cpu().numpy(), want["sIdx"]), shards
         assert np.array_equal(gD.cpu().numpy(), want["gDist"]), shards
+
+
+def test_match_sharded_cudaops_single_rank(s3d, synth, port):
+    dist_mod = __import__("importlib").import_module("3dsift_b200.dist")
+    ref, tar, _ = synth.d_synth_pair(300, seed=55, k_tar=280)
+    for t in (1, 2, 3):
+        got = dist_mod.match_sharded(t, ref, tar, 0.85)
+        want = port.match(t, ref, tar, 0.85)
+        for k in ("gIdx", "sIdx", "gDist", "sDist", "pairs"):
+            assert np.array_equal(got[k], want[k]), (t, k)
+
+
+def _nccl_worker(rank, world, port_no, ref, tar, q):
+    import os, sys, importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch, torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port_no)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    d = importlib.import_module("3dsift_b200.dist")
+    res = {t: d.match_sharded(t, ref, tar, 0.85) for t in (1, 3)}
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_match_sharded_nccl_two_gpus(s3d, synth, port):
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ref, tar, _ = synth.d_synth_pair(600, seed=66, k_tar=650)
+    want = {t: port.match(t, ref, tar, 0.85) for t in (1, 3)}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, 29650, ref, tar, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for rank in (0, 1):
+        for t in (1, 3):
+            for k in ("gIdx", "sIdx", "gDist", "sDist", "pairs"):
+                assert np.array_equal(got[rank][t][k], want[t][k]), (rank, t, k)
