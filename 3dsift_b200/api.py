@@ -92,6 +92,12 @@ def lib():
     L.s3d_count_mask_device.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp]
     L.s3d_biject_filter_device.argtypes = [vp, C.c_int, vp, vp, vp]
     L.s3d_pairs_device.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.s3d_match_ex.argtypes = [C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_double] + [vp] * 12
+    L.s3d_set_match_path.argtypes = [C.c_int]
+    L.s3d_match_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
+    L.s3d_match_stats.restype = None
+    L.s3d_level_info.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.s3d_device_descriptors.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int)]
     _lib = L
     return L
 
@@ -124,6 +130,21 @@ def launch_count():
 
 def selftest(device=-1):
     check(lib().s3d_selftest(device))
+
+
+MATCH_AUTO, MATCH_EXACT, MATCH_TENSOR = 0, 1, 2
+
+
+def set_match_path(path):
+    """0 auto / 1 exact CUDA-core kernel / 2 tensor-core candidate pass (results are identical)."""
+    check(lib().s3d_set_match_path(int(path)))
+
+
+def match_stats(reset=False):
+    """(rows searched on the tensor-core path, rows that needed the exact fallback)."""
+    a, b = C.c_ulonglong(), C.c_ulonglong()
+    lib().s3d_match_stats(C.byref(a), C.byref(b), int(reset))
+    return int(a.value), int(b.value)
 
 
 # Defaults of CSIFT3DFactory::CreateCSIFT3D, Include/cSIFT3D.h:187-202 (values :13-21)

@@ -10,44 +10,11 @@
 #include <vector>
 
 #include "s3d_common.h"
+#include "s3d_match_internal.h"
 
 namespace s3d {
 
 constexpr int kD = S3D_DESC_LEN;
-
-struct Top2 {
-    double d1, d2;
-    int i1, i2;
-};
-
-__device__ __forceinline__ void top2_init(Top2& t) {
-    t.d1 = (double)FLT_MIN; t.d2 = (double)FLT_MIN;  // Src/cMatcher.cc:54-55
-    t.i1 = -1; t.i2 = -1;
-}
-
-// is (da, ia) ahead of (db, ib) in (dot desc, index asc)?  index -1 = empty slot (never ahead)
-__device__ __forceinline__ bool ahead(double da, int ia, double db, int ib) {
-    if (ia < 0) return false;
-    if (ib < 0) return true;
-    return da > db || (da == db && ia < ib);
-}
-
-// Insert one candidate (s, j).  Candidates with s <= FLT_MIN never enter (strict '>' against the
-// FLT_MIN initial values, Src/cMatcher.cc:60,66).
-__device__ __forceinline__ void top2_push(Top2& t, double s, int j) {
-    if (!(s > (double)FLT_MIN)) return;
-    if (ahead(s, j, t.d1, t.i1)) {
-        t.d2 = t.d1; t.i2 = t.i1;
-        t.d1 = s; t.i1 = j;
-    } else if (ahead(s, j, t.d2, t.i2)) {
-        t.d2 = s; t.i2 = j;
-    }
-}
-
-__device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
-    if (b.i1 >= 0) top2_push(a, b.d1, b.i1);
-    if (b.i2 >= 0) top2_push(a, b.d2, b.i2);
-}
 
 // Exact tile kernel: CTA = 64 queries x 64 database rows per step, 256 threads, each thread owns a
 // 4x4 block of (query, db) pairs (db rows interleaved by 16 to keep shared reads conflict-free) and walks k = 0..767 in order with a k-chunked shared-memory
@@ -55,8 +22,9 @@ __device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
 // `db_per_cta`-sized slices (gridDim.y) and merged by top2_merge_kernel.
 constexpr int kTQ = 64, kTD = 64, kTK = 32;
 
-__global__ void __launch_bounds__(256) top2_exact_kernel(const float* __restrict__ q, int nq, const float* __restrict__ db,
-                                                         int nd, int db_offset, const int* __restrict__ mask,
+// qlist (may be null) maps the nq listed queries to rows of q.
+__global__ void __launch_bounds__(256) top2_exact_kernel(const float* __restrict__ q, const int* __restrict__ qlist, int nq,
+                                                         const float* __restrict__ db, int nd, int db_offset,
                                                          int db_per_cta, Top2* __restrict__ part) {
     __shared__ float sq[kTK][kTQ + 1];
     __shared__ float sd[kTK][kTD + 1];
@@ -80,7 +48,7 @@ __global__ void __launch_bounds__(256) top2_exact_kernel(const float* __restrict
             for (int e = tid; e < kTQ * kTK; e += 256) {
                 const int row = e / kTK, kk = e % kTK;
                 const int qi = q0 + row, di = d0 + row;
-                sq[kk][row] = qi < nq ? q[(size_t)qi * kD + k0 + kk] : 0.0f;
+                sq[kk][row] = qi < nq ? q[(size_t)(qlist ? qlist[qi] : qi) * kD + k0 + kk] : 0.0f;
                 sd[kk][row] = di < dend ? db[(size_t)di * kD + k0 + kk] : 0.0f;
             }
             __syncthreads();
@@ -113,18 +81,31 @@ __global__ void __launch_bounds__(256) top2_exact_kernel(const float* __restrict
         Top2 r = red[tid][0];
         for (int j = 1; j < 16; ++j) top2_merge(r, red[tid][j]);
         const int qi = q0 + tid;
-        if (qi < nq) {
-            if (mask && mask[qi] == 0) top2_init(r);
-            part[(size_t)blockIdx.y * nq + qi] = r;
-        }
+        if (qi < nq) part[(size_t)blockIdx.y * nq + qi] = r;
     }
 }
 
-// Merge `parts` partial lists per query and emit calMatches' outputs (Src/cMatcher.cc:71-77);
-// masked-out queries get gIdx = -1 and nothing else (:48-52).
-__global__ void __launch_bounds__(256) top2_merge_kernel(int parts, int nq, const Top2* __restrict__ part,
-                                                         const int* __restrict__ mask, double* d1o, int* i1o, double* d2o,
-                                                         int* i2o, float* gDist, int* gIdx, float* sDist, int* sIdx) {
+// Merge `parts` partial lists of the listed queries into out[orig] (merging INTO the existing
+// entry when `accumulate`, which the tensor-core fallback rows use to overwrite theirs).
+__global__ void __launch_bounds__(256) top2_merge_kernel(int parts, int nq, const int* __restrict__ qlist,
+                                                         const Top2* __restrict__ part, Top2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    Top2 r = part[i];
+    for (int p = 1; p < parts; ++p) top2_merge(r, part[(size_t)p * nq + i]);
+    out[qlist ? qlist[i] : i] = r;
+}
+
+__global__ void top2_fill_kernel(Top2* t, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) top2_init(t[i]);
+}
+
+// calMatches' outputs (Src/cMatcher.cc:71-77); masked-out queries get gIdx = -1 and nothing else
+// (:48-52).  Optionally also the raw (double dot, index) pairs for multi-GPU merging.
+__global__ void __launch_bounds__(256) top2_finalize_kernel(int nq, const Top2* __restrict__ top, const int* __restrict__ mask,
+                                                            double* d1o, int* i1o, double* d2o, int* i2o, float* gDist,
+                                                            int* gIdx, float* sDist, int* sIdx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     if (mask && mask[i] == 0) {
@@ -132,8 +113,7 @@ __global__ void __launch_bounds__(256) top2_merge_kernel(int parts, int nq, cons
         if (i1o) { i1o[i] = -1; i2o[i] = -1; d1o[i] = (double)FLT_MIN; d2o[i] = (double)FLT_MIN; }
         return;
     }
-    Top2 r = part[i];
-    for (int p = 1; p < parts; ++p) top2_merge(r, part[(size_t)p * nq + i]);
+    const Top2 r = top[i];
     if (i1o) { d1o[i] = r.d1; i1o[i] = r.i1; d2o[i] = r.d2; i2o[i] = r.i2; }
     if (gIdx) {
         gDist[i] = (float)(2 - 2 * r.d1);
@@ -141,6 +121,27 @@ __global__ void __launch_bounds__(256) top2_merge_kernel(int parts, int nq, cons
         gIdx[i] = r.i1;
         sIdx[i] = r.i2;
     }
+}
+
+// ordered list of the queries with mask != 0 — one CTA
+__global__ void __launch_bounds__(1024) mask_list_kernel(const int* __restrict__ mask, int n, int* list, int* count) {
+    __shared__ int part[1024];
+    const int per = (n + 1023) / 1024;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += mask[i] != 0;
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;
+    for (int i = b; i < e; ++i)
+        if (mask[i] != 0) list[run++] = i;
+    if (threadIdx.x == 1023) *count = part[1023];
 }
 
 // Merge across shards given as separate arrays laid out [part][nq] (multi-GPU gather).
@@ -230,25 +231,66 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
     if (i < n) p[i] = v;
 }
 
-// One search direction on device arrays: partial lists + merge.
-static int search_device(const float* d_q, int nq, const float* d_db, int nd, int db_offset, const int* d_mask,
-                         double* d1, int* i1, double* d2, int* i2, float* gDist, int* gIdx, float* sDist, int* sIdx,
-                         cudaStream_t st) {
-    if (nq <= 0) return S3D_OK;
+// 0 = auto (tensor cores for large searches), 1 = exact CUDA-core kernel only, 2 = tensor cores always
+static std::atomic<int> g_match_path{0};
+static std::atomic<unsigned long long> g_tc_rows{0}, g_fb_rows{0};
+
+// Exact CUDA-core search of the listed queries; results go to out[orig].
+static int exact_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, Top2* d_out,
+                        cudaStream_t st) {
+    if (nql <= 0) return S3D_OK;
     // split the database so the grid fills the GPU: ~148*4 CTAs
-    const int qtiles = (nq + kTQ - 1) / kTQ;
+    const int qtiles = (nql + kTQ - 1) / kTQ;
     int parts = std::max(1, std::min((nd + kTD - 1) / kTD, (148 * 4 + qtiles - 1) / qtiles));
     int db_per_cta = ((nd + parts - 1) / parts + kTD - 1) / kTD * kTD;
     if (db_per_cta < kTD) db_per_cta = kTD;
     parts = std::max(1, (nd + db_per_cta - 1) / db_per_cta);
     Top2* d_part = nullptr;
-    S3D_CUDA(cudaMallocAsync((void**)&d_part, sizeof(Top2) * (size_t)parts * nq, st));
+    S3D_CUDA(cudaMallocAsync((void**)&d_part, sizeof(Top2) * (size_t)parts * nql, st));
     dim3 grid(qtiles, parts);
-    S3D_LAUNCH(top2_exact_kernel, grid, 256, 0, st, d_q, nq, d_db, nd, db_offset, d_mask, db_per_cta, d_part);
-    S3D_LAUNCH(top2_merge_kernel, s3d_blocks(nq, 256), 256, 0, st, parts, nq, d_part, d_mask, d1, i1, d2, i2, gDist, gIdx,
-               sDist, sIdx);
+    S3D_LAUNCH(top2_exact_kernel, grid, 256, 0, st, d_q, d_qlist, nql, d_db, nd, db_offset, db_per_cta, d_part);
+    S3D_LAUNCH(top2_merge_kernel, s3d_blocks(nql, 256), 256, 0, st, parts, nql, d_qlist, d_part, d_out);
     S3D_CUDA(cudaGetLastError());
     S3D_CUDA(cudaFreeAsync(d_part, st));
+    return S3D_OK;
+}
+
+// One search direction (calMatches, Src/cMatcher.cc:40-79) on device arrays.
+static int search_device(const float* d_q, int nq, const float* d_db, int nd, int db_offset, const int* d_mask,
+                         double* d1, int* i1, double* d2, int* i2, float* gDist, int* gIdx, float* sDist, int* sIdx,
+                         cudaStream_t st) {
+    if (nq <= 0) return S3D_OK;
+    Top2* d_top = nullptr;
+    int *d_list = nullptr, *d_cnt = nullptr, *d_fb = nullptr;
+    S3D_CUDA(cudaMallocAsync((void**)&d_top, sizeof(Top2) * (size_t)nq, st));
+    S3D_CUDA(cudaMallocAsync((void**)&d_cnt, sizeof(int) * 2, st));
+    S3D_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * 2, st));
+    S3D_LAUNCH(top2_fill_kernel, s3d_blocks(nq, 256), 256, 0, st, d_top, nq);
+    int n_act = nq;
+    if (d_mask) {  // only the unmasked queries are searched (Src/cMatcher.cc:48-52)
+        S3D_CUDA(cudaMallocAsync((void**)&d_list, sizeof(int) * (size_t)nq, st));
+        S3D_LAUNCH(mask_list_kernel, 1, 1024, 0, st, d_mask, nq, d_list, d_cnt);
+        S3D_CUDA(cudaMemcpyAsync(&n_act, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+        S3D_CUDA(cudaStreamSynchronize(st));
+    }
+    const int path = g_match_path.load();
+    const bool use_tc = nd > 0 && n_act > 0 && (path == 2 || (path == 0 && (double)n_act * nd >= 4.0e6 && nd >= 512));
+    if (use_tc) {
+        S3D_CUDA(cudaMallocAsync((void**)&d_fb, sizeof(int) * (size_t)n_act, st));
+        S3D_TRY(tc_search(d_q, d_list, n_act, d_db, nd, db_offset, d_top, d_fb, d_cnt + 1, st));
+        int n_fb = 0;
+        S3D_CUDA(cudaMemcpyAsync(&n_fb, d_cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        S3D_CUDA(cudaStreamSynchronize(st));
+        g_tc_rows += (unsigned long long)n_act;
+        g_fb_rows += (unsigned long long)n_fb;
+        if (n_fb > 0) S3D_TRY(exact_search(d_q, d_fb, n_fb, d_db, nd, db_offset, d_top, st));
+    } else if (nd > 0) {
+        S3D_TRY(exact_search(d_q, d_list, n_act, d_db, nd, db_offset, d_top, st));
+    }
+    S3D_LAUNCH(top2_finalize_kernel, s3d_blocks(nq, 256), 256, 0, st, nq, d_top, d_mask, d1, i1, d2, i2, gDist, gIdx, sDist, sIdx);
+    S3D_CUDA(cudaGetLastError());
+    void* tmp[] = {d_top, d_list, d_cnt, d_fb};
+    for (void* p : tmp) if (p) S3D_CUDA(cudaFreeAsync(p, st));
     return S3D_OK;
 }
 
@@ -257,6 +299,18 @@ static int search_device(const float* d_q, int nq, const float* d_db, int nd, in
 using namespace s3d;
 
 extern "C" {
+
+int s3d_set_match_path(int path) {
+    if (path < 0 || path > 2) return fail(S3D_ERR_ARG, "match path %d (0 auto, 1 exact, 2 tensor-core)", path);
+    g_match_path = path;
+    return S3D_OK;
+}
+
+void s3d_match_stats(unsigned long long* tc_rows, unsigned long long* fallback_rows, int reset) {
+    if (tc_rows) *tc_rows = g_tc_rows.load();
+    if (fallback_rows) *fallback_rows = g_fb_rows.load();
+    if (reset) { g_tc_rows = 0; g_fb_rows = 0; }
+}
 
 int s3d_top2_device(const float* d_q, int n_q, const float* d_db, int n_db, int db_offset, const int* d_mask,
                     double* d_dot1, int* d_idx1, double* d_dot2, int* d_idx2, void* stream) {

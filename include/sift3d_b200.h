@@ -171,6 +171,13 @@ S3D_API int s3d_match_ex(int type, const float* ref_desc, int n_ref, int ref_on_
                          int tar_on_device, double thr, int* gIdx, float* gDist, int* sIdx, float* sDist, int* gIdx2,
                          float* gDist2, int* sIdx2, float* sDist2, int* pair_ref, int* pair_tar, int* n_pairs,
                          double* times3);
+/* Search path of calMatches: 0 = auto (tensor-core candidate pass + exact re-rank for large
+ * searches, exact CUDA-core kernel for small ones), 1 = exact kernel only, 2 = tensor cores always.
+ * Results are identical on every path (the tensor-core pass proves its candidate set complete or
+ * falls back per row). */
+S3D_API int s3d_set_match_path(int path);
+/* Rows searched on the tensor-core path and rows that needed the exact fallback, since start/reset. */
+S3D_API void s3d_match_stats(unsigned long long* tc_rows, unsigned long long* fallback_rows, int reset);
 /* Same with DEVICE-resident descriptor sets and DEVICE outputs (HBM-resident timing; the
  * extract→match handoff of SURVEY.md §8f-1).  stream is a cudaStream_t (0 = default). */
 S3D_API int s3d_match_device(int type, const float* d_ref, int n_ref, const float* d_tar, int n_tar, double thr,
