@@ -232,7 +232,12 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
 }
 
 // 0 = auto (tensor cores for large searches), 1 = exact CUDA-core kernel only, 2 = tensor cores always
-static std::atomic<int> g_match_path{0};
+// (initial value from the environment: S3D_MATCH_PATH=0|1|2)
+static int initial_match_path() {
+    const char* e = getenv("S3D_MATCH_PATH");
+    return (e && e[0] >= '0' && e[0] <= '2' && !e[1]) ? e[0] - '0' : 0;
+}
+static std::atomic<int> g_match_path{initial_match_path()};
 static std::atomic<unsigned long long> g_tc_rows{0}, g_fb_rows{0};
 
 // Exact CUDA-core search of the listed queries; results go to out[orig].
