@@ -64,6 +64,7 @@ def lib():
     L.s3d_selftest.argtypes = [C.c_int]
     L.s3d_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
     L.s3d_create_device.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
+    L.s3d_create_async.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
     for n in ("s3d_run", "s3d_run_async", "s3d_wait"):
         getattr(L, n).argtypes = [vp]
     L.s3d_destroy.argtypes = [vp]
@@ -158,7 +159,7 @@ class CSIFT3D:
     def __init__(self, volume, x_dim=None, y_dim=None, z_dim=None, num_kp_levels=NUM_KP_LEVELS,
                  sigma_default=SIGMA_DEFAULT, sigma_n_default=SIGMA_N_DEFAULT, peak_thresh=PEAK_THRESH,
                  max_eig_thres=EIG_THRES, corner_thresh=CORNER_THRESH, *, device=-1, keep_levels=False,
-                 exact_recheck=True, profile=False, stream=None):
+                 exact_recheck=True, profile=False, stream=None, async_upload=False):
         L = lib()
         self._h = C.c_void_p()
         p = s3d_params()
@@ -179,6 +180,10 @@ class CSIFT3D:
             if p.device < 0:
                 p.device = volume.device.index
             check(L.s3d_create_device(_ptr(volume), x_dim, y_dim, z_dim, C.byref(p), C.byref(self._h)))
+        elif async_upload:
+            # the upload is only enqueued: `volume` (pinned) must stay alive until KpSiftAlgorithm returns
+            self._pinned = volume
+            check(L.s3d_create_async(_ptr(volume), x_dim, y_dim, z_dim, C.byref(p), C.byref(self._h)))
         else:
             check(L.s3d_create(_ptr(volume), x_dim, y_dim, z_dim, C.byref(p), C.byref(self._h)))
         self._kp = None

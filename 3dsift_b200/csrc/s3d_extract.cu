@@ -323,7 +323,7 @@ struct s3d_ctx {
     s3d_keypoint* d_kps = nullptr;
     float* d_desc = nullptr;
     int n_rechecked = 0, n_flipped = 0;
-    bool ran = false, levels_alive = false, queued = false;
+    bool ran = false, levels_alive = false, queued = false, h2d_pending = false;
     cudaEvent_t ev[8];
     bool ev_ok = false;
     double timers[10] = {0};
@@ -431,7 +431,7 @@ int s3d_selftest(int device) {
     return S3D_OK;
 }
 
-int s3d_create(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
+static int create_host(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out, bool sync) {
     clear_error();
     if (!vol || !out) return fail(S3D_ERR_ARG, "null argument");
     s3d_ctx* c = new s3d_ctx();
@@ -449,17 +449,29 @@ int s3d_create(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3
     r = ctx_normalize(c, d_raw);
     cudaFreeAsync(d_raw, c->stream);
     if (r != S3D_OK) { s3d_destroy(c); return r; }
-    // the caller may free/reuse `vol` as soon as we return (the reference's ctor memcpy's it)
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
-        r = fail(S3D_ERR_CUDA, "create: %s", cudaGetErrorString(cudaGetLastError()));
-        s3d_destroy(c);
-        return r;
+    c->h2d_pending = true;
+    if (sync) {
+        // the caller may free/reuse `vol` as soon as we return (the reference's ctor memcpy's it)
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            r = fail(S3D_ERR_CUDA, "create: %s", cudaGetErrorString(cudaGetLastError()));
+            s3d_destroy(c);
+            return r;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+        c->timers[8] = ms * 1e-3;
+        c->h2d_pending = false;
     }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
-    c->timers[8] = ms * 1e-3;
     *out = c;
     return S3D_OK;
+}
+
+int s3d_create(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
+    return create_host(vol, nx, ny, nz, p, out, true);
+}
+
+int s3d_create_async(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
+    return create_host(vol, nx, ny, nz, p, out, false);
 }
 
 int s3d_create_device(const float* d_vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
@@ -498,6 +510,13 @@ static int run_impl(s3d_ctx* c) {
     cudaStream_t st = c->stream;
     S3D_CUDA(cudaSetDevice(c->device));
     const int L = c->L, G = c->G, D = c->D;
+    if (c->h2d_pending) {  // s3d_create_async: the copy's events are about to be reused
+        S3D_CUDA(cudaEventSynchronize(c->ev[7]));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+        c->timers[8] = ms * 1e-3;
+        c->h2d_pending = false;
+    }
     S3D_CUDA(cudaEventRecord(c->ev[0], st));
     // ---- Initialize --------------------------------------------------------------------------
     int mn = std::min(c->nx, std::min(c->ny, c->nz));
@@ -620,25 +639,44 @@ static int run_impl(s3d_ctx* c) {
             tab.scale[o * G + i] = host_level_scale(o, i, L, c->prm.sigma_default);
         }
     }
-    float* d_margins = nullptr;
+    // Gaussian window weight tables (wtab_kernel): one per (octave, keypoint level) and stage
+    float* d_wtab = nullptr;
+    {
+        int off = 0;
+        for (int o = 0; o < c->noct; o++)
+            for (int i = 1; i <= L; i++) {
+                const int lv = o * G + i;
+                const float u = (float)(1 << o), scale = tab.scale[lv];
+                const float so = 1.5f * scale, ro = so * 3.0f;                       // :27-28,:442,:915
+                const float sd = scale * 7.071067812f, rd = 2.0f * sd;               // :30-31,:1155-1156
+                tab.ori_off[lv] = off; tab.ori_n[lv] = (int)(ro * ro / (u * u)) + 2; off += tab.ori_n[lv];
+                tab.desc_off[lv] = off; tab.desc_n[lv] = (int)(rd * rd / (u * u)) + 2; off += tab.desc_n[lv];
+            }
+        S3D_CUDA(cudaMallocAsync((void**)&d_wtab, sizeof(float) * std::max(off, 1), st));
+        tab.wtab = d_wtab;
+        if (ne > 0) S3D_LAUNCH(wtab_kernel, dim3(2, c->noct * G), 256, 0, st, tab, c->noct, d_wtab);
+    }
+    int *d_recheck = nullptr;
     int* d_surv = nullptr;
     const size_t nea = std::max(ne, 1);
     S3D_CUDA(cudaMallocAsync((void**)&c->d_extre, sizeof(s3d_keypoint) * nea, st));
     S3D_CUDA(cudaMallocAsync((void**)&c->d_codes, sizeof(int) * nea, st));
     S3D_CUDA(cudaMallocAsync((void**)&c->d_xyz5, sizeof(int) * 5 * nea, st));
-    S3D_CUDA(cudaMallocAsync((void**)&d_margins, sizeof(float) * nea, st));
+    S3D_CUDA(cudaMallocAsync((void**)&d_recheck, sizeof(int) * nea, st));
     S3D_CUDA(cudaMallocAsync((void**)&d_surv, sizeof(int) * nea, st));
     if (ne > 0) {
         const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks((size_t)ne * 32, 256), 148 * 32);
         {
             ProfScope ps(&c->prof, K_ORIENT, 200.0 * ne);
-            S3D_LAUNCH(orient_kernel, grid, 256, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes, c->d_xyz5, d_margins,
-                       c->prm.max_eig_thres, c->prm.corner_thresh);
+            S3D_LAUNCH(orient_kernel, grid, 256, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes, c->d_xyz5,
+                       c->prm.max_eig_thres, c->prm.corner_thresh, 2e-3f, c->prm.exact_recheck ? d_recheck : (int*)nullptr,
+                       d_total + 1);
         }
         ProfScope ps(&c->prof, K_ORIENT_EXACT, 0.0);
         if (c->prm.exact_recheck)
-            S3D_LAUNCH(orient_exact_kernel, (unsigned)std::min<size_t>(s3d_blocks((size_t)ne * 32, 256), 148 * 8), 256, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes,
-                       d_margins, 2e-3f, c->prm.max_eig_thres, c->prm.corner_thresh, d_total + 1, d_total + 2);
+            S3D_LAUNCH(orient_exact_kernel, (unsigned)std::min<size_t>(s3d_blocks((size_t)ne, kExactWarps), 148 * 16),
+                       kExactWarps * 32, 0, st, d_cand, tab, c->d_extre, c->d_codes, d_recheck, d_total + 1,
+                       c->prm.max_eig_thres, c->prm.corner_thresh, d_total + 2);
     }
     {
         ProfScope ps(&c->prof, K_SURVIVORS, 8.0 * ne);
@@ -670,7 +708,7 @@ static int run_impl(s3d_ctx* c) {
 
     // ---- Release_SIFT (:1659-1678) unless the caller asked to keep the pyramids ---------------
     if (!c->prm.keep_levels) free_levels(c);
-    void* tmp[] = {d_blk_cnt, d_blk_off, d_total, d_stage, d_stage_count, d_cand, d_margins, d_surv};
+    void* tmp[] = {d_blk_cnt, d_blk_off, d_total, d_stage, d_stage_count, d_cand, d_recheck, d_surv, d_wtab};
     for (void* q : tmp) if (q) cudaFreeAsync(q, st);
     S3D_CUDA(cudaEventRecord(c->ev[6], st));
     c->queued = true;

@@ -310,8 +310,8 @@ __global__ void __launch_bounds__(256) downsample_kernel(const float* __restrict
 //     thres = peak_thresh * max|D[j]| (:384-385); candidate iff |val| > thres (strict) and val is
 //     strictly below or strictly above its 6 face neighbours in D[j] and the same voxel in
 //     D[j-1], D[j+1] (8 neighbours, App. B Q1); x,y,z in [1, n-2].
-//     Ordered compaction: each CTA owns 1024 consecutive voxels; flagged voxels are ranked inside
-//     the CTA (ballot-free prefix over 4 flags/thread + warp scan), staged under an atomically
+//     Ordered compaction: each CTA owns 4096 consecutive voxels (16 per thread); flagged voxels are
+//     ranked inside the CTA (popc prefix over 16 flags/thread + warp scan), staged under an atomically
 //     claimed segment, and a later scan of per-CTA counts turns (cta, rank) into the raster
 //     position — the reference's (octave, level, z, y, x) emission order (App. B Q16).
 // ---------------------------------------------------------------------------------------------
@@ -322,8 +322,13 @@ struct StageEntry {
     uint32_t unit;  // octave * L + (level - 1)
 };
 
-constexpr int kDetectChunk = 1024;
+constexpr int kDetectPer = 16;                    // voxels per thread: 4 float4 groups
+constexpr int kDetectChunk = 256 * kDetectPer;    // voxels per CTA (8 warps x 512 consecutive voxels)
 
+// Voxel layout inside a CTA: warp w owns voxels [w*512, w*512+512) of the CTA's chunk; its load q
+// (0..3) is the float4 at index q*32 + lane of that range, so every request is one fully coalesced
+// 512-byte line group.  A thread therefore holds 4 groups of 4 consecutive voxels; raster order
+// inside the warp is (q, lane, j).
 __global__ void __launch_bounds__(256) detect_kernel(const float* __restrict__ Dm, const float* __restrict__ D0,
                                                      const float* __restrict__ Dp, int nx, int ny, int nz,
                                                      const unsigned* __restrict__ maxslot, float peak, uint32_t unit,
@@ -333,61 +338,77 @@ __global__ void __launch_bounds__(256) detect_kernel(const float* __restrict__ D
     __shared__ int warp_tot[8];
     __shared__ unsigned seg_base;
     const ll total = (ll)nx * ny * nz;
-    const ll base = ((ll)blockIdx.x * 256 + threadIdx.x) * 4;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const ll wbase_vox = (ll)blockIdx.x * kDetectChunk + (ll)wid * 512;
     const float thres = peak * __uint_as_float(*maxslot);
     if (blockIdx.x == 0 && threadIdx.x == 0 && thres_out) *thres_out = thres;
-    const ll ys = nx, zs = (ll)nx * ny;
+    // Phase 1 (every voxel, HBM-bound): |val| > thres  (val > thres || val < -thres, Src/cSIFT3D.cc:394)
+    unsigned above = 0;
+    if (wbase_vox + 512 <= total) {
+        float4 f[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) f[q] = *(reinterpret_cast<const float4*>(D0 + wbase_vox) + q * 32 + lane);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            above |= ((fabsf(f[q].x) > thres ? 1u : 0u) | (fabsf(f[q].y) > thres ? 2u : 0u) | (fabsf(f[q].z) > thres ? 4u : 0u) |
+                      (fabsf(f[q].w) > thres ? 8u : 0u)) << (4 * q);
+    } else {
+#pragma unroll
+        for (int b = 0; b < kDetectPer; ++b) {
+            const ll i = wbase_vox + (ll)((b >> 2) * 32 + lane) * 4 + (b & 3);
+            if (i < total && fabsf(D0[i]) > thres) above |= 1u << b;
+        }
+    }
+    // Phase 2 (rare): the 8-neighbour test for the voxels above the threshold
     unsigned flags = 0;
-    if (base < total) {
-        float v[4];
-        if (base + 3 < total && (total & 3) == 0) {
-            const float4 f = *reinterpret_cast<const float4*>(D0 + base);
-            v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = (base + j < total) ? D0[base + j] : 0.0f;
-        }
-        bool any = false;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) any |= (v[j] > thres || v[j] < -thres);
-        // total < 2^32 (checked at create): 32-bit divisions, once per thread
-        uint32_t x0 = 0, y0 = 0, z0 = 0;
-        if (any) {
-            const uint32_t b = (uint32_t)base, unx = (uint32_t)nx, uny = (uint32_t)ny;
-            const uint32_t tq = b / unx;
-            x0 = b - tq * unx; z0 = tq / uny; y0 = tq - z0 * uny;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const ll i = base + j;
-            const float val = v[j];
-            if (any && i < total && (val > thres || val < -thres)) {
-                int x = (int)x0 + j, y = (int)y0, z = (int)z0;
-                if (x >= nx) {  // only when nx % 4 != 0: the group straddles a row
-                    x -= nx;
-                    if (++y >= ny) { y = 0; ++z; }
-                }
-                if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
-                    const float t0 = Dm[i], t1 = D0[i - 1], t2 = D0[i + 1], t3 = D0[i + ys], t4 = D0[i - ys],
-                                t5 = D0[i + zs], t6 = D0[i - zs], t7 = Dp[i];
-                    const bool mn = val < t0 && val < t1 && val < t2 && val < t3 && val < t4 && val < t5 && val < t6 &&
-                                    val < t7;
-                    const bool mx = val > t0 && val > t1 && val > t2 && val > t3 && val > t4 && val > t5 && val > t6 &&
-                                    val > t7;
-                    if (mn || mx) flags |= 1u << j;
-                }
+    if (above) {
+        const ll ys = nx, zs = (ll)nx * ny;
+        const uint32_t unx = (uint32_t)nx, uny = (uint32_t)ny;
+        for (unsigned m = above; m; m &= m - 1) {
+            const int b = __ffs(m) - 1;
+            const ll i = wbase_vox + (ll)((b >> 2) * 32 + lane) * 4 + (b & 3);
+            // total < 2^32 (checked at create): 32-bit divisions
+            const uint32_t bi = (uint32_t)i, tq = bi / unx;
+            const int x = (int)(bi - tq * unx), z = (int)(tq / uny), y = (int)(tq - (uint32_t)z * uny);
+            if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && z >= 1 && z <= nz - 2) {
+                // strict extremum against all 8 neighbours (:889-902); cheapest (cached) neighbours
+                // first, the conjunction is order-independent
+                const float val = D0[i];
+                const float t1 = D0[i - 1], t2 = D0[i + 1];
+                bool mn = val < t1 && val < t2, mx = val > t1 && val > t2;
+                if (!(mn || mx)) continue;
+                const float t3 = D0[i + ys], t4 = D0[i - ys];
+                mn = mn && val < t3 && val < t4; mx = mx && val > t3 && val > t4;
+                if (!(mn || mx)) continue;
+                const float t5 = D0[i + zs], t6 = D0[i - zs];
+                mn = mn && val < t5 && val < t6; mx = mx && val > t5 && val > t6;
+                if (!(mn || mx)) continue;
+                const float t0 = Dm[i], t7 = Dp[i];
+                mn = mn && val < t0 && val < t7; mx = mx && val > t0 && val > t7;
+                if (mn || mx) flags |= 1u << b;
             }
         }
     }
-    const int cnt = __popc(flags);
-    int incl = cnt;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int nb = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += nb;
+    // CTAs without any detection (the majority) leave here
+    if (!__syncthreads_or(flags != 0)) {
+        if (threadIdx.x == 0) blk_cnt[gb_base + blockIdx.x] = 0;
+        return;
     }
-    if (lane == 31) warp_tot[wid] = incl;
+    // Ranks in raster order: warp base + groups before mine + lanes before me in my group + bits below
+    int excl[4], run = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = __popc((flags >> (4 * q)) & 15u);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        excl[q] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) warp_tot[wid] = run;
     __syncthreads();
     int wbase = 0, tot = 0;
 #pragma unroll
@@ -397,23 +418,26 @@ __global__ void __launch_bounds__(256) detect_kernel(const float* __restrict__ D
     }
     if (threadIdx.x == 0) {
         blk_cnt[gb_base + blockIdx.x] = tot;
-        seg_base = tot ? atomicAdd(stage_count, (unsigned)tot) : 0u;
+        seg_base = atomicAdd(stage_count, (unsigned)tot);
     }
     __syncthreads();
-    if (cnt) {
-        unsigned rank = (unsigned)(wbase + incl - cnt);
+    if (flags) {
         const unsigned sb = seg_base;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (flags & (1u << j)) {
+        for (int q = 0; q < 4; ++q) {
+            unsigned rank = (unsigned)(wbase + excl[q]);
+            for (unsigned m = (flags >> (4 * q)) & 15u; m; m &= m - 1) {
+                const int j = __ffs(m) - 1;
                 const unsigned pos = sb + rank;
                 if (pos < stage_cap) {
                     StageEntry e;
-                    e.key = (uint32_t)(base + j); e.gb = gb_base + blockIdx.x; e.rank = rank; e.unit = unit;
+                    e.key = (uint32_t)(wbase_vox + (ll)(q * 32 + lane) * 4 + j);
+                    e.gb = gb_base + blockIdx.x; e.rank = rank; e.unit = unit;
                     stage[pos] = e;
                 }
                 ++rank;
             }
+        }
     }
 }
 
@@ -466,7 +490,39 @@ struct LevelTable {
     int dims[kMaxOct][3];
     int L;  // num_kp_levels
     int G;  // L + 3
+    // Gaussian window weights as tables (see wtab_kernel): offsets into `wtab`, entries per table
+    const float* wtab;
+    int ori_off[kMaxOct * kMaxG], ori_n[kMaxOct * kMaxG];
+    int desc_off[kMaxOct * kMaxG], desc_n[kMaxOct * kMaxG];
 };
+
+// Window weights depend on the voxel only through m = i^2+j^2+k^2 (integer voxel offsets from the
+// integer keypoint position): disp = offset * u with u = 2^octave, so
+// sq = dx*dx+dy*dy+dz*dz = u*u*m EXACTLY in FP32 (all terms are small integers times a power of two).
+// The tables hold, per (octave, level), the reference's expression evaluated at every m:
+//   orientation  expf((float)(-0.5 * (double)sq / (double)(sigma*sigma)))   Src/cSIFT3D.cc:971
+//   descriptor   expf(-0.5f * sq / (sigma*sigma))                            Src/cSIFT3D.cc:1312
+// with expf = s3d_expf_ref (glibc's algorithm), so a lookup returns bit for bit what the
+// per-voxel evaluation did.  One thread per entry.
+__global__ void __launch_bounds__(256) wtab_kernel(LevelTable tab, int noct, float* __restrict__ out) {
+    const int lv = blockIdx.y;                 // o * G + level
+    const int o = lv / tab.G;
+    if (o >= noct) return;
+    const float u = (float)(1 << o);
+    const float scale = tab.scale[lv];
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < tab.ori_n[lv] + tab.desc_n[lv]; m += gridDim.x * blockDim.x) {
+        if (m < tab.ori_n[lv]) {
+            const float sigma = 1.5f * scale;
+            const float sq = u * u * (float)m;
+            out[tab.ori_off[lv] + m] = s3d_expf_ref((float)(-0.5 * (double)sq / (double)(sigma * sigma)));
+        } else {
+            const int md = m - tab.ori_n[lv];
+            const float sigma = scale * 7.071067812f;
+            const float sq = u * u * (float)md;
+            out[tab.desc_off[lv] + md] = s3d_expf_ref(-0.5f * sq / (sigma * sigma));
+        }
+    }
+}
 
 // Symmetric 3x3 eigen-decomposition in double (cyclic Jacobi), columns of V = unit eigenvectors.
 // Stands in for Eigen::EigenSolver<Matrix3d> (Src/cSIFT3D.cc:1016-1029): eigenvalues agree to
@@ -528,15 +584,16 @@ struct OrientSums {
 };
 
 // One window voxel of Assign_Orientation_Imp, Src/cSIFT3D.cc:964-994 (same operation order).
+// (0.5 * (double)(a - b) rounded to float == 0.5f * (a - b): halving is exact.)
 __device__ __forceinline__ void orient_voxel(const float* __restrict__ g, ll i, ll ys, ll zs, float dx, float dy, float dz,
-                                             float u, float sigma, float r2, OrientSums& S) {
+                                             float iu, float inv_u2, const float* __restrict__ wt, float r2,
+                                             OrientSums& S) {
     const float sq = dx * dx + dy * dy + dz * dz;
     if (sq > r2) return;
-    const float weight = s3d_expf_ref((float)(-0.5 * (double)sq / (double)(sigma * sigma)));
-    float vx = (float)(0.5 * (double)(g[i + 1] - g[i - 1]));
-    float vy = (float)(0.5 * (double)(g[i + ys] - g[i - ys]));
-    float vz = (float)(0.5 * (double)(g[i + zs] - g[i - zs]));
-    const float iu = 1.0f / u;
+    const float weight = wt[(int)(sq * inv_u2)];
+    float vx = 0.5f * (g[i + 1] - g[i - 1]);
+    float vy = 0.5f * (g[i + ys] - g[i - ys]);
+    float vz = 0.5f * (g[i + zs] - g[i - zs]);
     vx *= iu; vy *= iu; vz *= iu;
     S.t00 += vx * vx * weight;
     S.t01 += vx * vy * weight;
@@ -656,21 +713,25 @@ __device__ __forceinline__ void kp_init(s3d_keypoint& kp, int o, int lvl, int x,
 //     Lanes stride over the (y,x) plane of each z slice, keep 9 partial sums, butterfly-reduce
 //     (fixed tree, so results are run-to-run deterministic), then finish redundantly per lane.
 //     The FP32 summation order differs from the reference's serial z,y,x order; detections whose
-//     tests land within `recheck_margin` of a threshold are flagged (margins[]) for the exact
+//     tests land within `recheck_margin` of a threshold are appended to recheck_list for the exact
 //     serial re-evaluation kernel below.
 __global__ void __launch_bounds__(256) orient_kernel(const Cand* __restrict__ cand, int ncand, LevelTable tab,
                                                      s3d_keypoint* __restrict__ out, int* __restrict__ codes,
-                                                     int* __restrict__ xyz5, float* __restrict__ margins, float max_eig,
-                                                     float corner) {
+                                                     int* __restrict__ xyz5, float max_eig, float corner,
+                                                     float recheck_margin, int* __restrict__ recheck_list,
+                                                     int* __restrict__ n_recheck) {
     const int lane = threadIdx.x & 31;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < ncand; ci += warps_per_grid) {
         int o, lvl, x, y, z;
         cand_decode(cand[ci], tab, o, lvl, x, y, z);
         const int nx = tab.dims[o][0], ny = tab.dims[o][1], nz = tab.dims[o][2];
-        const float* g = tab.gss[o * tab.G + lvl];
-        const float scale = tab.scale[o * tab.G + lvl];
+        const int lv = o * tab.G + lvl;
+        const float* g = tab.gss[lv];
+        const float* wt = tab.wtab + tab.ori_off[lv];
+        const float scale = tab.scale[lv];
         const float u = (float)(1 << o);
+        const float iu = 1.0f / u, inv_u2 = iu * iu;
         s3d_keypoint kp;
         kp_init(kp, o, lvl, x, y, z, scale);
         const float sigma = 1.5f * scale;          // ori_sig_fctr, :27,:442
@@ -682,14 +743,19 @@ __global__ void __launch_bounds__(256) orient_kernel(const Cand* __restrict__ ca
         window_bounds(kp.z, win_radius / u, nz, z0, z1);
         const int wxn = xe - xs + 1, wyn = y1 - y0 + 1;
         const int plane = wxn > 0 && wyn > 0 ? wxn * wyn : 0;
+        const float inv_wxn = 1.0f / (float)(wxn > 0 ? wxn : 1);
         const ll ys = nx, zs = (ll)nx * ny;
         OrientSums S = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         for (int zz = z0; zz <= z1; ++zz) {
             const float dz = ((float)zz - kp.z) * u;
+            const float* gz = g + (ll)zz * zs;
             for (int tI = lane; tI < plane; tI += 32) {
-                const int yy = y0 + tI / wxn, xx = xs + tI % wxn;
+                // tI / wxn without an integer division: (tI + 0.5) / wxn is at least 0.5/wxn away from
+                // an integer, far more than the FP32 error for tI < 2^20
+                const int ry = (int)(((float)tI + 0.5f) * inv_wxn);
+                const int yy = y0 + ry, xx = xs + (tI - ry * wxn);
                 const float dx = ((float)xx - kp.x) * u, dy = ((float)yy - kp.y) * u;
-                orient_voxel(g, (ll)xx + (ll)yy * ys + (ll)zz * zs, ys, zs, dx, dy, dz, u, sigma, r2, S);
+                orient_voxel(gz, (ll)xx + (ll)yy * ys, ys, zs, dx, dy, dz, iu, inv_u2, wt, r2, S);
             }
         }
         float* sp = reinterpret_cast<float*>(&S);
@@ -706,7 +772,7 @@ __global__ void __launch_bounds__(256) orient_kernel(const Cand* __restrict__ ca
             if (code < 1) kp.x = kp.y = kp.z = -1.0f;  // :446-450
             out[ci] = kp;
             codes[ci] = code;
-            margins[ci] = margin;
+            if (recheck_list && margin < recheck_margin) recheck_list[atomicAdd(n_recheck, 1)] = ci;
             xyz5[5 * ci + 0] = x; xyz5[5 * ci + 1] = y; xyz5[5 * ci + 2] = z; xyz5[5 * ci + 3] = o; xyz5[5 * ci + 4] = lvl;
         }
     }
@@ -714,14 +780,14 @@ __global__ void __launch_bounds__(256) orient_kernel(const Cand* __restrict__ ca
 
 // One window voxel's nine addends (no accumulation), same arithmetic as orient_voxel.
 __device__ __forceinline__ bool orient_terms(const float* __restrict__ g, ll i, ll ys, ll zs, float dx, float dy, float dz,
-                                             float u, float sigma, float r2, float tm[9]) {
+                                             float iu, float inv_u2, const float* __restrict__ wt, float r2,
+                                             float tm[9]) {
     const float sq = dx * dx + dy * dy + dz * dz;
     if (sq > r2) return false;
-    const float weight = s3d_expf_ref((float)(-0.5 * (double)sq / (double)(sigma * sigma)));
-    float vx = (float)(0.5 * (double)(g[i + 1] - g[i - 1]));
-    float vy = (float)(0.5 * (double)(g[i + ys] - g[i - ys]));
-    float vz = (float)(0.5 * (double)(g[i + zs] - g[i - zs]));
-    const float iu = 1.0f / u;
+    const float weight = wt[(int)(sq * inv_u2)];
+    float vx = 0.5f * (g[i + 1] - g[i - 1]);
+    float vy = 0.5f * (g[i + ys] - g[i - ys]);
+    float vz = 0.5f * (g[i + zs] - g[i - zs]);
     vx *= iu; vy *= iu; vz *= iu;
     tm[0] = vx * vx * weight; tm[1] = vx * vy * weight; tm[2] = vx * vz * weight;
     tm[3] = vy * vy * weight; tm[4] = vy * vz * weight; tm[5] = vz * vz * weight;
@@ -732,23 +798,35 @@ __device__ __forceinline__ bool orient_terms(const float* __restrict__ g, ll i, 
 // Exact re-evaluation of the flagged detections in the reference's own summation order
 // (z, y, x serial FP32 accumulation, Src/cSIFT3D.cc:958-998), so near-threshold accept/reject
 // decisions follow the reference's rounding instead of the warp-parallel tree's.  One warp per
-// flagged detection: lanes compute the addends of 32 consecutive voxels of a row in parallel,
-// then every lane accumulates them IN ORDER (broadcast by shuffle), which reproduces the serial
-// sum bit for bit at 1/32 of the serial latency.
-__global__ void __launch_bounds__(256) orient_exact_kernel(const Cand* __restrict__ cand, int ncand, LevelTable tab,
-                                                           s3d_keypoint* __restrict__ out, int* __restrict__ codes,
-                                                           const float* __restrict__ margins, float recheck_margin,
-                                                           float max_eig, float corner, int* n_rechecked, int* n_flipped) {
-    const int lane = threadIdx.x & 31;
+// flagged detection (the list orient_kernel compacted): for each window row the lanes compute the
+// nine addends of up to 32 consecutive voxels in parallel and park them, rank-compacted, in a
+// per-warp shared-memory tile; lane k < 9 then adds column k IN ORDER — the serial sum of
+// component k, bit for bit, at one LDS + FADD per voxel for all nine components together.
+constexpr int kExactWarps = 2;
+__global__ void __launch_bounds__(kExactWarps * 32) orient_exact_kernel(const Cand* __restrict__ cand, LevelTable tab,
+                                                                        s3d_keypoint* __restrict__ out,
+                                                                        int* __restrict__ codes,
+                                                                        const int* __restrict__ recheck_list,
+                                                                        const int* __restrict__ n_recheck, float max_eig,
+                                                                        float corner, int* n_flipped) {
+    __shared__ float tile[kExactWarps][9][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-    for (int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < ncand; ci += warps_per_grid) {
-        if (!(margins[ci] < recheck_margin)) continue;
+    const int nre = *n_recheck;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int row9 = lane < 9 ? lane : 0;
+    float(*tl)[33] = tile[wid];
+    for (int ri = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ri < nre; ri += warps_per_grid) {
+        const int ci = recheck_list[ri];
         int o, lvl, x, y, z;
         cand_decode(cand[ci], tab, o, lvl, x, y, z);
         const int nx = tab.dims[o][0], ny = tab.dims[o][1], nz = tab.dims[o][2];
-        const float* g = tab.gss[o * tab.G + lvl];
-        const float scale = tab.scale[o * tab.G + lvl];
+        const int lv = o * tab.G + lvl;
+        const float* g = tab.gss[lv];
+        const float* wt = tab.wtab + tab.ori_off[lv];
+        const float scale = tab.scale[lv];
         const float u = (float)(1 << o);
+        const float iu = 1.0f / u, inv_u2 = iu * iu;
         s3d_keypoint kp;
         kp_init(kp, o, lvl, x, y, z, scale);
         const float sigma = 1.5f * scale;
@@ -759,7 +837,7 @@ __global__ void __launch_bounds__(256) orient_exact_kernel(const Cand* __restric
         window_bounds(kp.y, win_radius / u, ny, y0, y1);
         window_bounds(kp.z, win_radius / u, nz, z0, z1);
         const ll ys = nx, zs = (ll)nx * ny;
-        float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float acc = 0.0f;  // lane k < 9 owns component k
         for (int zz = z0; zz <= z1; ++zz)
             for (int yy = y0; yy <= y1; ++yy) {
                 const float dy = ((float)yy - kp.y) * u, dz = ((float)zz - kp.z) * u;
@@ -767,23 +845,35 @@ __global__ void __launch_bounds__(256) orient_exact_kernel(const Cand* __restric
                     const int xx = xb + lane;
                     float tm[9];
                     bool in = false;
-                    if (xx <= xe) in = orient_terms(g, (ll)xx + (ll)yy * ys + (ll)zz * zs, ys, zs, ((float)xx - kp.x) * u, dy, dz, u, sigma, r2, tm);
-                    unsigned m = __ballot_sync(0xffffffffu, in);
-                    while (m) {
-                        const int j = __ffs(m) - 1;
-                        m &= m - 1;
+                    if (xx <= xe)
+                        in = orient_terms(g, (ll)xx + (ll)yy * ys + (ll)zz * zs, ys, zs, ((float)xx - kp.x) * u, dy, dz, iu,
+                                          inv_u2, wt, r2, tm);
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (in) {
+                        const int col = __popc(m & lt_mask);
 #pragma unroll
-                        for (int k = 0; k < 9; ++k) acc[k] += __shfl_sync(0xffffffffu, tm[k], j);
+                        for (int k = 0; k < 9; ++k) tl[k][col] = tm[k];
                     }
+                    __syncwarp();
+                    const int cnt = __popc(m);
+                    int j = 0;
+                    for (; j + 4 <= cnt; j += 4) {
+                        const float a0 = tl[row9][j], a1 = tl[row9][j + 1], a2 = tl[row9][j + 2], a3 = tl[row9][j + 3];
+                        acc += a0; acc += a1; acc += a2; acc += a3;
+                    }
+                    for (; j < cnt; ++j) acc += tl[row9][j];
+                    __syncwarp();
                 }
             }
         OrientSums S;
-        S.t00 = acc[0]; S.t01 = acc[1]; S.t02 = acc[2]; S.t11 = acc[3]; S.t12 = acc[4]; S.t22 = acc[5];
-        S.wx = acc[6]; S.wy = acc[7]; S.wz = acc[8];
+        S.t00 = __shfl_sync(0xffffffffu, acc, 0); S.t01 = __shfl_sync(0xffffffffu, acc, 1);
+        S.t02 = __shfl_sync(0xffffffffu, acc, 2); S.t11 = __shfl_sync(0xffffffffu, acc, 3);
+        S.t12 = __shfl_sync(0xffffffffu, acc, 4); S.t22 = __shfl_sync(0xffffffffu, acc, 5);
+        S.wx = __shfl_sync(0xffffffffu, acc, 6); S.wy = __shfl_sync(0xffffffffu, acc, 7);
+        S.wz = __shfl_sync(0xffffffffu, acc, 8);
         const int code = orient_finish(S, kp, max_eig, corner, nullptr);
         if (lane == 0) {
             if (code < 1) kp.x = kp.y = kp.z = -1.0f;
-            atomicAdd(n_rechecked, 1);
             if (code != codes[ci]) atomicAdd(n_flipped, 1);
             out[ci] = kp;
             codes[ci] = code;
@@ -885,16 +975,19 @@ constexpr int kDescThreads = kDescWarps * 32;
 // Histogram bin (x,y,z,v) lives at (x + 4y)*12 + z*kHistZ + v: the z stride is padded from 192 to
 // 200 words so the 8 trilinear cells of a voxel fall into 8 different bank groups.
 constexpr int kHistZ = 200;
-constexpr int kHistDump = 3 * kHistZ + 192;      // slot for out-of-grid cells
-constexpr int kHistStride = kHistDump + 8;
+constexpr int kHistDump = 3 * kHistZ + 192;      // 12 slots (one per vertex) for out-of-grid cells
+constexpr int kHistStride = kHistDump + 16;
+constexpr int kStageCols = 33;                   // 32 voxels + 1 pad: conflict-free 64-bit rows and columns
+constexpr int kDescWtCap = 1312;                 // default parameters need <= 1292 entries
 
 struct DescSmem {
     float hist[kDescWarps][kHistStride];
-    uint2 stage[kDescWarps][24][32];                 // (bin address, value bits); column = rank ^ entry
+    uint2 stage[kDescWarps][24][kStageCols];         // (bin address, value bits); column = rank in the batch
     uint32_t queue[kDescWarps][64];                  // per-warp ring of voxels that passed the cheap tests
     MeshConst M;
     s3d_keypoint kp;
     float red[kDescWarps + 1];
+    float wt[kDescWtCap];                            // Gaussian window weight by m = i^2+j^2+k^2 (wtab_kernel)
 };
 
 // One CTA per surviving keypoint, 7 warps, 3 CTAs per SM.
@@ -934,6 +1027,12 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
     const int o = kp.octave, lvl = kp.level;
     const int nx = tab.dims[o][0], ny = tab.dims[o][1], nz = tab.dims[o][2];
     const float* g = tab.gss[o * tab.G + lvl];
+    const float* wt_g = tab.wtab + tab.desc_off[o * tab.G + lvl];
+    const int wt_n = tab.desc_n[o * tab.G + lvl];
+    const bool wt_s = wt_n <= kDescWtCap;
+    if (wt_s)
+        for (int i = tid; i < wt_n; i += kDescThreads) S.wt[i] = wt_g[i];
+    __syncthreads();
     const float u = (float)(1 << o);
     const float bary_eps = (float)(FLT_EPSILON * 1E1);          // :23
     const float sigma = kp.scale * 7.071067812f;                // desc_sig_fctr :30,:1155
@@ -942,7 +1041,6 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
     const float desc_width = 2.0f * desc_hw;
     const float desc_bin_fctr = 4.0f / desc_width;
     const float r2 = win_radius * win_radius;
-    const float s2 = sigma * sigma;
     const float cx = kp.x, cy = kp.y, cz = kp.z;
     // Transpose_Matrix(kp.Rotation) :1214 — R below is the transpose (App. B Q11)
     const float R0 = kp.Rotation[0], R1 = kp.Rotation[3], R2 = kp.Rotation[6];
@@ -957,9 +1055,9 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
     const int npairs = (wyn > 0 && wzn > 0) ? wyp * wzn : 0;
     const ll ys = nx, zs = (ll)nx * ny;
     float* myh = S.hist[wid];
-    uint2(*stg)[32] = S.stage[wid];
+    uint2(*stg)[kStageCols] = S.stage[wid];
     uint32_t* que = S.queue[wid];
-    const float iu = 1.0f / u;
+    const float iu = 1.0f / u, inv_u2 = iu * iu;
     // conservative clip of a row to the rotated grid: |R_k . disp| < slab for k = 0..2, with
     // R_k . disp = a_k * (x - cx) + (R_k1*dy + R_k2*dz); the reciprocals are per keypoint
     const float slab = desc_hw * 1.001f + 1e-3f;
@@ -983,11 +1081,12 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
             vb1 = (R3 * dx + R4 * dy + R5 * dz + desc_hw) * desc_bin_fctr;
             vb2 = (R6 * dx + R7 * dy + R8 * dz + desc_hw) * desc_bin_fctr;
             vb0 -= 0.5f; vb1 -= 0.5f; vb2 -= 0.5f;
-            const float weight = s3d_expf_ref(-0.5f * sq / s2);
+            const int mi = (int)(sq * inv_u2);  // sq = u*u*m exactly, see wtab_kernel
+            const float weight = wt_s ? S.wt[mi] : wt_g[mi];  // == expf(-0.5f * sq / s2), :1312
             const ll i = (ll)xx + (ll)yy * ys + (ll)zz * zs;
-            float gx = (float)(0.5 * (double)(g[i + 1] - g[i - 1]));
-            float gy = (float)(0.5 * (double)(g[i + ys] - g[i - ys]));
-            float gz = (float)(0.5 * (double)(g[i + zs] - g[i - zs]));
+            float gx = 0.5f * (g[i + 1] - g[i - 1]);  // == (float)(0.5 * (double)(a - b))
+            float gy = 0.5f * (g[i + ys] - g[i - ys]);
+            float gz = 0.5f * (g[i + zs] - g[i - zs]);
             gx *= iu; gy *= iu; gz *= iu;
             gx = gx * weight; gy = gy * weight; gz = gz * weight;  // SIFT3D_CVEC_SCALE :1322
             const float rx = R0 * gx + R1 * gy + R2 * gz;
@@ -1017,27 +1116,37 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
             const bool okz[2] = {ib2 >= 0 && ib2 <= 3, ib2 >= -1 && ib2 <= 2};
             const int ax[2] = {ib0 * 12, ib0 * 12 + 12}, ay[2] = {ib1 * 48, ib1 * 48 + 48}, az[2] = {ib2 * kHistZ, ib2 * kHistZ + kHistZ};
             const int i0 = M.idx[face][0], i1 = M.idx[face][1], i2 = M.idx[face][2];
+            uint2* col = &stg[0][rr];
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int ddx = (c >> 2) & 1, ddy = (c >> 1) & 1, ddz = c & 1;
                 const bool ok = okx[ddx] && oky[ddy] && okz[ddz];
                 const float wt = (float)(wx[ddx] * wy[ddy] * wz[ddz]);
                 const float mw = mag * wt;
-                const int base = ax[ddx] + ay[ddy] + az[ddz];
-                stg[c * 3 + 0][rr ^ (c * 3 + 0)] = make_uint2(ok ? base + i0 : kHistDump, __float_as_uint(mw * b[0]));
-                stg[c * 3 + 1][rr ^ (c * 3 + 1)] = make_uint2(ok ? base + i1 : kHistDump, __float_as_uint(mw * b[1]));
-                stg[c * 3 + 2][rr ^ (c * 3 + 2)] = make_uint2(ok ? base + i2 : kHistDump, __float_as_uint(mw * b[2]));
+                const int base = ok ? ax[ddx] + ay[ddy] + az[ddz] : kHistDump;  // dump: 12 slots, any vertex
+                col[(c * 3 + 0) * kStageCols] = make_uint2(base + i0, __float_as_uint(mw * b[0]));
+                col[(c * 3 + 1) * kStageCols] = make_uint2(base + i1, __float_as_uint(mw * b[1]));
+                col[(c * 3 + 2) * kStageCols] = make_uint2(base + i2, __float_as_uint(mw * b[2]));
             }
         }
         __syncwarp();
         const int cnt = __popc(mc);
         if (cnt) {
-            uint2 cur = stg[l24][l24];  // column 0 ^ l24
-            for (int j = 0; j < cnt; ++j) {
-                const uint2 nxt = stg[l24][((j + 1) & 31) ^ l24];  // prefetch the next voxel's entry
-                if (lane < 24) myh[cur.x] += __uint_as_float(cur.y);
+            // lane l < 24 adds entry l of each staged voxel, in order; entries are prefetched two ahead
+            const uint2* row = stg[l24];
+            uint2 e0 = row[0], e1 = row[1];
+            int j = 0;
+            for (; j + 2 <= cnt; j += 2) {
+                const uint2 n0 = row[j + 2], n1 = row[min(j + 3, kStageCols - 1)];
+                if (lane < 24) myh[e0.x] += __uint_as_float(e0.y);
                 __syncwarp();
-                cur = nxt;
+                if (lane < 24) myh[e1.x] += __uint_as_float(e1.y);
+                __syncwarp();
+                e0 = n0; e1 = n1;
+            }
+            if (j < cnt) {
+                if (lane < 24) myh[e0.x] += __uint_as_float(e0.y);
+                __syncwarp();
             }
         }
     };

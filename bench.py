@@ -199,17 +199,28 @@ def main():
     h_desc = torch.empty((cap, 768), dtype=torch.float32).pin_memory()
     first.close()
 
-    def step_e2e():
-        sift = s3d.CSIFT3DFactory.CreateCSIFT3D(h_vol, x_dim=n, y_dim=n, z_dim=n, device=local, stream=stream)
-        sift.KpSiftAlgorithm()
-        k = sift.num_keypoints()
-        s3d.check(L.s3d_get_keypoints(sift._h, h_kp.data_ptr(), h_desc.data_ptr()))
-        sift.close()
+    # e2e: the public host API with HOST buffers.  Every step uploads its own 512 MiB volume from pinned
+    # memory and reads its keypoints + descriptors back; the upload of step i+1 is enqueued
+    # (s3d_create_async, private stream per handle) before step i's extraction so the copy engine
+    # works under the kernels — a two-deep software pipeline, all of it inside the timed region.
+    def upload():
+        return s3d.CSIFT3DFactory.CreateCSIFT3D(h_vol, x_dim=n, y_dim=n, z_dim=n, device=local, async_upload=True)
+
+    def e2e_steps(k_steps):
+        k = 0
+        cur = upload()
+        for i in range(k_steps):
+            nxt = upload() if i + 1 < k_steps else None
+            cur.KpSiftAlgorithm()
+            k = cur.num_keypoints()
+            s3d.check(L.s3d_get_keypoints(cur._h, h_kp.data_ptr(), h_desc.data_ptr()))
+            cur.close()
+            cur = nxt
         return k
 
     for _ in range(a.warmup):
         step_resident(False).close()
-        step_e2e()
+    e2e_steps(a.warmup)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -243,8 +254,8 @@ def main():
     w0 = time.time()
     ev0.record()
     t0 = time.perf_counter()
-    for _ in range(a.steps):
-        k = step_e2e()
+    k = e2e_steps(a.steps)
+    torch.cuda.synchronize()
     ev1.record()
     barrier()
     wall_e2e = (time.perf_counter() - t0) / a.steps * 1e3
@@ -279,7 +290,8 @@ def main():
         match = {"metric": "match pairs/s (enhancedMatch, thr 0.85)", "n_ref": nr, "n_tar": nt, "ms": ms_match,
                  "pairs_per_s": nr * nt / (ms_match * 1e-3), "matches": int(bufs[10].item()), "reverse_rows_searched": rev_rows,
                  "algorithmic_tflops": 2 * 768 * (nr * nt + rev_rows * nr) / (ms_match * 1e-3) / 1e12,
-                 "path": "exact FP32-product / FP64-sum CUDA-core kernel (tensor-core pass not enabled in this round)"}
+                 "path": "tcgen05 FP16 candidate pass (top-8 per row) + exact FP32-product/FP64-sum re-rank with guard; "
+                         "rows on the tensor-core path / exact-fallback rows since start: %d / %d" % s3d.match_stats()}
 
     time.sleep(0.3)
     sampler.stop()

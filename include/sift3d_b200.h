@@ -88,6 +88,11 @@ S3D_API uint64_t s3d_launch_count(void);
  * `vol` is HOST memory, x fastest (xs=1, ys=nx, zs=nx*ny; Src/Util/cTexImage.cc:28-30); it is
  * copied and never written.  Pinned host memory is copied asynchronously. */
 S3D_API int s3d_create(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out);
+/* Same, without waiting for the copy: the H2D transfer, max|v| and the division are only ENQUEUED on
+ * the handle's stream.  `vol` must be pinned host memory and must stay alive and unchanged until
+ * s3d_run / s3d_wait on this handle has returned.  Lets the upload of volume k+1 overlap the
+ * extraction of volume k (each handle has its own stream unless params.stream is set). */
+S3D_API int s3d_create_async(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out);
 /* Same, for a volume already resident in device memory (HBM-resident timing, chained pipelines). */
 S3D_API int s3d_create_device(const float* d_vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out);
 /* CSIFT3D::KpSiftAlgorithm()  Src/cSIFT3D.cc:165-235: Initialize, Gaussian scale space, DoG,
