@@ -99,6 +99,18 @@ def lib():
     L.s3d_match_stats.restype = None
     L.s3d_level_info.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.s3d_device_descriptors.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int)]
+    ip = C.POINTER(C.c_int)
+    L.s3d_slab_extent.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.c_int, ip]
+    L.s3d_slab_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
+    L.s3d_slab_local_max.argtypes = [vp, C.POINTER(C.c_float)]
+    L.s3d_slab_begin.argtypes = [vp, C.c_float]
+    L.s3d_slab_info.argtypes = [vp, ip, ip, ip]
+    L.s3d_slab_seed.argtypes = [vp, C.c_int]
+    L.s3d_slab_octave.argtypes = [vp, C.c_int]
+    L.s3d_slab_level_buffer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), ip]
+    L.s3d_slab_get_maxima.argtypes = [vp, vp, C.c_int]
+    L.s3d_slab_set_maxima.argtypes = [vp, vp, C.c_int]
+    L.s3d_slab_finish.argtypes = [vp]
     _lib = L
     return L
 

@@ -324,6 +324,16 @@ struct s3d_ctx {
     float* d_desc = nullptr;
     int n_rechecked = 0, n_flipped = 0;
     bool ran = false, levels_alive = false, queued = false, h2d_pending = false;
+    // z-slab sharding.  Unsharded: slab = false, za = p0 = 0, zb = p1 = nz_o.
+    // A shard OWNS global planes [p0[o], p1[o]) of octave o and keeps local buffers for planes
+    // [za[o], zb[o]) (owned + halo).  nz / dims[][2] / nvox[] stay the GLOBAL sizes.
+    bool slab = false;
+    int own0 = 0, own1 = 0, halo = 0;      // owned octave-0 planes, halo depth (planes, every octave)
+    int za[kMaxOct], zb[kMaxOct], p0[kMaxOct], p1[kMaxOct];
+    int stage = 0;                          // 0 created, 1 initialised, 2 + o = octave o done, 100 sparse done
+    int next_octave = 0;
+    size_t lvox(int o) const { return (size_t)dims[o][0] * dims[o][1] * (size_t)(zb[o] - za[o]); }
+    size_t plane(int o) const { return (size_t)dims[o][0] * dims[o][1]; }
     cudaEvent_t ev[8];
     bool ev_ok = false;
     double timers[10] = {0};
@@ -505,8 +515,26 @@ void s3d_destroy(s3d_handle c) {
 // Initialize (Src/cSIFT3D.cc:237-266) + Build_Gaussian_Scale_Space (:268-319) +
 // Build_DOG_Scale_Space (:346-360; fused into the Z pass) + Detect_KeyPoints (:362-425) +
 // Assign_Orientation (:427-482) + Extract_Description (:484-502).
-static int run_impl(s3d_ctx* c) {
-    if (c->ran) return fail(S3D_ERR_STATE, "s3d_run called twice on one handle (KpSiftAlgorithm is single-shot)");
+// ---- the pipeline in stages (shared by the unsharded run and the z-slab shards) ----------------
+//
+// Initialize (Src/cSIFT3D.cc:237-266) -> per octave Build_Gaussian_Scale_Space (:268-319) with
+// Build_DOG_Scale_Space (:346-360) fused into the Z pass -> Detect_KeyPoints (:362-425) ->
+// Assign_Orientation (:427-482) -> Extract_Description (:484-502).
+
+static int halo_for(const s3d_ctx* c) {
+    // planes a shard needs beyond its owned range: the blur chain must leave every DoG level valid
+    // on owned +-1 (detection neighbours), and the descriptor window reaches ceil(r/u)+1 planes
+    // (r = 2*7.0711*scale, Src/cSIFT3D.cc:1155-1156, clamped windows :1182-1198, +1 for the gradient)
+    int cum = 0;
+    for (int i = 0; i < c->G; i++) cum += c->taps[i].hw;
+    const int blur_need = 1 + cum + c->G;  // low side needs 1 + sum(hw); high side one more plane per level
+    const float ratio = host_level_scale(0, c->L, c->L, c->prm.sigma_default);
+    const int desc_need = (int)ceilf(2.0f * 7.071067812f * ratio) + 2;
+    return std::max(blur_need, desc_need);
+}
+
+static int stage_init(s3d_ctx* c) {
+    if (c->stage != 0) return fail(S3D_ERR_STATE, "already initialised (KpSiftAlgorithm is single-shot)");
     cudaStream_t st = c->stream;
     S3D_CUDA(cudaSetDevice(c->device));
     const int L = c->L, G = c->G, D = c->D;
@@ -518,11 +546,10 @@ static int run_impl(s3d_ctx* c) {
         c->h2d_pending = false;
     }
     S3D_CUDA(cudaEventRecord(c->ev[0], st));
-    // ---- Initialize --------------------------------------------------------------------------
     int mn = std::min(c->nx, std::min(c->ny, c->nz));
     c->noct = (int)log2f((float)mn) - 3 + 1;  // :254-255
     if (c->noct < 1 || c->noct > kMaxOct) return fail(S3D_ERR_ARG, "octave count %d out of range", c->noct);
-    if (1 + c->noct * D > 256) return fail(S3D_ERR_ARG, "too many levels");
+    if (1 + c->noct * D > 255) return fail(S3D_ERR_ARG, "too many levels");
     {
         int nx = c->nx, ny = c->ny, nz = c->nz;
         for (int o = 0; o < c->noct; o++) {
@@ -535,14 +562,40 @@ static int run_impl(s3d_ctx* c) {
     for (int i = 0; i < G; i++)
         if (host_taps(c->sig[i], &c->taps[i]) < 0)
             return fail(S3D_ERR_ARG, "sigma %g needs more than %d taps per side", c->sig[i], kMaxHW);
+    for (int o = 0; o < c->noct; o++) {
+        const int nzo = c->dims[o][2];
+        if (!c->slab) {
+            c->p0[o] = c->za[o] = 0; c->p1[o] = c->zb[o] = nzo;
+        } else {
+            // plane k of octave o is owned iff own0 <= k * 2^o < own1 (== the owner of plane 2k one octave down)
+            const int sh = 1 << o;
+            c->p0[o] = std::min(nzo, (c->own0 + sh - 1) >> o);
+            c->p1[o] = std::min(nzo, (c->own1 + sh - 1) >> o);
+            if (o > 0) {  // nz/2 truncation can drop the last plane of an odd level
+                c->p0[o] = std::min(c->p0[o], nzo);
+                c->p1[o] = std::min(c->p1[o], nzo);
+            }
+            c->za[o] = std::max(0, c->p0[o] - c->halo);
+            c->zb[o] = std::min(nzo, c->p1[o] + c->halo);
+            if (c->p1[o] <= c->p0[o]) { c->za[o] = c->zb[o] = c->p0[o]; }  // owns nothing here
+        }
+    }
     c->gss.assign((size_t)c->noct * G, nullptr);
     c->dog.assign((size_t)c->noct * D, nullptr);
+    size_t tmp_elems = 4;
     for (int o = 0; o < c->noct; o++) {
-        const size_t bytes = std::max<size_t>(c->nvox[o], 4) * sizeof(float);
+        const size_t bytes = std::max<size_t>(c->lvox(o), 4) * sizeof(float);
+        tmp_elems = std::max(tmp_elems, c->lvox(o));
         for (int i = 0; i < G; i++) S3D_CUDA(cudaMallocAsync((void**)&c->gss[o * G + i], bytes, st));
         for (int i = 0; i < D; i++) S3D_CUDA(cudaMallocAsync((void**)&c->dog[o * D + i], bytes, st));
     }
-    for (int i = 0; i < 2; i++) S3D_CUDA(cudaMallocAsync((void**)&c->d_tmp[i], c->n0 * sizeof(float), st));
+    for (int i = 0; i < 2; i++) S3D_CUDA(cudaMallocAsync((void**)&c->d_tmp[i], tmp_elems * sizeof(float), st));
+    if (c->slab && getenv("S3D_SLAB_POISON")) {  // tests: a halo plane that was never filled must show up as NaN
+        for (int o = 0; o < c->noct; o++) {
+            for (int i = 0; i < G; i++) S3D_CUDA(cudaMemsetAsync(c->gss[o * G + i], 0xFF, c->lvox(o) * sizeof(float), st));
+            for (int i = 0; i < D; i++) S3D_CUDA(cudaMemsetAsync(c->dog[o * D + i], 0xFF, c->lvox(o) * sizeof(float), st));
+        }
+    }
     c->levels_alive = true;
     S3D_CUDA(cudaMallocAsync((void**)&c->d_thres, sizeof(float) * c->noct * L, st));
     {
@@ -553,41 +606,81 @@ static int run_impl(s3d_ctx* c) {
         S3D_CUDA(cudaStreamSynchronize(st));  // hm is a stack object
     }
     S3D_CUDA(cudaEventRecord(c->ev[1], st));
+    c->stage = 1;
+    c->next_octave = 0;
+    return S3D_OK;
+}
 
-    // ---- Gaussian scale space + DoG ------------------------------------------------------------
-    for (int o = 0; o < c->noct; o++) {
-        const int nx = c->dims[o][0], ny = c->dims[o][1], nz = c->dims[o][2];
-        for (int i = 0; i < G; i++) {
-            float* dst = c->gss[o * G + i];
-            if (i == 0 && o > 0) {
-                // octave seed = even-index decimation of level L of the previous octave (:311)
-                ProfScope ps(&c->prof, K_DOWNSAMPLE, 8.0 * c->nvox[o]);
-                S3D_LAUNCH(downsample_kernel, s3d_blocks(c->nvox[o], 256), 256, 0, st, c->gss[(o - 1) * G + L],
-                           c->dims[o - 1][0], c->dims[o - 1][1], dst, nx, ny, nz);
-                continue;
+// Octave seed = even-index decimation of level L of the previous octave (:311), owned planes only
+// (a shard's halo planes of the seed come from their owners, s3d_slab_level_buffer + exchange).
+static int stage_seed(s3d_ctx* c, int o) {
+    cudaStream_t st = c->stream;
+    const int L = c->L, G = c->G;
+    const int nown = c->p1[o] - c->p0[o];
+    if (o < 1 || nown <= 0) return S3D_OK;
+    const int nx = c->dims[o][0], ny = c->dims[o][1];
+    const float* src = c->gss[(o - 1) * G + L] + (size_t)(2 * c->p0[o] - c->za[o - 1]) * c->plane(o - 1);
+    float* dst = c->gss[o * G] + (size_t)(c->p0[o] - c->za[o]) * c->plane(o);
+    const size_t nout = (size_t)nown * c->plane(o);
+    ProfScope ps(&c->prof, K_DOWNSAMPLE, 8.0 * nout);
+    S3D_LAUNCH(downsample_kernel, s3d_blocks(nout, 256), 256, 0, st, src, c->dims[o - 1][0], c->dims[o - 1][1], dst, nx, ny, nown);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+// Levels of one octave over the local planes [za, zb): X -> Y -> Z (:609-617); the Z pass of level
+// i >= 1 also emits DoG[i-1] = G[i-1] - G[i] and (unsharded) folds max|DoG| into its slot.  A shard
+// takes the maxima over its OWNED planes only (halo planes hold partial results) with maxabs_kernel.
+static int stage_octave(s3d_ctx* c, int o) {
+    cudaStream_t st = c->stream;
+    const int L = c->L, G = c->G, D = c->D;
+    (void)L;
+    const int nx = c->dims[o][0], ny = c->dims[o][1], nz = c->zb[o] - c->za[o];
+    if (nz <= 0) return S3D_OK;
+    unsigned* scratch_slot = c->d_slots + 255;  // sink for the fused max of a shard's Z passes
+    for (int i = 0; i < G; i++) {
+        if (i == 0 && o > 0) continue;  // seed already in place
+        float* dst = c->gss[o * G + i];
+        const float* src = (o == 0 && i == 0) ? c->d_input : c->gss[o * G + i - 1];
+        const Taps& t = c->taps[i];
+        blur_pass(src, c->d_tmp[0], nx, ny, nz, 0, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
+        blur_pass(c->d_tmp[0], c->d_tmp[1], nx, ny, nz, 1, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
+        if (i >= 1) {
+            unsigned* slot = c->d_slots + 1 + o * D + i - 1;
+            blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, src, c->dog[o * D + i - 1], c->slab ? scratch_slot : slot, st,
+                      &c->prof);
+            if (c->slab && c->p1[o] > c->p0[o]) {
+                const size_t n = (size_t)(c->p1[o] - c->p0[o]) * c->plane(o);
+                const float* own = c->dog[o * D + i - 1] + (size_t)(c->p0[o] - c->za[o]) * c->plane(o);
+                ProfScope ps(&c->prof, K_MAXABS, 4.0 * n);
+                S3D_LAUNCH(maxabs_kernel, (unsigned)std::min<size_t>(s3d_blocks(n / 4 + 1, 256), 148 * 16), 256, 0, st, own, n, slot);
             }
-            const float* src = (o == 0 && i == 0) ? c->d_input : c->gss[o * G + i - 1];
-            const Taps& t = c->taps[i];
-            // X -> Y -> Z (:609-617); the Z pass of level i >= 1 also emits DoG[i-1] = G[i-1] - G[i]
-            blur_pass(src, c->d_tmp[0], nx, ny, nz, 0, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
-            blur_pass(c->d_tmp[0], c->d_tmp[1], nx, ny, nz, 1, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
-            if (i >= 1)
-                blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, src, c->dog[o * D + i - 1], c->d_slots + 1 + o * D + i - 1, st,
-                          &c->prof);
-            else
-                blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
+        } else {
+            blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
         }
     }
     S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+static int stage_sparse(s3d_ctx* c) {
+    cudaStream_t st = c->stream;
+    const int L = c->L, G = c->G, D = c->D;
     S3D_CUDA(cudaEventRecord(c->ev[2], st));
+    // level pointers as seen with GLOBAL voxel indices (virtual origin for a shard's local planes)
+    auto vdog = [&](int o, int i) { return c->dog[o * D + i] - (ptrdiff_t)c->za[o] * (ptrdiff_t)c->plane(o); };
+    auto vgss = [&](int o, int i) { return c->gss[o * G + i] - (ptrdiff_t)c->za[o] * (ptrdiff_t)c->plane(o); };
 
     // ---- Detection -------------------------------------------------------------------------------
     std::vector<uint32_t> gb_base((size_t)c->noct * L + 1, 0);
-    for (int o = 0; o < c->noct; o++)
-        for (int j = 0; j < L; j++)
-            gb_base[o * L + j + 1] = gb_base[o * L + j] + s3d_blocks(c->nvox[o], kDetectChunk);
-    const int nblk = (int)gb_base[(size_t)c->noct * L];
-    const unsigned stage_cap = (unsigned)std::max<size_t>(65536, c->n0 / 32);
+    size_t own_total = 0;
+    for (int o = 0; o < c->noct; o++) {
+        const size_t nown = (size_t)std::max(0, c->p1[o] - c->p0[o]) * c->plane(o);
+        own_total += nown;
+        for (int j = 0; j < L; j++) gb_base[o * L + j + 1] = gb_base[o * L + j] + s3d_blocks(nown, kDetectChunk);
+    }
+    const int nblk = std::max<int>(1, (int)gb_base[(size_t)c->noct * L]);
+    const unsigned stage_cap = (unsigned)std::max<size_t>(65536, own_total / 28);
     int *d_blk_cnt = nullptr, *d_blk_off = nullptr, *d_total = nullptr;
     StageEntry* d_stage = nullptr;
     unsigned* d_stage_count = nullptr;
@@ -599,15 +692,19 @@ static int run_impl(s3d_ctx* c) {
     S3D_CUDA(cudaMallocAsync((void**)&d_stage_count, sizeof(unsigned), st));
     S3D_CUDA(cudaMemsetAsync(d_stage_count, 0, sizeof(unsigned), st));
     S3D_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int) * 4, st));
-    for (int o = 0; o < c->noct; o++)
+    S3D_CUDA(cudaMemsetAsync(d_blk_cnt, 0, sizeof(int) * nblk, st));
+    for (int o = 0; o < c->noct; o++) {
+        const ll vb = (ll)c->p0[o] * (ll)c->plane(o), ve = (ll)c->p1[o] * (ll)c->plane(o);
+        if (ve <= vb) continue;
         for (int j = 1; j <= L; j++) {
             const int unit = o * L + (j - 1);
-            ProfScope ps(&c->prof, K_DETECT, 4.0 * c->nvox[o]);
-            S3D_LAUNCH(detect_kernel, s3d_blocks(c->nvox[o], kDetectChunk), 256, 0, st, c->dog[o * D + j - 1],
-                       c->dog[o * D + j], c->dog[o * D + j + 1], c->dims[o][0], c->dims[o][1], c->dims[o][2],
-                       c->d_slots + 1 + o * D + j, c->prm.peak_thresh, (uint32_t)unit, gb_base[unit], d_blk_cnt, d_stage,
-                       d_stage_count, stage_cap, c->d_thres + unit);
+            ProfScope ps(&c->prof, K_DETECT, 4.0 * (double)(ve - vb));
+            S3D_LAUNCH(detect_kernel, s3d_blocks((size_t)(ve - vb), kDetectChunk), 256, 0, st, vdog(o, j - 1), vdog(o, j),
+                       vdog(o, j + 1), c->dims[o][0], c->dims[o][1], c->dims[o][2], c->d_slots + 1 + o * D + j,
+                       c->prm.peak_thresh, (uint32_t)unit, gb_base[unit], d_blk_cnt, d_stage, d_stage_count, stage_cap,
+                       c->d_thres + unit, vb, ve);
         }
+    }
     {
         ProfScope ps(&c->prof, K_COMPACT, 8.0 * nblk);
         S3D_LAUNCH(scan_kernel, 1, 1024, 0, st, d_blk_cnt, d_blk_off, nblk, d_total);
@@ -635,7 +732,7 @@ static int run_impl(s3d_ctx* c) {
     for (int o = 0; o < c->noct; o++) {
         for (int k = 0; k < 3; k++) tab.dims[o][k] = c->dims[o][k];
         for (int i = 0; i < G; i++) {
-            tab.gss[o * G + i] = c->gss[o * G + i];
+            tab.gss[o * G + i] = vgss(o, i);
             tab.scale[o * G + i] = host_level_scale(o, i, L, c->prm.sigma_default);
         }
     }
@@ -712,7 +809,19 @@ static int run_impl(s3d_ctx* c) {
     for (void* q : tmp) if (q) cudaFreeAsync(q, st);
     S3D_CUDA(cudaEventRecord(c->ev[6], st));
     c->queued = true;
+    c->stage = 100;
     return S3D_OK;
+}
+
+static int run_impl(s3d_ctx* c) {
+    if (c->ran || c->stage != 0) return fail(S3D_ERR_STATE, "s3d_run called twice on one handle (KpSiftAlgorithm is single-shot)");
+    if (c->slab) return fail(S3D_ERR_STATE, "a z-slab shard is driven stage by stage (s3d_slab_*), not by s3d_run");
+    S3D_TRY(stage_init(c));
+    for (int o = 0; o < c->noct; o++) {
+        S3D_TRY(stage_seed(c, o));
+        S3D_TRY(stage_octave(c, o));
+    }
+    return stage_sparse(c);
 }
 
 int s3d_run_async(s3d_handle c) {
@@ -746,6 +855,169 @@ int s3d_wait(s3d_handle c) {
 int s3d_run(s3d_handle c) {
     int r = s3d_run_async(c);
     if (r != S3D_OK) return r;
+    return s3d_wait(c);
+}
+
+// ---- z-slab shards ---------------------------------------------------------
+// One handle per shard (one process per GPU, or several logical shards on one device).  The caller
+// drives the stages in lockstep over all shards and moves planes between the shards' level buffers
+// (s3d_slab_level_buffer) and scalars (maxima) between the stages: NCCL send/recv + all-reduce in
+// 3dsift_b200/dist.py.  Every stage only enqueues work on the handle's stream unless noted.
+
+static int slab_halo_from_params(const s3d_params* p, int* halo) {
+    s3d_ctx tmp;
+    s3d_params def;
+    s3d_default_params(&def);
+    tmp.prm = p ? *p : def;
+    tmp.L = tmp.prm.num_kp_levels;
+    if (tmp.L < 1 || tmp.L + 3 > kMaxG) return fail(S3D_ERR_ARG, "num_kp_levels %d unsupported", tmp.L);
+    tmp.G = tmp.L + 3;
+    host_sigmas(tmp.L, tmp.prm.sigma_default, tmp.prm.sigma_n_default, tmp.sig);
+    for (int i = 0; i < tmp.G; i++)
+        if (host_taps(tmp.sig[i], &tmp.taps[i]) < 0) return fail(S3D_ERR_ARG, "sigma %g too wide", tmp.sig[i]);
+    *halo = halo_for(&tmp);
+    return S3D_OK;
+}
+
+int s3d_slab_extent(int nz, int own0, int own1, const s3d_params* p, int octave, int* out4) {
+    clear_error();
+    if (!out4 || nz < 1 || own0 < 0 || own1 < own0 || own1 > nz || octave < 0 || octave >= kMaxOct) return fail(S3D_ERR_ARG, "bad argument");
+    int halo = 0;
+    S3D_TRY(slab_halo_from_params(p, &halo));
+    int nzo = nz;
+    for (int o = 0; o < octave; o++) nzo /= 2;
+    const int sh = 1 << octave;
+    int p0 = std::min(nzo, (own0 + sh - 1) >> octave), p1 = std::min(nzo, (own1 + sh - 1) >> octave);
+    int za = std::max(0, p0 - halo), zb = std::min(nzo, p1 + halo);
+    if (p1 <= p0) za = zb = p0;
+    out4[0] = za; out4[1] = zb; out4[2] = p0; out4[3] = p1;
+    return S3D_OK;
+}
+
+int s3d_slab_create(const float* vol_ext, int on_device, int nx, int ny, int nz, int own0, int own1, const s3d_params* p,
+                    s3d_handle* out) {
+    clear_error();
+    if (!vol_ext || !out || own0 < 0 || own1 <= own0 || own1 > nz) return fail(S3D_ERR_ARG, "bad slab arguments");
+    s3d_ctx* c = new s3d_ctx();
+    int r = ctx_common_init(c, nx, ny, nz, p);
+    if (r == S3D_OK) r = slab_halo_from_params(&c->prm, &c->halo);
+    if (r != S3D_OK) { s3d_destroy(c); return r; }
+    c->slab = true;
+    c->own0 = own0; c->own1 = own1;
+    const int za = std::max(0, own0 - c->halo), zb = std::min(nz, own1 + c->halo);
+    const size_t plane = (size_t)nx * ny, nloc = plane * (size_t)(zb - za);
+    auto body = [&]() -> int {
+        // d_input first holds the raw local planes; s3d_slab_begin normalises them in place
+        S3D_CUDA(cudaMallocAsync((void**)&c->d_input, nloc * sizeof(float), c->stream));
+        S3D_CUDA(cudaMallocAsync((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
+        S3D_CUDA(cudaMemsetAsync(c->d_slots, 0, 256 * sizeof(unsigned), c->stream));
+        S3D_CUDA(cudaMemcpyAsync(c->d_input, vol_ext, nloc * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                 c->stream));
+        const size_t nown = plane * (size_t)(own1 - own0);
+        ProfScope ps(&c->prof, K_MAXABS, 4.0 * nown);
+        S3D_LAUNCH(maxabs_kernel, (unsigned)std::min<size_t>(s3d_blocks(nown / 4 + 1, 256), 148 * 16), 256, 0, c->stream,
+                   c->d_input + plane * (size_t)(own0 - za), nown, c->d_slots);
+        S3D_CUDA(cudaGetLastError());
+        S3D_CUDA(cudaStreamSynchronize(c->stream));  // `vol_ext` may be released by the caller
+        return S3D_OK;
+    };
+    r = body();
+    if (r != S3D_OK) { s3d_destroy(c); return r; }
+    *out = c;
+    return S3D_OK;
+}
+
+int s3d_slab_local_max(s3d_handle c, float* mx) {
+    clear_error();
+    if (!c || !mx || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
+    S3D_CUDA(cudaSetDevice(c->device));
+    S3D_CUDA(cudaMemcpyAsync(mx, c->d_slots, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    return S3D_OK;
+}
+
+int s3d_slab_begin(s3d_handle c, float global_max) {
+    clear_error();
+    if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
+    if (c->stage != 0) return fail(S3D_ERR_STATE, "s3d_slab_begin called twice");
+    S3D_CUDA(cudaSetDevice(c->device));
+    S3D_CUDA(cudaMemcpyAsync(c->d_slots, &global_max, sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    S3D_CUDA(cudaStreamSynchronize(c->stream));  // global_max is a stack value
+    const int za = std::max(0, c->own0 - c->halo), zb = std::min(c->nz, c->own1 + c->halo);
+    const size_t nloc = (size_t)c->nx * c->ny * (size_t)(zb - za);
+    {
+        ProfScope ps(&c->prof, K_NORMALIZE, 8.0 * nloc);
+        S3D_LAUNCH(normalize_kernel, (unsigned)std::min<size_t>(s3d_blocks(nloc / 4 + 1, 256), 148 * 16), 256, 0, c->stream,
+                   c->d_input, c->d_input, nloc, c->d_slots);
+    }
+    S3D_TRY(stage_init(c));
+    return stage_octave(c, 0);
+}
+
+int s3d_slab_info(s3d_handle c, int* noct, int* halo, int* levels_per_octave) {
+    if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
+    if (c->stage < 1) return fail(S3D_ERR_STATE, "s3d_slab_begin first");
+    if (noct) *noct = c->noct;
+    if (halo) *halo = c->halo;
+    if (levels_per_octave) *levels_per_octave = c->G;
+    return S3D_OK;
+}
+
+int s3d_slab_seed(s3d_handle c, int octave) {
+    clear_error();
+    if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
+    if (c->stage < 1 || octave < 1 || octave >= c->noct) return fail(S3D_ERR_STATE, "bad octave / order");
+    S3D_CUDA(cudaSetDevice(c->device));
+    return stage_seed(c, octave);
+}
+
+int s3d_slab_octave(s3d_handle c, int octave) {
+    clear_error();
+    if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
+    if (c->stage < 1 || octave < 1 || octave >= c->noct) return fail(S3D_ERR_STATE, "bad octave / order");
+    S3D_CUDA(cudaSetDevice(c->device));
+    return stage_octave(c, octave);
+}
+
+int s3d_slab_level_buffer(s3d_handle c, int which, int idx, float** d_ptr, int* ext4) {
+    if (!c || !c->slab || !d_ptr || !ext4) return fail(S3D_ERR_ARG, "bad argument");
+    if (c->stage < 1 || !c->levels_alive) return fail(S3D_ERR_STATE, "levels not allocated");
+    const int per = which == 0 ? c->G : c->D;
+    if (which < 0 || which > 1 || idx < 0 || idx >= c->noct * per) return fail(S3D_ERR_ARG, "level index out of range");
+    const int o = idx / per;
+    *d_ptr = which == 0 ? c->gss[idx] : c->dog[idx];
+    ext4[0] = c->za[o]; ext4[1] = c->zb[o]; ext4[2] = c->p0[o]; ext4[3] = c->p1[o];
+    return S3D_OK;
+}
+
+int s3d_slab_get_maxima(s3d_handle c, float* out, int n) {
+    clear_error();
+    if (!c || !c->slab || !out) return fail(S3D_ERR_ARG, "bad argument");
+    if (c->stage < 1) return fail(S3D_ERR_STATE, "s3d_slab_begin first");
+    n = std::min(n, c->noct * c->D);
+    S3D_CUDA(cudaSetDevice(c->device));
+    S3D_CUDA(cudaMemcpyAsync(out, c->d_slots + 1, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    return S3D_OK;
+}
+
+int s3d_slab_set_maxima(s3d_handle c, const float* in, int n) {
+    clear_error();
+    if (!c || !c->slab || !in) return fail(S3D_ERR_ARG, "bad argument");
+    if (c->stage < 1) return fail(S3D_ERR_STATE, "s3d_slab_begin first");
+    n = std::min(n, c->noct * c->D);
+    S3D_CUDA(cudaSetDevice(c->device));
+    S3D_CUDA(cudaMemcpyAsync(c->d_slots + 1, in, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    return S3D_OK;
+}
+
+int s3d_slab_finish(s3d_handle c) {
+    clear_error();
+    if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
+    if (c->stage != 1) return fail(S3D_ERR_STATE, "s3d_slab_finish out of order");
+    S3D_CUDA(cudaSetDevice(c->device));
+    S3D_TRY(stage_sparse(c));
     return s3d_wait(c);
 }
 
@@ -822,7 +1094,8 @@ int s3d_get_level(s3d_handle c, int which, int idx, float* out) {
     if (which < 0 || which > 1 || idx < 0 || idx >= c->noct * per) return fail(S3D_ERR_ARG, "level index out of range");
     const float* src = which == 0 ? c->gss[idx] : c->dog[idx];
     S3D_CUDA(cudaSetDevice(c->device));
-    S3D_CUDA(cudaMemcpyAsync(out, src, c->nvox[idx / per] * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    // (a z-slab shard returns its local planes [za, zb) of the level, see s3d_slab_extent)
+    S3D_CUDA(cudaMemcpyAsync(out, src, c->lvox(idx / per) * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     S3D_CUDA(cudaStreamSynchronize(c->stream));
     return S3D_OK;
 }
@@ -851,7 +1124,8 @@ int s3d_get_input(s3d_handle c, float* out) {
     clear_error();
     if (!c || !out) return fail(S3D_ERR_ARG, "null argument");
     S3D_CUDA(cudaSetDevice(c->device));
-    S3D_CUDA(cudaMemcpyAsync(out, c->d_input, c->n0 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    const size_t nin = c->slab ? (size_t)c->nx * c->ny * (size_t)(std::min(c->nz, c->own1 + c->halo) - std::max(0, c->own0 - c->halo)) : c->n0;
+    S3D_CUDA(cudaMemcpyAsync(out, c->d_input, nin * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     S3D_CUDA(cudaStreamSynchronize(c->stream));
     return S3D_OK;
 }

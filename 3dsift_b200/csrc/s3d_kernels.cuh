@@ -112,14 +112,19 @@ __device__ __forceinline__ float warp_max(float v) {
 __global__ void __launch_bounds__(256) maxabs_kernel(const float* __restrict__ src, size_t n, unsigned* slot) {
     float m = 0.0f;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t n4 = n >> 2;
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // a shard's owned planes may start at any element: peel to 16-byte alignment
+    size_t head = ((16 - (reinterpret_cast<uintptr_t>(src) & 15)) & 15) >> 2;
+    head = head < n ? head : n;
+    if (gid < head) m = fabsf(src[gid]);
+    const float* body = src + head;
+    const size_t nb = n - head, n4 = nb >> 2;
+    const float4* s4 = reinterpret_cast<const float4*>(body);
+    for (size_t i = gid; i < n4; i += stride) {
         float4 v = s4[i];
         m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
-    for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        m = fmaxf(m, fabsf(src[i]));
+    for (size_t i = (n4 << 2) + gid; i < nb; i += stride) m = fmaxf(m, fabsf(body[i]));
     m = warp_max(m);
     if ((threadIdx.x & 31) == 0) atomic_max_abs(slot, m);
 }
@@ -334,17 +339,20 @@ __global__ void __launch_bounds__(256) detect_kernel(const float* __restrict__ D
                                                      const unsigned* __restrict__ maxslot, float peak, uint32_t unit,
                                                      uint32_t gb_base, int* __restrict__ blk_cnt,
                                                      StageEntry* __restrict__ stage, unsigned* stage_count,
-                                                     unsigned stage_cap, float* thres_out) {
+                                                     unsigned stage_cap, float* thres_out, ll vox_begin, ll vox_end) {
+    // [vox_begin, vox_end): the voxels this launch owns, as linear indices of the WHOLE level
+    // (nx, ny, nz are the level's global dims).  A z-slab shard passes pointers offset to a virtual
+    // origin so that global indices address its local planes; the unsharded run passes [0, total).
     __shared__ int warp_tot[8];
     __shared__ unsigned seg_base;
-    const ll total = (ll)nx * ny * nz;
+    const ll total = vox_end;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const ll wbase_vox = (ll)blockIdx.x * kDetectChunk + (ll)wid * 512;
+    const ll wbase_vox = vox_begin + (ll)blockIdx.x * kDetectChunk + (ll)wid * 512;
     const float thres = peak * __uint_as_float(*maxslot);
     if (blockIdx.x == 0 && threadIdx.x == 0 && thres_out) *thres_out = thres;
     // Phase 1 (every voxel, HBM-bound): |val| > thres  (val > thres || val < -thres, Src/cSIFT3D.cc:394)
     unsigned above = 0;
-    if (wbase_vox + 512 <= total) {
+    if (wbase_vox + 512 <= total && (reinterpret_cast<uintptr_t>(D0 + wbase_vox) & 15) == 0) {
         float4 f[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) f[q] = *(reinterpret_cast<const float4*>(D0 + wbase_vox) + q * 32 + lane);

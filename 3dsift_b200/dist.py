@@ -155,3 +155,295 @@ def extract_batch(volumes, group=None, **params):
         for b, kp, desc in part:
             out[b] = (kp, desc)
     return out
+
+
+# ---- one large volume in z-slabs (BASELINE.json configs[2]) ------------------------
+
+def slab_bounds(nz, shards):
+    """Owned octave-0 plane ranges: contiguous, balanced, even starts (so decimation pairs stay together)."""
+    b = [min(nz, (nz * r // shards) & ~1) for r in range(shards)] + [nz]
+    b[0] = 0
+    return b
+
+
+def needed_from(ext_src, ext_dst):
+    """Plane intervals [k0, k1) that shard `dst` must receive from shard `src` for one level: the part
+    of dst's halo ([za, p0) and [p1, zb)) that src owns.  ext = (za, zb, p0, p1) in global planes."""
+    za, zb, p0, p1 = ext_dst
+    s0, s1 = ext_src[2], ext_src[3]
+    out = []
+    for lo, hi in ((za, p0), (p1, zb)):
+        k0, k1 = max(lo, s0), min(hi, s1)
+        if k1 > k0:
+            out.append((k0, k1))
+    return out
+
+
+class _DevMem:
+    """Zero-copy view of raw device memory for torch (``torch.as_tensor(_DevMem(...), device='cuda')``)."""
+
+    def __init__(self, ptr, nelem):
+        self.__cuda_array_interface__ = {"shape": (int(nelem),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class SlabShard:
+    """One shard of a z-slab extraction: an s3d slab handle plus its plane bookkeeping."""
+
+    def __init__(self, gid, vol_ext, dims, own, params=None, device=-1, stream=None):
+        L = api.lib()
+        self.gid = gid
+        self.nx, self.ny, self.nz = dims
+        self.own = own
+        p = api.s3d_params()
+        L.s3d_default_params(C.byref(p))
+        for k, v in (params or {}).items():
+            setattr(p, k, v)
+        p.device = device
+        p.stream = C.c_void_p(int(stream)) if stream else None
+        self._p = p
+        self._h = C.c_void_p()
+        on_dev = hasattr(vol_ext, "is_cuda") and vol_ext.is_cuda
+        api.check(L.s3d_slab_create(api._ptr(vol_ext), int(on_dev), self.nx, self.ny, self.nz, own[0], own[1], C.byref(p),
+                                    C.byref(self._h)))
+
+    def local_max(self):
+        v = C.c_float()
+        api.check(api.lib().s3d_slab_local_max(self._h, C.byref(v)))
+        return float(v.value)
+
+    def begin(self, gmax):
+        api.check(api.lib().s3d_slab_begin(self._h, C.c_float(gmax)))
+        n, h, g = C.c_int(), C.c_int(), C.c_int()
+        api.check(api.lib().s3d_slab_info(self._h, C.byref(n), C.byref(h), C.byref(g)))
+        self.noct, self.halo, self.G = n.value, h.value, g.value
+
+    def seed(self, o):
+        api.check(api.lib().s3d_slab_seed(self._h, o))
+
+    def octave(self, o):
+        api.check(api.lib().s3d_slab_octave(self._h, o))
+
+    def level(self, which, idx):
+        """(torch tensor [local planes, ny_o*nx_o] aliasing the level buffer, (za, zb, p0, p1))."""
+        import torch
+        ptr = C.c_void_p()
+        ext = (C.c_int * 4)()
+        api.check(api.lib().s3d_slab_level_buffer(self._h, which, idx, C.byref(ptr), ext))
+        za, zb, p0, p1 = (int(v) for v in ext)
+        per = self.G if which == 0 else self.G - 1
+        o = idx // per
+        plane = (self.nx >> o) * (self.ny >> o)
+        n = (zb - za) * plane
+        if n == 0:
+            return None, (za, zb, p0, p1)
+        t = torch.as_tensor(_DevMem(ptr.value, n), device="cuda").view(zb - za, plane)
+        return t, (za, zb, p0, p1)
+
+    def maxima(self):
+        n = self.noct * (self.G - 1)
+        out = np.zeros(n, np.float32)
+        api.check(api.lib().s3d_slab_get_maxima(self._h, api._ptr(out), n))
+        return out
+
+    def set_maxima(self, m):
+        m = np.ascontiguousarray(m, np.float32)
+        api.check(api.lib().s3d_slab_set_maxima(self._h, api._ptr(m), len(m)))
+
+    def finish(self):
+        api.check(api.lib().s3d_slab_finish(self._h))
+
+    def results(self):
+        L = api.lib()
+        n = C.c_int()
+        api.check(L.s3d_num_keypoints(self._h, C.byref(n)))
+        k = n.value
+        kp = np.zeros(max(k, 1), api.KP_DTYPE)
+        desc = np.zeros((max(k, 1), api.DESC_LENGTH), np.float32)
+        api.check(L.s3d_get_keypoints(self._h, api._ptr(kp), api._ptr(desc)))
+        api.check(L.s3d_num_extrema(self._h, C.byref(n)))
+        e = n.value
+        ex = np.zeros(max(e, 1), api.KP_DTYPE)
+        codes = np.zeros(max(e, 1), np.int32)
+        xyz5 = np.zeros((max(e, 1), 5), np.int32)
+        api.check(L.s3d_get_extrema(self._h, api._ptr(ex), api._ptr(codes), api._ptr(xyz5)))
+        return dict(kp=kp[:k], desc=desc[:k], extrema=ex[:e], codes=codes[:e], xyz5=xyz5[:e])
+
+    def get_level_host(self, which, idx):
+        t, ext = self.level(which, idx)
+        return (None if t is None else t.cpu().numpy()), ext
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            api.lib().s3d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def exchange_plan(exts, owner_rank, my_rank):
+    """Halo fill of one level as a list of transfers, identical (and identically ordered) on every rank.
+    exts[g] = (za, zb, p0, p1) of shard g; owner_rank[g] = process that holds shard g.
+    Returns [(src_gid, dst_gid, k0, k1, kind)] with kind in {"copy", "send", "recv"} for this rank."""
+    plan = []
+    for d in range(len(exts)):
+        for s in range(len(exts)):
+            if s == d:
+                continue
+            for k0, k1 in needed_from(exts[s], exts[d]):
+                src_here, dst_here = owner_rank[s] == my_rank, owner_rank[d] == my_rank
+                if src_here and dst_here:
+                    plan.append((s, d, k0, k1, "copy"))
+                elif src_here:
+                    plan.append((s, d, k0, k1, "send"))
+                elif dst_here:
+                    plan.append((s, d, k0, k1, "recv"))
+    return plan
+
+
+def exchange_halos(levels, exts, owner_rank, my_rank, group=None):
+    """levels: {gid: 2-D tensor [zb-za, plane]} for the shards held by this rank (all the same level).
+    Fills every held shard's halo planes from their owners: device copies between shards of this
+    process, NCCL/gloo send/recv (one batch) between processes."""
+    import torch.distributed as dist
+    ops = []
+    for s, d, k0, k1, kind in exchange_plan(exts, owner_rank, my_rank):
+        if kind == "copy":
+            levels[d][k0 - exts[d][0]:k1 - exts[d][0]].copy_(levels[s][k0 - exts[s][0]:k1 - exts[s][0]])
+        elif kind == "send":
+            ops.append(dist.P2POp(dist.isend, levels[s][k0 - exts[s][0]:k1 - exts[s][0]], owner_rank[d], group))
+        else:
+            ops.append(dist.P2POp(dist.irecv, levels[d][k0 - exts[d][0]:k1 - exts[d][0]], owner_rank[s], group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
+def merge_shard_results(parts, num_kp_levels=3):
+    """Concatenate shard outputs in the reference's order (octave, level, z, y, x): shards partition
+    z, each shard's lists are already in raster order, so per (octave, level) unit the global list is
+    the shards' segments in shard order (App. B Q16)."""
+    def unit_of(o, l):
+        return o.astype(np.int64) * (num_kp_levels + 1) + l
+    out = {}
+    kp_units = [unit_of(p["kp"]["octave"], p["kp"]["level"]) for p in parts]
+    ex_units = [unit_of(p["xyz5"][:, 3], p["xyz5"][:, 4]) for p in parts]
+    def order(units):
+        key = np.concatenate(units) if units else np.zeros(0, np.int64)
+        shard = np.concatenate([np.full(len(u), i, np.int64) for i, u in enumerate(units)]) if units else key
+        pos = np.concatenate([np.arange(len(u), dtype=np.int64) for u in units]) if units else key
+        return np.lexsort((pos, shard, key))
+    ko, eo = order(kp_units), order(ex_units)
+    out["kp"] = np.concatenate([p["kp"] for p in parts])[ko]
+    out["desc"] = np.concatenate([p["desc"] for p in parts])[ko]
+    out["extrema"] = np.concatenate([p["extrema"] for p in parts])[eo]
+    out["codes"] = np.concatenate([p["codes"] for p in parts])[eo]
+    out["xyz5"] = np.concatenate([p["xyz5"] for p in parts])[eo]
+    return out
+
+
+def extract_slabs(volume, shards=None, group=None, params=None, keep=False):
+    """Full extraction of ONE volume split into z-slabs.
+
+    * distributed (torch.distributed initialised, ``shards`` None): one shard per rank of ``group``;
+      every rank passes the same host ``volume`` ([nz, ny, nx] float32; only its own planes + halo
+      are uploaded) and receives the merged result.
+    * single process (``shards`` = G): G logical shards on the current device, same code path with
+      device copies instead of send/recv — the CI check that sharded == unsharded.
+
+    Returns dict(kp, desc, extrema, codes, xyz5[, shards]) in the reference's order."""
+    import torch
+    import torch.distributed as dist
+    distributed = shards is None and dist.is_initialized() and dist.get_world_size(group) > 1
+    if distributed:
+        world, me = dist.get_world_size(group), dist.get_rank(group)
+        G = world
+        owner = list(range(G))
+    else:
+        G = int(shards or 1)
+        world, me = 1, 0
+        owner = [0] * G
+    nz, ny, nx = (int(v) for v in volume.shape)
+    bounds = slab_bounds(nz, G)
+    held = [g for g in range(G) if owner[g] == me and bounds[g + 1] > bounds[g]]
+    L = api.lib()
+    p = api.s3d_params()
+    L.s3d_default_params(C.byref(p))
+    for k, v in (params or {}).items():
+        setattr(p, k, v)
+    nlev = p.num_kp_levels
+
+    def ext_of(g, o):
+        e = (C.c_int * 4)()
+        if bounds[g + 1] <= bounds[g]:
+            return (0, 0, 0, 0)
+        api.check(L.s3d_slab_extent(nz, bounds[g], bounds[g + 1], C.byref(p), o, e))
+        return tuple(int(v) for v in e)
+
+    # the shards run on torch's current stream so that the plane copies / NCCL calls below are
+    # ordered with the kernels (0 = the legacy default stream: pass its explicit handle, 0x1)
+    stream = torch.cuda.current_stream().cuda_stream or 1
+    sh = {}
+    for g in held:
+        za, zb, _, _ = ext_of(g, 0)
+        sh[g] = SlabShard(g, np.ascontiguousarray(volume[za:zb], dtype=np.float32), (nx, ny, nz), (bounds[g], bounds[g + 1]),
+                          params, device=torch.cuda.current_device(), stream=stream)
+    # global max|v| (data_scale, Src/cUtil.cc:538-550)
+    m = max([sh[g].local_max() for g in held] or [0.0])
+    if distributed:
+        t = torch.tensor([m], dtype=torch.float32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        m = float(t.item())
+    for g in held:
+        sh[g].begin(m)
+    any_s = sh[held[0]] if held else None
+    noct = any_s.noct if any_s else 0
+    Gl = any_s.G if any_s else nlev + 3
+    if distributed:  # ranks that hold nothing still take part in the collectives
+        t = torch.tensor([noct, Gl], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        noct, Gl = int(t[0]), int(t[1])
+    for o in range(1, noct):
+        for g in held:
+            sh[g].seed(o)
+        exts = [ext_of(g, o) for g in range(G)]
+        lv = {g: sh[g].level(0, o * Gl)[0] for g in held}
+        exchange_halos(lv, exts, owner, me, group)
+        for g in held:
+            sh[g].octave(o)
+    # global max|DoG| per level (Detect_KeyPoints threshold, Src/cSIFT3D.cc:384-385)
+    mx = np.zeros(noct * (Gl - 1), np.float32)
+    for g in held:
+        mx = np.maximum(mx, sh[g].maxima())
+    if distributed:
+        t = torch.from_numpy(mx).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        mx = t.cpu().numpy()
+    for g in held:
+        sh[g].set_maxima(mx)
+    # descriptor windows reach into the neighbours' planes: fill the halos of levels 1..L of every octave
+    for o in range(noct):
+        exts = [ext_of(g, o) for g in range(G)]
+        for i in range(1, nlev + 1):
+            lv = {g: sh[g].level(0, o * Gl + i)[0] for g in held}
+            exchange_halos(lv, exts, owner, me, group)
+    for g in held:
+        sh[g].finish()
+    mine = [(g, sh[g].results()) for g in held]
+    if distributed:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        allp = sorted((x for part in gathered for x in part), key=lambda t: t[0])
+    else:
+        allp = mine
+    out = merge_shard_results([r for _, r in allp], nlev)
+    if keep:
+        out["shards"] = sh
+        out["bounds"] = bounds
+    else:
+        for g in held:
+            sh[g].close()
+    return out

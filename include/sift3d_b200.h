@@ -65,7 +65,8 @@ typedef struct s3d_params {
     int exact_recheck;     /* 1 = re-evaluate orientation candidates whose accept/reject tests are
                               within a small margin in the reference's serial FP32 order */
     int profile;           /* 1 = bracket every kernel launch with CUDA events (s3d_get_kernel_stats) */
-    void* stream;          /* cudaStream_t to run on (caller keeps it alive); NULL = a private stream */
+    void* stream;          /* cudaStream_t to run on (caller keeps it alive); NULL = a private stream;
+                              (void*)1 = cudaStreamLegacy, the default stream */
 } s3d_params;
 
 typedef struct s3d_ctx* s3d_handle;
@@ -143,6 +144,46 @@ S3D_API int s3d_get_timers(s3d_handle h, double* t10);
 S3D_API int s3d_get_kernel_stats(s3d_handle h, int cap, int* n_classes, double* ms, long long* launches,
                                  double* alg_bytes);
 S3D_API const char* s3d_kernel_class_name(int cls);
+
+/* ---- one large volume in z-slabs over several GPUs (BASELINE.json configs[2]) ----
+ * The reference processes one volume in one address space (Src/cSIFT3D.cc:165-235).  Here shard r
+ * OWNS octave-0 planes [own0, own1) (plane k of octave o belongs to the owner of plane k*2^o) and
+ * keeps local level buffers for owned planes +- `halo`.  The caller steps all shards through the
+ * stages below in lockstep and moves data between them (3dsift_b200/dist.py: NCCL send/recv of
+ * planes, all-reduce(max) of scalars).  Results (levels on owned planes, detections, keypoints,
+ * descriptors) are identical to the unsharded run; concatenating the shards' lists per
+ * (octave, level) in shard order gives the reference's order.
+ *
+ *   s3d_slab_extent      local/owned plane ranges {za, zb, p0, p1} of an octave (no handle needed)
+ *   s3d_slab_create      vol_ext = raw planes [za, zb) of octave 0 (host or device); computes max|v|
+ *                        over the OWNED planes; blocks until the copy is done
+ *   s3d_slab_local_max   that maximum                      -> caller: all-reduce(max)
+ *   s3d_slab_begin       divide by the global maximum (data_scale, Src/cUtil.cc:552-561), allocate
+ *                        the pyramids, run octave 0
+ *   s3d_slab_seed(o)     decimate the owned planes of octave o from level L of octave o-1
+ *                        (DownSample_3D :506-533)          -> caller: fill the halo planes of
+ *                        Gaussian level o*G+0 from their owners (s3d_slab_level_buffer)
+ *   s3d_slab_octave(o)   levels 1.. of octave o + DoG, maxima over owned planes
+ *   s3d_slab_get_maxima / s3d_slab_set_maxima   max|DoG| per level (noct*D floats)
+ *                                                          -> caller: all-reduce(max)
+ *                        -> caller: fill the halo planes of Gaussian levels 1..L of every octave
+ *                           (descriptor windows reach up to `halo` planes beyond the owned range)
+ *   s3d_slab_finish      detection on the owned planes, orientation, description; blocks.  Then
+ *                        s3d_num_keypoints / s3d_get_keypoints / s3d_get_extrema as usual.
+ */
+S3D_API int s3d_slab_extent(int nz, int own0, int own1, const s3d_params* p, int octave, int* out4);
+S3D_API int s3d_slab_create(const float* vol_ext, int on_device, int nx, int ny, int nz, int own0, int own1,
+                            const s3d_params* p, s3d_handle* out);
+S3D_API int s3d_slab_local_max(s3d_handle h, float* mx);
+S3D_API int s3d_slab_begin(s3d_handle h, float global_max);
+S3D_API int s3d_slab_info(s3d_handle h, int* noct, int* halo, int* levels_per_octave);
+S3D_API int s3d_slab_seed(s3d_handle h, int octave);
+S3D_API int s3d_slab_octave(s3d_handle h, int octave);
+/* Device address of the local planes of a level (which: 0 Gaussian, 1 DoG) and {za, zb, p0, p1}. */
+S3D_API int s3d_slab_level_buffer(s3d_handle h, int which, int idx, float** d_ptr, int* ext4);
+S3D_API int s3d_slab_get_maxima(s3d_handle h, float* out, int n);
+S3D_API int s3d_slab_set_maxima(s3d_handle h, const float* in, int n);
+S3D_API int s3d_slab_finish(s3d_handle h);
 
 /* ---- free kernels (parity hooks ≙ Include/cSIFT3D.h:208-239) ------------------------------- */
 /* GaussianSmooth_3D  Src/cSIFT3D.cc:535-622 (host buffers in/out). */

@@ -137,3 +137,105 @@ def test_single_process_path_equals_oracle(port, synth):
         got = d.match_sharded(t, ref, tar, 0.85, ops=NumpyOps())
         want = port.match(t, ref, tar, 0.85)
         assert np.array_equal(got["gIdx"], want["gIdx"]) and np.array_equal(got["pairs"], want["pairs"])
+
+
+# ---- z-slab sharding: plane bookkeeping and the halo exchange (CPU, gloo) ---------------------------------
+
+def test_slab_bounds_and_extents(s3d):
+    import ctypes as C
+    d = importlib.import_module("3dsift_b200.dist")
+    L = s3d.lib()
+    p = s3d.api.s3d_params()
+    L.s3d_default_params(C.byref(p))
+    for nz, G in ((512, 8), (96, 3), (70, 2), (64, 4), (20, 8)):
+        b = d.slab_bounds(nz, G)
+        assert b[0] == 0 and b[-1] == nz and all(b[i] <= b[i + 1] for i in range(G)) and all(v % 2 == 0 for v in b[:-1])
+        nzo = nz
+        for o in range(4):
+            owned = []
+            for g in range(G):
+                if b[g + 1] <= b[g]:
+                    continue
+                e = (C.c_int * 4)()
+                assert L.s3d_slab_extent(nz, b[g], b[g + 1], C.byref(p), o, e) == 0
+                za, zb, p0, p1 = (int(v) for v in e)
+                assert 0 <= za <= p0 <= p1 <= zb <= nzo
+                if p1 > p0:
+                    assert za == max(0, p0 - 38) and zb == min(nzo, p1 + 38)     # default parameters: halo 38
+                    assert (p0 << o) >= b[g] and ((p1 - 1) << o) < b[g + 1]
+                owned.append((p0, p1))
+            assert owned[0][0] == 0 and owned[-1][1] == nzo                       # the owned ranges tile [0, nz_o)
+            assert all(owned[i][1] == owned[i + 1][0] for i in range(len(owned) - 1))
+            nzo //= 2
+
+
+def test_exchange_plan_covers_every_halo_plane_once():
+    d = importlib.import_module("3dsift_b200.dist")
+    exts = [(0, 20, 0, 8), (0, 28, 8, 16), (4, 32, 16, 24), (12, 32, 24, 32)]    # halo 12 > slab 8: multi-hop
+    for me in range(4):
+        plan = d.exchange_plan(exts, [0, 1, 2, 3], me)
+        got = sorted((k0, k1) for s, dd, k0, k1, kind in plan if dd == me and kind == "recv")
+        za, zb, p0, p1 = exts[me]
+        need = set(range(za, p0)) | set(range(p1, zb))
+        have = [k for k0, k1 in got for k in range(k0, k1)]
+        assert sorted(have) == sorted(need)
+        sends = [(s, dd, k0, k1) for s, dd, k0, k1, kind in plan if kind == "send"]
+        assert all(s == me and exts[me][2] <= k0 < k1 <= exts[me][3] for s, dd, k0, k1 in sends)
+    allcopy = d.exchange_plan(exts, [0, 0, 0, 0], 0)
+    assert all(kind == "copy" for *_, kind in allcopy) and len(allcopy) > 0
+
+
+def _halo_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d = importlib.import_module("3dsift_b200.dist")
+    exts = [(0, 14, 0, 10), (6, 20, 10, 20)]                   # 20 planes, halo 4
+    plane = 6
+    truth = torch.arange(20 * plane, dtype=torch.float32).view(20, plane)
+    za, zb, p0, p1 = exts[rank]
+    buf = torch.full((zb - za, plane), -1.0)
+    buf[p0 - za:p1 - za] = truth[p0:p1]                        # only the owned planes are valid
+    d.exchange_halos({rank: buf}, exts, [0, 1], rank)
+    q.put((rank, bool(torch.equal(buf, truth[za:zb]))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_halo_exchange_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port_no = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_halo_worker, args=(r, 2, port_no, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == {0: True, 1: True}
+
+
+def test_merge_shard_results_restores_reference_order(s3d):
+    d = importlib.import_module("3dsift_b200.dist")
+    KP = s3d.api.KP_DTYPE
+
+    def part(rows):                                            # rows: (octave, level, z)
+        kp = np.zeros(len(rows), KP)
+        xyz5 = np.zeros((len(rows), 5), np.int32)
+        for i, (o, l, z) in enumerate(rows):
+            kp[i]["octave"], kp[i]["level"], kp[i]["z"] = o, l, z
+            xyz5[i] = (0, 0, z, o, l)
+        return dict(kp=kp, desc=np.zeros((len(rows), 768), np.float32), extrema=kp.copy(), codes=np.ones(len(rows), np.int32), xyz5=xyz5)
+
+    a = part([(0, 1, 3), (0, 1, 5), (0, 2, 1), (1, 1, 2)])
+    b = part([(0, 1, 40), (0, 3, 33), (1, 1, 20), (1, 1, 21)])
+    m = d.merge_shard_results([a, b])
+    got = [(int(r["octave"]), int(r["level"]), int(r["z"])) for r in m["kp"]]
+    assert got == [(0, 1, 3), (0, 1, 5), (0, 1, 40), (0, 2, 1), (0, 3, 33), (1, 1, 2), (1, 1, 20), (1, 1, 21)]
+    assert [tuple(r[2:]) for r in m["xyz5"]] == [(z, o, l) for o, l, z in got]

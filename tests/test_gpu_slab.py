@@ -1,0 +1,63 @@
+"""z-slab sharded extraction must equal the unsharded extraction: every level
+bit-exact on the owned planes, the same detections, codes, keypoint records and descriptors in the
+same order.  G logical shards run on ONE device here (device copies instead of NCCL send/recv; the
+plan, the stages and the kernels are the ones the multi-process path uses)."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+os.environ["S3D_SLAB_POISON"] = "1"     # level buffers start as NaN: an unfilled halo plane cannot pass by luck
+
+
+def _unsharded(s3d, vol):
+    s = s3d.CSIFT3DFactory.CreateCSIFT3D(vol, keep_levels=True)
+    s.KpSiftAlgorithm()
+    return s
+
+
+def _same_records(a, b):
+    fields = [f for f in a.dtype.names if f != "desc"]
+    return all(np.array_equal(a[f], b[f]) for f in fields)
+
+
+@pytest.mark.parametrize("shape,shards", [((96, 64, 72), 2), ((96, 64, 72), 3), ((128, 48, 64), 4), ((70, 66, 68), 2)])
+def test_slabs_equal_unsharded(s3d, synth, shape, shards):
+    d = importlib.import_module("3dsift_b200.dist")
+    vol = synth.v_blobs(shape, seed=11)
+    ref = _unsharded(s3d, vol)
+    out = d.extract_slabs(vol, shards=shards, params=dict(keep_levels=1), keep=True)
+    G, D = 6, 5
+    nchecked = 0
+    for g, sh in out["shards"].items():
+        for o in range(sh.noct):
+            for which, per in ((0, G), (1, D)):
+                for i in range(per):
+                    got, (za, zb, p0, p1) = sh.get_level_host(which, o * per + i)
+                    if got is None or p1 <= p0:
+                        continue
+                    want = (ref.GET_GSS if which == 0 else ref.GET_DOG)(o * per + i)
+                    got = got.reshape(zb - za, *want.shape[1:])
+                    assert np.array_equal(got[p0 - za:p1 - za], want[p0:p1]), (g, o, which, i)
+                    nchecked += 1
+    assert nchecked > 20
+    kp_r, codes_r, xyz_r = ref.extrema()
+    assert np.array_equal(out["xyz5"], xyz_r)
+    assert np.array_equal(out["codes"], codes_r)
+    assert _same_records(out["extrema"], kp_r)
+    kps = ref.GetKeypoints()
+    assert len(out["kp"]) == len(kps) and len(kps) > 20
+    assert _same_records(out["kp"], kps)
+    assert np.array_equal(out["desc"], ref.descriptors)
+    for sh in out["shards"].values():
+        sh.close()
+
+
+def test_single_shard_is_the_plain_path(s3d, synth):
+    d = importlib.import_module("3dsift_b200.dist")
+    vol = synth.v_blobs((64, 64, 64), seed=2)
+    ref = _unsharded(s3d, vol)
+    out = d.extract_slabs(vol, shards=1)
+    assert _same_records(out["kp"], ref.GetKeypoints()) and np.array_equal(out["desc"], ref.descriptors)
