@@ -145,11 +145,12 @@ def selftest(device=-1):
     check(lib().s3d_selftest(device))
 
 
-MATCH_AUTO, MATCH_EXACT, MATCH_TENSOR = 0, 1, 2
+MATCH_AUTO, MATCH_EXACT, MATCH_TENSOR, MATCH_TENSOR_SINGLE, MATCH_TENSOR_PAIR = 0, 1, 2, 3, 4
 
 
 def set_match_path(path):
-    """0 auto / 1 exact CUDA-core kernel / 2 tensor-core candidate pass (results are identical)."""
+    """0 auto / 1 exact CUDA-core kernel / 2 tensor-core candidate pass (variant by size) / 3 tensor cores,
+    one CTA per tile / 4 tensor cores, CTA pairs with resident query tile (results are identical)."""
     check(lib().s3d_set_match_path(int(path)))
 
 

@@ -232,10 +232,11 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
 }
 
 // 0 = auto (tensor cores for large searches), 1 = exact CUDA-core kernel only, 2 = tensor cores always
-// (initial value from the environment: S3D_MATCH_PATH=0|1|2)
+// (kernel variant by size), 3 = tensor cores, one CTA per tile, 4 = tensor cores, CTA pairs with the
+// query tile resident in shared memory  (initial value from the environment: S3D_MATCH_PATH=0..4)
 static int initial_match_path() {
     const char* e = getenv("S3D_MATCH_PATH");
-    return (e && e[0] >= '0' && e[0] <= '2' && !e[1]) ? e[0] - '0' : 0;
+    return (e && e[0] >= '0' && e[0] <= '4' && !e[1]) ? e[0] - '0' : 0;
 }
 static std::atomic<int> g_match_path{initial_match_path()};
 static std::atomic<unsigned long long> g_tc_rows{0}, g_fb_rows{0};
@@ -279,10 +280,10 @@ static int search_device(const float* d_q, int nq, const float* d_db, int nd, in
         S3D_CUDA(cudaStreamSynchronize(st));
     }
     const int path = g_match_path.load();
-    const bool use_tc = nd > 0 && n_act > 0 && (path == 2 || (path == 0 && (double)n_act * nd >= 4.0e6 && nd >= 512));
+    const bool use_tc = nd > 0 && n_act > 0 && (path >= 2 || (path == 0 && (double)n_act * nd >= 4.0e6 && nd >= 512));
     if (use_tc) {
         S3D_CUDA(cudaMallocAsync((void**)&d_fb, sizeof(int) * (size_t)n_act, st));
-        S3D_TRY(tc_search(d_q, d_list, n_act, d_db, nd, db_offset, d_top, d_fb, d_cnt + 1, st));
+        S3D_TRY(tc_search(d_q, d_list, n_act, d_db, nd, db_offset, d_top, d_fb, d_cnt + 1, st, path == 3 ? 1 : (path == 4 ? 2 : 0)));
         int n_fb = 0;
         S3D_CUDA(cudaMemcpyAsync(&n_fb, d_cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         S3D_CUDA(cudaStreamSynchronize(st));
@@ -306,7 +307,8 @@ using namespace s3d;
 extern "C" {
 
 int s3d_set_match_path(int path) {
-    if (path < 0 || path > 2) return fail(S3D_ERR_ARG, "match path %d (0 auto, 1 exact, 2 tensor-core)", path);
+    if (path < 0 || path > 4)
+        return fail(S3D_ERR_ARG, "match path %d (0 auto, 1 exact, 2 tensor-core, 3 tensor-core single-CTA, 4 tensor-core CTA-pair)", path);
     g_match_path = path;
     return S3D_OK;
 }

@@ -47,6 +47,6 @@ __device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
 
 // s3d_match_tc.cu
 int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, Top2* d_out,
-              int* d_fb_list, int* d_fb_count, cudaStream_t st);
+              int* d_fb_list, int* d_fb_count, cudaStream_t st, int variant);
 
 }  // namespace s3d

@@ -96,6 +96,59 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- cluster / 2-CTA (cta_group::2) variants ------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `local` (a shared::cta address of THIS CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t local, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier anywhere in the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA load into THIS CTA's shared memory that signals an mbarrier in this CTA or its peer
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t cluster_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(cluster_bar)
+        : "memory");
+}
+// the same with an L2 eviction-priority hint (createpolicy encodings as used by CUTLASS' TMA::CacheHintSm90)
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t cluster_bar,
+                                                      uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], "
+        "[%4], %5;" ::"r"(dst),
+        "l"(map), "r"(c0), "r"(c1), "r"(cluster_bar), "l"(hint)
+        : "memory");
+}
+// commit of the pair's MMAs: arrives on the mbarrier at the same shared offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 64 fp16 (128 B) per row, 8-row atoms
 // 1024 B apart (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64)).
@@ -112,6 +165,57 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 // a/b K-major (0), N>>3 [17,23), M>>4 [24,29).
 __device__ __forceinline__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Epilogue of one accumulator tile, shared by both candidate kernels: fold the BN columns of this
+// thread's row (TMEM lane) into the running top-8 (RAW accumulator value = 4096 x approximate dot,
+// database index), kept sorted in registers.  j0 = database index of column 0.
+//   * the TMEM loads are software-pipelined (chunk c+1 is in flight while chunk c is reduced);
+//   * the common case costs a 32-wide max (FMNMX3) and one compare per chunk;
+//   * a chunk that does hold a new candidate is handled WITHOUT per-element branches: locate the
+//     maximum (select chain), insert it, knock it out, re-reduce — one round per insertion, and
+//     insertions become rare as the 8th-best value rises (a warp leaves the fast path only while
+//     one of its 32 rows still improves).
+__device__ __forceinline__ void topk_insert(float x, int j, float (&v)[TOPK], int (&id)[TOPK]) {
+    v[TOPK - 1] = x; id[TOPK - 1] = j;
+#pragma unroll
+    for (int i = TOPK - 1; i > 0; --i) {
+        const bool sw = v[i] > v[i - 1];
+        const float hi = sw ? v[i] : v[i - 1], lo = sw ? v[i - 1] : v[i];
+        const int ihi = sw ? id[i] : id[i - 1], ilo = sw ? id[i - 1] : id[i];
+        v[i - 1] = hi; v[i] = lo; id[i - 1] = ihi; id[i] = ilo;
+    }
+}
+
+__device__ __forceinline__ void topk_reduce32(uint32_t (&r)[32], int j0, int nvalid, float (&v)[TOPK], int (&id)[TOPK]) {
+    float mx = __uint_as_float(r[0]);
+#pragma unroll
+    for (int e = 1; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+    while (mx > v[TOPK - 1]) {
+        int idx = 31;
+#pragma unroll
+        for (int e = 30; e >= 0; --e) idx = (__uint_as_float(r[e]) == mx) ? e : idx;
+        if (idx < nvalid) topk_insert(mx, j0 + idx, v, id);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) r[e] = (e == idx) ? 0xff800000u /* -inf */ : r[e];
+        mx = __uint_as_float(r[0]);
+#pragma unroll
+        for (int e = 1; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
+    }
+}
+
+__device__ __forceinline__ void topk_scan_tile(uint32_t taddr, int j0, int nd, float (&v)[TOPK], int (&id)[TOPK]) {
+    uint32_t ra[32], rb[32];
+    tc_ld32(taddr, ra);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c += 2) {
+        tc_wait_ld();
+        tc_ld32(taddr + (uint32_t)((c + 1) * 32), rb);
+        topk_reduce32(ra, j0 + c * 32, nd - (j0 + c * 32), v, id);
+        tc_wait_ld();
+        if (c + 2 < BN / 32) tc_ld32(taddr + (uint32_t)((c + 2) * 32), ra);
+        topk_reduce32(rb, j0 + (c + 1) * 32, nd - (j0 + (c + 1) * 32), v, id);
+    }
 }
 
 __global__ void cvt_f16_kernel(const float* __restrict__ src, const int* __restrict__ rows, int nrows, __half* __restrict__ dst) {
@@ -231,31 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_topk_kernel(const __grid_const
                 mbar_wait(tfull(acc), acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t r[32];
-                    tc_ld32(taddr + (uint32_t)(c * 32), r);
-                    tc_wait_ld();
-                    float mx = __uint_as_float(r[0]);
-#pragma unroll
-                    for (int e = 1; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(r[e]));
-                    if (mx * INV_SCALE2 > v[TOPK - 1]) {
-                        const int j0 = t * BN + c * 32;
-#pragma unroll
-                        for (int e = 0; e < 32; ++e) {
-                            const float x = __uint_as_float(r[e]) * INV_SCALE2;
-                            if (x > v[TOPK - 1] && j0 + e < nd) {
-                                v[TOPK - 1] = x; id[TOPK - 1] = j0 + e;
-#pragma unroll
-                                for (int i = TOPK - 1; i > 0; --i)
-                                    if (v[i] > v[i - 1]) {
-                                        const float tv = v[i]; v[i] = v[i - 1]; v[i - 1] = tv;
-                                        const int ti = id[i]; id[i] = id[i - 1]; id[i - 1] = ti;
-                                    }
-                            }
-                        }
-                    }
-                }
+                topk_scan_tile(taddr, t * BN, nd, v, id);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty(acc));  // 4 epilogue warps -> count 4
@@ -264,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_topk_kernel(const __grid_const
             if (row < nq) {
                 const size_t o = ((size_t)row * parts + p) * TOPK;
 #pragma unroll
-                for (int i = 0; i < TOPK; ++i) { cand_val[o + i] = v[i]; cand_idx[o + i] = id[i]; }
+                for (int i = 0; i < TOPK; ++i) { cand_val[o + i] = id[i] >= 0 ? v[i] * INV_SCALE2 : -1.0f; cand_idx[o + i] = id[i]; }
             }
         }
     }
@@ -276,48 +356,298 @@ __global__ void __launch_bounds__(kThreads, 1) tc_topk_kernel(const __grid_const
     }
 }
 
-// Exact re-rank of the candidates of one query per warp (lane = candidate slot), guard, outputs.
+// ---------------------------------------------------------------------------------------------
+// CTA-pair candidate kernel (cta_group::2): the query tile stays RESIDENT in shared memory.
+//
+// With one CTA per tile the kernel above streams 16 KB of queries + 32 KB of database rows per
+// 512 tensor clocks = 96 B/clk/SM, more than twice what L2 can deliver to every SM at once
+// (~6300 B/clk chip-wide = 42.6 B/clk/SM), so the tensor pipe idles ~60 % of the time.  Here two
+// CTAs of one TPC form a pair: each keeps its own 128 query rows x 768 (fp16, 192 KB, 12 blocks of
+// 128 B-swizzled 64-wide K) in shared memory for the whole sweep, and each stages only HALF of the
+// database rows of an MMA (64 of N = 128) — tcgen05.mma.cta_group::2 (M = 256) reads B from both
+// CTAs' shared memory.  Streaming traffic drops to 8 KB per 256 tensor clocks = 32 B/clk/SM.
+//   ring      4 stages x 8 KB (64 database rows x 64 K), TMA with .cta_group::2 so the peer's loads
+//             complete on the LEADER's full barrier; empty barriers are signalled in both CTAs by
+//             tcgen05.commit ... multicast::cluster
+//   TMEM      512 columns = two 128-lane x 256-column FP32 accumulators per CTA (double-buffered
+//             database tiles; a tile is two N = 128 halves)
+//   epilogue  4 warps per CTA, the same running top-8 as above on the CTA's own 128 rows; drained
+//             accumulators are released with a remote arrive on the leader's barrier.
+// Work unit = (pair of query tiles, database part), owned by ONE cluster for the whole launch.  The
+// database part is swept in L2-sized chunks, chunk-major: every cluster runs all its units over
+// chunk k before anyone moves to chunk k+1, so the ~150 SMs stream the SAME few tens of MB at the
+// same time and the ring's TMA loads hit L2 (a database of 1 M rows is 1.5 GB in fp16; swept
+// unit-major it would be re-read from HBM by every cluster, 9 TB/s of demand).  A unit's running
+// top-8 is parked in the candidate arrays between chunks (same thread writes and re-reads it).
+// Query tiles are loaded with an evict-first hint so they do not displace the chunk.
+// ---------------------------------------------------------------------------------------------
+namespace pr {
+constexpr int BMC = 128, BNH = 128, BROWS = 64, BSTAGES = 4;
+constexpr uint32_t A_BLK = BMC * BK * 2, A_ALL = KBLKS * A_BLK, B_STAGE = BROWS * BK * 2;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)A_ALL + (size_t)BSTAGES * B_STAGE + 256;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared memory of an sm_100 CTA");
+constexpr int kChunkTiles = 64;  // 64 tiles x 256 rows x 1536 B = 24 MB of fp16 database rows per chunk
+}  // namespace pr
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    tc_pair_topk_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, int nq, int nd,
+                        int n_qpairs, int parts, int tiles_per_part, int n_dbtiles, int chunk_tiles,
+                        float* __restrict__ cand_val, int* __restrict__ cand_idx) {
+    using namespace pr;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_b = base + A_ALL;
+    const uint32_t bars = smem_b + BSTAGES * B_STAGE;
+    auto full = [&](int s) { return bars + 8u * s; };
+    auto empty = [&](int s) { return bars + 8u * (BSTAGES + s); };
+    auto tfull = [&](int a) { return bars + 8u * (2 * BSTAGES + a); };
+    auto tempty = [&](int a) { return bars + 8u * (2 * BSTAGES + 2 + a); };
+    const uint32_t afull = bars + 8u * (2 * BSTAGES + 4), aempty = bars + 8u * (2 * BSTAGES + 5);
+    const uint32_t tmem_slot = bars + 8u * (2 * BSTAGES + 6);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < BSTAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 8); }  // 4 epilogue warps x 2 CTAs
+        mbar_init(afull, 1);
+        mbar_init(aempty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_db) : "memory");
+    }
+    if (warp == 1) {  // the same warp of both CTAs allocates the pair's 512 columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();  // barrier inits and the allocation are visible to the peer before any remote arrive
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int n_units = n_qpairs * parts;
+    const int n_chunks = (tiles_per_part + chunk_tiles - 1) / chunk_tiles;
+    // every role walks the same (chunk, unit) sequence; empty chunk ranges are skipped by all alike
+    auto for_items = [&](auto&& body) {
+        for (int ck = 0; ck < n_chunks; ++ck)
+            for (int unit = cluster_id; unit < n_units; unit += n_clusters) {
+                const int qp = unit / parts, p = unit - qp * parts;
+                const int pt1 = min(n_dbtiles, (p + 1) * tiles_per_part);
+                const int t0 = p * tiles_per_part + ck * chunk_tiles, t1 = min(pt1, t0 + chunk_tiles);
+                if (t0 < t1) body(ck, qp, p, t0, t1);
+            }
+    };
+    if (warp == 0) {
+        // ===== TMA producer (one thread in EACH CTA; transaction bytes land on the leader's barriers) =====
+        if (lane == 0) {
+            const uint32_t afull_l = mapa(afull, 0);
+            int stage = 0;
+            uint32_t phase = 0, aphase = 0;
+            for_items([&](int ck, int qp, int p, int t0, int t1) {
+                mbar_wait(aempty, aphase ^ 1);  // the previous item's MMAs no longer read the resident tile
+                if (leader) mbar_expect_tx(afull, 2u * A_ALL);
+                for (int kb = 0; kb < KBLKS; ++kb)
+                    tma_load_2d_pair_hint(base + kb * A_BLK, &map_q, kb * BK, qp * (2 * BMC) + (int)rank * BMC, afull_l, kEvictFirst);
+                aphase ^= 1;
+                for (int t = t0; t < t1; ++t)
+                    for (int h = 0; h < 2; ++h)
+                        for (int kb = 0; kb < KBLKS; ++kb) {
+                            mbar_wait(empty(stage), phase ^ 1);
+                            if (leader) mbar_expect_tx(full(stage), 2u * B_STAGE);
+                            tma_load_2d_pair(smem_b + stage * B_STAGE, &map_db, kb * BK, t * BN + h * BNH + (int)rank * BROWS,
+                                             mapa(full(stage), 0));
+                            if (++stage == BSTAGES) { stage = 0; phase ^= 1; }
+                        }
+            });
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores =====
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc(2 * BMC, BNH);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, aphase = 0;
+            for_items([&](int ck, int qp, int p, int t0, int t1) {
+                mbar_wait(afull, aphase);
+                aphase ^= 1;
+                tc_fence_after();
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(tempty(acc), acc_phase ^ 1);  // both CTAs' epilogues have drained this accumulator
+                    tc_fence_after();
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN + h * BNH);
+                        for (int kb = 0; kb < KBLKS; ++kb) {
+                            mbar_wait(full(stage), phase);
+                            tc_fence_after();
+                            const uint64_t da = make_desc(base + kb * A_BLK), db = make_desc(smem_b + stage * B_STAGE);
+#pragma unroll
+                            for (int k4 = 0; k4 < BK / 16; ++k4)
+                                tc_mma_pair(d_tmem, da + (uint64_t)(2 * k4), db + (uint64_t)(2 * k4), idesc, (kb | k4) ? 1u : 0u);
+                            tc_commit_pair(empty(stage));
+                            if (++stage == BSTAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    tc_commit_pair(tfull(acc));
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                tc_commit_pair(aempty);
+            });
+        }
+    } else {
+        // ===== epilogue (both CTAs): warps 2..5 own TMEM lanes 32*(warp%4) .. +31 of their CTA =====
+        const int quad = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const uint32_t tempty_l[2] = {mapa(tempty(0), 0), mapa(tempty(1), 0)};
+        for_items([&](int ck, int qp, int p, int t0, int t1) {
+            const int row = qp * (2 * BMC) + (int)rank * BMC + quad * 32 + lane;
+            const size_t o = ((size_t)row * parts + p) * TOPK;
+            float v[TOPK];
+            int id[TOPK];
+            if (ck > 0 && row < nq) {  // resume the running top-8 parked after the previous chunk
+#pragma unroll
+                for (int i = 0; i < TOPK; ++i) {
+                    id[i] = cand_idx[o + i];
+                    v[i] = id[i] >= 0 ? cand_val[o + i] * (SCALE * SCALE) : -1.0f;  // back to raw accumulator units (exact)
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < TOPK; ++i) { v[i] = -1.0f; id[i] = -1; }
+            }
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(tfull(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+                topk_scan_tile(taddr, t * BN, nd, v, id);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(tempty_l[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (row < nq) {
+#pragma unroll
+                for (int i = 0; i < TOPK; ++i) { cand_val[o + i] = id[i] >= 0 ? v[i] * INV_SCALE2 : -1.0f; cand_idx[o + i] = id[i]; }
+            }
+        });
+    }
+    tc_fence_before();
+    cluster_sync_all();  // neither CTA may leave (or free TMEM) while the other can still signal it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// Exact re-rank.  Four queries per warp, eight lanes per query:
+//   1. merge  the parts' top-8 lists of a query are merged to ONE top-8 by approximate value (8
+//             rounds of an 8-lane arg-max), so the exact work does not grow with the number of parts.
+//   2. exact  dots of the 32 (query, candidate) pairs of the warp in the reference's arithmetic
+//             (float product, sequential double sum over k = 0..767, KP_squareSum cMatcher.cc:17-23).
+//             Rows are read COALESCED — for each pair the warp loads 32 consecutive k of both rows
+//             and parks the 32 products in a shared-memory tile; lane l then adds the 32 products of
+//             pair l in order.  (One lane walking one database row touches a new 32-byte sector
+//             every 8 elements: 8x the traffic, which made this kernel L2-bound.)
+//   3. top-2  under (dot desc, index asc) over the query's eight lanes, and the GUARD: every row that
+//             is not among the merged eight has approximate dot <= a8 (the 8th merged value, which is
+//             >= each full part's own 8th), hence exact dot <= a8*(1+eps)+eps_abs; if the exact
+//             second-best exceeds that bound the eight provably contain the true top-2, otherwise the
+//             row goes to the exact CUDA-core kernel.
 // q rows are addressed through qlist (original row index); results are written to out[orig].
-__global__ void __launch_bounds__(256) rerank_kernel(const float* __restrict__ q, const int* __restrict__ qlist, int nql,
-                                                     const float* __restrict__ db, int nd, int db_offset, int ncand,
-                                                     const float* __restrict__ cand_val, const int* __restrict__ cand_idx,
-                                                     Top2* __restrict__ out, int* __restrict__ fb_list, int* fb_count) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (w >= nql) return;
-    const int orig = qlist ? qlist[w] : w;
-    const float* a = q + (size_t)orig * KD;
+constexpr int kRrWarps = 8;
+__global__ void __launch_bounds__(kRrWarps * 32) rerank_kernel(const float* __restrict__ q, const int* __restrict__ qlist, int nql,
+                                                               const float* __restrict__ db, int nd, int db_offset, int ncand,
+                                                               const float* __restrict__ cand_val,
+                                                               const int* __restrict__ cand_idx, Top2* __restrict__ out,
+                                                               int* __restrict__ fb_list, int* fb_count) {
+    __shared__ float tile[kRrWarps][32][33];
+    __shared__ int pair_j[kRrWarps][32];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
+    const int gw = blockIdx.x * kRrWarps + wid;
+    if (gw * 4 >= nql) return;  // warp-uniform
+    const int qi = gw * 4 + g;
+    const bool qvalid = qi < nql;
+    const int orig = qvalid ? (qlist ? qlist[qi] : qi) : 0;
+    const int parts = ncand / TOPK;  // <= 8
+    // ---- 1. merge ----
+    float ev[8];
+    int ej[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        const bool ok = qvalid && p < parts;
+        ej[p] = ok ? cand_idx[(size_t)qi * ncand + p * TOPK + c] : -1;
+        ev[p] = ok ? cand_val[(size_t)qi * ncand + p * TOPK + c] : -1.0f;
+    }
+    int myj = -1;
+    float a8 = -1.0f;
+#pragma unroll 1
+    for (int r = 0; r < TOPK; ++r) {
+        float lv = -2.0f;
+        int lp = -1;
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+            if (ej[p] >= 0 && ev[p] > lv) { lv = ev[p]; lp = p; }
+        float gv = lv;
+        int gl = c;
+#pragma unroll
+        for (int off = 4; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, gv, off);
+            const int ol = __shfl_xor_sync(0xffffffffu, gl, off);
+            if (ov > gv || (ov == gv && ol < gl)) { gv = ov; gl = ol; }
+        }
+        int lj = -1;
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+            if (p == lp) lj = ej[p];
+        const int selj = __shfl_sync(0xffffffffu, lj, (lane & ~7) | gl);
+        if (c == r) myj = selj;
+        if (c == gl && lp >= 0) {
+#pragma unroll
+            for (int p = 0; p < 8; ++p)
+                if (p == lp) ej[p] = -1;
+        }
+        if (r == TOPK - 1) a8 = selj >= 0 ? gv : -1.0f;
+    }
+    // ---- 2. exact dots, coalesced ----
+    pair_j[wid][lane] = myj;
+    int qrow[4];
+#pragma unroll
+    for (int gg = 0; gg < 4; ++gg) qrow[gg] = __shfl_sync(0xffffffffu, orig, gg * 8);
+    __syncwarp();
+    double sum = 0.0;
+#pragma unroll 1
+    for (int kb = 0; kb < KD / 32; ++kb) {
+        float av[4];
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) av[gg] = q[(size_t)qrow[gg] * KD + kb * 32 + lane];
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+            const int j = pair_j[wid][l];
+            if (j >= 0) tile[wid][l][lane] = __fmul_rn(av[l >> 3], db[(size_t)j * KD + kb * 32 + lane]);
+        }
+        __syncwarp();
+        if (myj >= 0) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) sum = __dadd_rn(sum, (double)tile[wid][lane][k]);
+        }
+        __syncwarp();
+    }
+    // ---- 3. top-2 of the query's eight lanes, guard ----
     Top2 best;
     top2_init(best);
-    float a_floor = -1.0f;  // largest "smallest kept approximate value" over the parts that were full
-    for (int c0 = 0; c0 < ncand; c0 += 32) {
-        const int c = c0 + lane;
-        int j = -1;
-        float av = -1.0f;
-        if (c < ncand) { j = cand_idx[(size_t)w * ncand + c]; av = cand_val[(size_t)w * ncand + c]; }
-        // a part whose 8th slot is filled may hide better rows below its threshold
-        if (c < ncand && (c % TOPK) == TOPK - 1 && j >= 0) a_floor = fmaxf(a_floor, av);
-        double s = 0.0;
-        if (j >= 0) {
-            const float* b = db + (size_t)j * KD;
-#pragma unroll 8
-            for (int k = 0; k < KD; ++k) s = __dadd_rn(s, (double)__fmul_rn(a[k], b[k]));
-            top2_push(best, s, j + db_offset);
-        }
-    }
-    // warp merge under (dot desc, index asc)
+    if (myj >= 0) top2_push(best, sum, myj + db_offset);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
+    for (int off = 4; off > 0; off >>= 1) {
         Top2 o;
         o.d1 = __shfl_xor_sync(0xffffffffu, best.d1, off); o.d2 = __shfl_xor_sync(0xffffffffu, best.d2, off);
         o.i1 = __shfl_xor_sync(0xffffffffu, best.i1, off); o.i2 = __shfl_xor_sync(0xffffffffu, best.i2, off);
         top2_merge(best, o);
-        a_floor = fmaxf(a_floor, __shfl_xor_sync(0xffffffffu, a_floor, off));
     }
-    if (lane == 0) {
+    if (c == 0 && qvalid) {
         out[orig] = best;
-        // GUARD (see file header): non-candidates satisfy exact <= a_floor*(1+eps) + eps_abs
-        const double bound = (double)a_floor * (1.0 + 1.2e-3) + 1e-6;
-        const bool safe = a_floor < 0.0f || (best.i2 >= 0 && best.d2 > bound);
+        const double bound = (double)a8 * (1.0 + 1.2e-3) + 1e-6;
+        const bool safe = a8 < 0.0f || (best.i2 >= 0 && best.d2 > bound);
         if (!safe) fb_list[atomicAdd(fb_count, 1)] = orig;
     }
 }
@@ -348,11 +678,29 @@ static int make_map(CUtensorMap* m, const __half* base, int rows, int box_rows) 
 
 }  // namespace tc
 
+// Number of database parts per query tile: the smallest split whose last wave is at least 90 % full
+// (items = units * parts over `workers` persistent CTAs / CTA pairs), else the best one seen.
+static int choose_parts(int units, int n_dbtiles, int workers) {
+    int best = 1;
+    double best_eff = 0.0;
+    const int pmax = std::max(1, std::min(8, n_dbtiles / 4));
+    for (int parts = 1; parts <= pmax; ++parts) {
+        const long long items = (long long)units * parts;
+        const long long waves = (items + workers - 1) / workers;
+        const double eff = (double)items / (double)(waves * workers);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = parts; }
+        if (eff >= 0.9) break;
+    }
+    return best;
+}
+
 // Tensor-core search of `nql` query rows (qlist maps to original rows, may be null) against db.
 // out[orig] receives the exact top-2; rows whose candidate set could not be proven complete are
 // appended to fb_list / *fb_count (device) for the exact kernel.
+// variant: 0 = choose by size, 1 = one CTA per tile (tc_topk_kernel), 2 = CTA pairs with the query
+// tile resident in shared memory (tc_pair_topk_kernel).
 int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, Top2* d_out,
-              int* d_fb_list, int* d_fb_count, cudaStream_t st) {
+              int* d_fb_list, int* d_fb_count, cudaStream_t st, int variant) {
     using namespace tc;
     if (nql <= 0 || nd <= 0) return S3D_OK;
     int dev = 0, sms = 148;
@@ -361,15 +709,20 @@ int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, 
     static bool attr_set[64] = {false};
     if (dev < 64 && !attr_set[dev]) {
         S3D_CUDA(cudaFuncSetAttribute(tc_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        S3D_CUDA(cudaFuncSetAttribute(tc_pair_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pr::SMEM_BYTES));
         attr_set[dev] = true;
     }
+    // Measured on B200 (profiles/): the one-CTA-per-tile kernel keeps the tensor pipe 90 % busy; the pair
+    // kernel moves a third of the L2->SM bytes (and holds higher clocks under the power cap) but its
+    // 4 x 8 KB ring leaves the pipe 79 % busy, so it is selected only on request.
+    const bool pair = variant == 2;
     __half *q16 = nullptr, *db16 = nullptr;
     float* cand_val = nullptr;
     int* cand_idx = nullptr;
-    const int n_qtiles = (nql + BM - 1) / BM, n_dbtiles = (nd + BN - 1) / BN;
-    // split the database only when there are too few query tiles to fill the GPU
-    int parts = std::max(1, std::min(n_dbtiles, (sms + n_qtiles - 1) / n_qtiles));
-    parts = std::min(parts, 4);
+    const int n_dbtiles = (nd + BN - 1) / BN;
+    const int n_units = pair ? (nql + 2 * pr::BMC - 1) / (2 * pr::BMC) : (nql + BM - 1) / BM;
+    const int workers = pair ? std::max(1, sms / 2) : sms;
+    int parts = choose_parts(n_units, n_dbtiles, workers);
     const int tiles_per_part = (n_dbtiles + parts - 1) / parts;
     parts = (n_dbtiles + tiles_per_part - 1) / tiles_per_part;
     const int ncand = parts * TOPK;
@@ -381,11 +734,20 @@ int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, 
     S3D_LAUNCH(cvt_f16_kernel, s3d_blocks((size_t)nd * 32, 256), 256, 0, st, d_db, (const int*)nullptr, nd, db16);
     CUtensorMap mq, mdb;
     S3D_TRY(make_map(&mq, q16, nql, BM));
-    S3D_TRY(make_map(&mdb, db16, nd, BN));
-    const int grid = std::min(sms, n_qtiles * parts);
-    S3D_LAUNCH(tc_topk_kernel, grid, kThreads, SMEM_BYTES, st, mq, mdb, nql, nd, n_qtiles, parts, tiles_per_part, n_dbtiles,
-               cand_val, cand_idx);
-    S3D_LAUNCH(rerank_kernel, s3d_blocks((size_t)nql * 32, 256), 256, 0, st, d_q, d_qlist, nql, d_db, nd, db_offset, ncand,
+    S3D_TRY(make_map(&mdb, db16, nd, pair ? pr::BROWS : BN));
+    if (pair) {
+        const int grid = 2 * std::min(workers, n_units * parts);
+        // chunk = the slice of the database all clusters sweep together; parts are swept concurrently, so
+        // together they should stay well inside L2 (126 MB, shared with the streaming query tiles)
+        const int chunk_tiles = std::max(8, pr::kChunkTiles / parts);
+        S3D_LAUNCH(tc_pair_topk_kernel, grid, kThreads, pr::SMEM_BYTES, st, mq, mdb, nql, nd, n_units, parts, tiles_per_part,
+                   n_dbtiles, chunk_tiles, cand_val, cand_idx);
+    } else {
+        const int grid = std::min(sms, n_units * parts);
+        S3D_LAUNCH(tc_topk_kernel, grid, kThreads, SMEM_BYTES, st, mq, mdb, nql, nd, n_units, parts, tiles_per_part, n_dbtiles,
+                   cand_val, cand_idx);
+    }
+    S3D_LAUNCH(rerank_kernel, s3d_blocks((size_t)nql, 4 * kRrWarps), kRrWarps * 32, 0, st, d_q, d_qlist, nql, d_db, nd, db_offset, ncand,
                cand_val, cand_idx, d_out, d_fb_list, d_fb_count);
     S3D_CUDA(cudaGetLastError());
     void* tmp[] = {q16, db16, cand_val, cand_idx};

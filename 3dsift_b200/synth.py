@@ -152,3 +152,39 @@ def d_synth_pair(k, seed=0, k_tar=None):
     truth = np.full(k, -1, dtype=np.int64)
     truth[src] = pos
     return ref, np.ascontiguousarray(tar), truth
+
+
+def d_synth_pair_device(k, seed=0, k_tar=None, device="cuda", chunk=65536):
+    """D-synth(K) generated on the GPU with torch (same recipe as d_synth_pair, different random
+    stream): for the matching sizes where building 2 x K x 768 floats with numpy would dominate a
+    benchmark's wall time.  Returns (ref, tar, truth) as device tensors."""
+    import torch
+    k_tar = k if k_tar is None else k_tar
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+
+    def finish(d):
+        d = d / (d.norm(dim=1, keepdim=True) + 1e-12)
+        d = torch.clamp(d, max=float(TRUNC))
+        return d / (d.norm(dim=1, keepdim=True) + 1e-12)
+
+    def synth(n):
+        out = torch.empty((n, 768), dtype=torch.float32, device=device)
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            v = torch.empty((e - s, 768), dtype=torch.float32, device=device).exponential_(1.0, generator=g)
+            v *= torch.rand((e - s, 768), device=device, generator=g) < 0.25
+            out[s:e] = finish(v)
+        return out
+
+    ref, tar = synth(k), synth(k_tar)
+    n_copy = min(int(0.7 * k_tar), k)
+    src = torch.randperm(k, device=device, generator=g)[:n_copy]
+    pos = torch.randperm(k_tar, device=device, generator=g)[:n_copy]
+    for s in range(0, n_copy, chunk):
+        e = min(n_copy, s + chunk)
+        noisy = ref[src[s:e]] * (1.0 + 0.1 * torch.randn((e - s, 768), device=device, generator=g))
+        tar[pos[s:e]] = finish(torch.clamp(noisy, min=0))
+    truth = torch.full((k,), -1, dtype=torch.int64, device=device)
+    truth[src] = pos
+    return ref, tar, truth

@@ -218,7 +218,9 @@ S3D_API int s3d_match_ex(int type, const float* ref_desc, int n_ref, int ref_on_
                          float* gDist2, int* sIdx2, float* sDist2, int* pair_ref, int* pair_tar, int* n_pairs,
                          double* times3);
 /* Search path of calMatches: 0 = auto (tensor-core candidate pass + exact re-rank for large
- * searches, exact CUDA-core kernel for small ones), 1 = exact kernel only, 2 = tensor cores always.
+ * searches, exact CUDA-core kernel for small ones), 1 = exact kernel only, 2 = tensor cores always
+ * (kernel variant chosen by size), 3 = tensor cores with one CTA per tile, 4 = tensor cores with CTA
+ * pairs (cta_group::2) and the query tile resident in shared memory.
  * Results are identical on every path (the tensor-core pass proves its candidate set complete or
  * falls back per row). */
 S3D_API int s3d_set_match_path(int path);

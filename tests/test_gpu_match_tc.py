@@ -7,9 +7,11 @@ pytestmark = pytest.mark.gpu
 NAMES = {1: "injectMatch", 2: "bijectMatch", 3: "enhancedMatch"}
 
 
-@pytest.fixture()
-def tc_path(s3d):
-    s3d.set_match_path(s3d.api.MATCH_TENSOR)
+@pytest.fixture(params=["single", "pair"])
+def tc_path(s3d, request):
+    """Both candidate kernels: one CTA per tile (tc_topk_kernel) and CTA pairs with the query tile
+    resident in shared memory (tc_pair_topk_kernel)."""
+    s3d.set_match_path(s3d.api.MATCH_TENSOR_SINGLE if request.param == "single" else s3d.api.MATCH_TENSOR_PAIR)
     s3d.match_stats(reset=True)
     yield
     s3d.set_match_path(s3d.api.MATCH_AUTO)
@@ -68,5 +70,6 @@ def test_tc_equals_exact_at_20k(s3d, synth, tc_path):
     assert np.array_equal(m_tc.pairs, m_ex.pairs)
     hit = truth[m_tc.pairs[:, 0]] == m_tc.pairs[:, 1]
     assert hit.mean() > 0.99 and len(m_tc.pairs) > 10000
+    assert fb <= 0.01 * rows                  # the candidate pass itself is right (fallback is the exception)
     print(f"20k x 20k: tc rows {rows}, exact-fallback rows {fb} ({100.0 * fb / max(rows, 1):.2f} %), time {m_tc.totalTime * 1e3:.1f} ms "
           f"vs exact {m_ex.totalTime * 1e3:.1f} ms")
