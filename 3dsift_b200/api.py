@@ -95,6 +95,8 @@ def lib():
     L.s3d_pairs_device.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.s3d_match_ex.argtypes = [C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_double] + [vp] * 12
     L.s3d_set_match_path.argtypes = [C.c_int]
+    L.s3d_set_describe_path.argtypes = [C.c_int]
+    L.s3d_get_counters.argtypes = [vp, C.POINTER(C.c_int)]
     L.s3d_match_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
     L.s3d_match_stats.restype = None
     L.s3d_level_info.argtypes = [vp, C.c_int, C.c_int, vp, vp]
@@ -152,6 +154,14 @@ def set_match_path(path):
     """0 auto / 1 exact CUDA-core kernel / 2 tensor-core candidate pass (variant by size) / 3 tensor cores,
     one CTA per tile / 4 tensor cores, CTA pairs with resident query tile (results are identical)."""
     check(lib().s3d_set_match_path(int(path)))
+
+
+DESC_FIXED, DESC_FP32, DESC_FORCE_REDO = 0, 1, 2
+
+
+def set_describe_path(path):
+    """0 fixed-point atomics + FP32 redo (default) / 1 FP32 ordered accumulation / 2 forced redo (tests)."""
+    check(lib().s3d_set_describe_path(int(path)))
 
 
 def match_stats(reset=False):
@@ -305,6 +315,12 @@ class CSIFT3D:
         check(lib().s3d_get_kernel_stats(self._h, cap, C.byref(n), _ptr(ms), _ptr(cnt), _ptr(by)))
         return {lib().s3d_kernel_class_name(i).decode(): dict(ms=float(ms[i]), launches=int(cnt[i]), alg_bytes=float(by[i]))
                 for i in range(n.value) if cnt[i]}
+
+    def counters(self):
+        """dict(orient_rechecked, orient_flipped, desc_redo): safeguard bookkeeping of the last run."""
+        out = (C.c_int * 4)()
+        check(lib().s3d_get_counters(self._h, out))
+        return dict(orient_rechecked=int(out[0]), orient_flipped=int(out[1]), desc_redo=int(out[2]))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

@@ -175,6 +175,16 @@ static Taps with_ext(const Taps& t0, int n) {
     return t;
 }
 
+// Descriptor accumulation: 0 = fixed-point shared-memory atomics with FP32 redo of overflow-flagged
+// keypoints (default), 1 = FP32 staged/ordered accumulation for every keypoint, 2 = as 0 but with a
+// deliberately tiny scale margin so that (nearly) every keypoint takes the redo path (tests).
+// Initial value from the environment: S3D_DESC_PATH=0|1|2.
+static int initial_describe_path() {
+    const char* e = getenv("S3D_DESC_PATH");
+    return (e && e[0] >= '0' && e[0] <= '2' && !e[1]) ? e[0] - '0' : 0;
+}
+static std::atomic<int> g_describe_path{initial_describe_path()};
+
 static bool supported_fast_hw(int hw) { return hw == 2 || hw == 3 || hw == 4 || hw == 5 || hw == 6 || hw == 8; }
 
 template <int HW>
@@ -211,9 +221,9 @@ static void launch_march(const float* src, float* dst, int nx, int n, ll st_m, i
 
 // ---- per-kernel-class device timing (params.profile) ---------------------------------------
 enum KCls { K_MAXABS, K_NORMALIZE, K_BLUR_X, K_BLUR_Y, K_BLUR_Z_DOG, K_BLUR_GENERIC, K_DOWNSAMPLE, K_DETECT, K_COMPACT,
-            K_ORIENT, K_ORIENT_EXACT, K_SURVIVORS, K_DESCRIBE, K_NCLS };
+            K_ORIENT, K_ORIENT_EXACT, K_SURVIVORS, K_DESCRIBE, K_DESCRIBE_REDO, K_NCLS };
 static const char* kClsName[K_NCLS] = {"maxabs", "normalize", "blur_x", "blur_y", "blur_z_dog", "blur_generic", "downsample",
-                                       "detect", "compact", "orient", "orient_exact", "survivors", "describe"};
+                                       "detect", "compact", "orient", "orient_exact", "survivors", "describe", "describe_redo"};
 struct Prof {
     bool on = false;
     cudaStream_t st = nullptr;
@@ -323,6 +333,8 @@ struct s3d_ctx {
     s3d_keypoint* d_kps = nullptr;
     float* d_desc = nullptr;
     int n_rechecked = 0, n_flipped = 0;
+    int* d_redo = nullptr;          // [0] = count, [1..] = keypoint indices (freed in s3d_wait)
+    int n_desc_redo = 0;            // keypoints the fixed-point descriptor kernel handed to the FP32 one
     bool ran = false, levels_alive = false, queued = false, h2d_pending = false;
     // z-slab sharding.  Unsharded: slab = false, za = p0 = 0, zb = p1 = nz_o.
     // A shard OWNS global planes [p0[o], p1[o]) of octave o and keeps local buffers for planes
@@ -502,7 +514,7 @@ void s3d_destroy(s3d_handle c) {
     if (c->stream) {
         cudaSetDevice(c->device);
         free_levels(c);
-        void* ptrs[] = {c->d_input, c->d_slots, c->d_thres, c->d_mesh, c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc};
+        void* ptrs[] = {c->d_input, c->d_slots, c->d_thres, c->d_mesh, c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc, c->d_redo};
         for (void* q : ptrs) if (q) cudaFreeAsync(q, c->stream);
         cudaStreamSynchronize(c->stream);
         c->prof.resolve();
@@ -790,22 +802,43 @@ static int stage_sparse(s3d_ctx* c) {
     const size_t nka = std::max(c->n_kps, 1);
     S3D_CUDA(cudaMallocAsync((void**)&c->d_kps, sizeof(s3d_keypoint) * nka, st));
     S3D_CUDA(cudaMallocAsync((void**)&c->d_desc, sizeof(float) * S3D_DESC_LEN * nka, st));
+    int* d_redo = nullptr;
     if (c->n_kps > 0) {
-        ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
         static bool attr_set[64] = {false};
         if (c->device < 64 && !attr_set[c->device]) {
-            S3D_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmem)));
+            S3D_CUDA(cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmem)));
+            S3D_CUDA(cudaFuncSetAttribute(describe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmemQ)));
             attr_set[c->device] = true;
         }
-        S3D_LAUNCH(describe_kernel, c->n_kps, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, c->n_kps, tab, c->d_mesh,
-                   c->d_kps, c->d_desc);
+        const int path = g_describe_path.load();
+        if (path == 1) {  // FP32 staged/ordered accumulation for every keypoint
+            ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
+            S3D_LAUNCH(describe_kernel<false>, c->n_kps, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, c->n_kps, tab,
+                       c->d_mesh, c->d_kps, c->d_desc, (const int*)nullptr, (const int*)nullptr, (int*)nullptr, (int*)nullptr, 0.0f);
+        } else {
+            // fixed-point atomics for all; the (normally empty) list of keypoints whose scale estimate was
+            // too low is redone in FP32 — its grid is sized for the worst case and reads the count on the device
+            S3D_CUDA(cudaMallocAsync((void**)&d_redo, sizeof(int) * ((size_t)c->n_kps + 1), st));
+            S3D_CUDA(cudaMemsetAsync(d_redo, 0, sizeof(int), st));
+            {
+                ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
+                S3D_LAUNCH(describe_kernel<true>, c->n_kps, kDescWarps * 32, sizeof(DescSmemQ), st, c->d_extre, d_surv, c->n_kps, tab,
+                           c->d_mesh, c->d_kps, c->d_desc, (const int*)nullptr, (const int*)nullptr, d_redo + 1, d_redo,
+                           path == 2 ? 0.02f : kQMargin);
+            }
+            ProfScope ps(&c->prof, K_DESCRIBE_REDO, 0.0);
+            S3D_LAUNCH(describe_kernel<false>, c->n_kps, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, c->n_kps, tab,
+                       c->d_mesh, c->d_kps, c->d_desc, (const int*)(d_redo + 1), (const int*)d_redo, (int*)nullptr, (int*)nullptr, 0.0f);
+            c->d_redo = d_redo;  // the count is read in s3d_wait
+            d_redo = nullptr;
+        }
     }
     S3D_CUDA(cudaGetLastError());
     S3D_CUDA(cudaEventRecord(c->ev[5], st));
 
     // ---- Release_SIFT (:1659-1678) unless the caller asked to keep the pyramids ---------------
     if (!c->prm.keep_levels) free_levels(c);
-    void* tmp[] = {d_blk_cnt, d_blk_off, d_total, d_stage, d_stage_count, d_cand, d_recheck, d_surv, d_wtab};
+    void* tmp[] = {d_blk_cnt, d_blk_off, d_total, d_stage, d_stage_count, d_cand, d_recheck, d_surv, d_wtab, d_redo};
     for (void* q : tmp) if (q) cudaFreeAsync(q, st);
     S3D_CUDA(cudaEventRecord(c->ev[6], st));
     c->queued = true;
@@ -835,6 +868,11 @@ int s3d_wait(s3d_handle c) {
     if (!c) return fail(S3D_ERR_ARG, "null handle");
     if (!c->queued) return fail(S3D_ERR_STATE, "s3d_wait before s3d_run_async");
     S3D_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d_redo) {
+        S3D_CUDA(cudaMemcpy(&c->n_desc_redo, c->d_redo, sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFreeAsync(c->d_redo, c->stream);
+        c->d_redo = nullptr;
+    }
     if (!c->ran) {
         float ms;
         for (int i = 0; i < 6; i++) {
@@ -1150,6 +1188,20 @@ int s3d_get_kernel_stats(s3d_handle c, int cap, int* n_classes, double* ms, long
 }
 
 const char* s3d_kernel_class_name(int cls) { return cls >= 0 && cls < K_NCLS ? kClsName[cls] : ""; }
+
+int s3d_set_describe_path(int path) {
+    if (path < 0 || path > 2) return fail(S3D_ERR_ARG, "describe path %d (0 fixed-point + FP32 redo, 1 FP32, 2 forced redo)", path);
+    g_describe_path = path;
+    return S3D_OK;
+}
+
+int s3d_get_counters(s3d_handle c, int* out4) {
+    clear_error();
+    if (!c || !out4) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "s3d_get_counters before s3d_run");
+    out4[0] = c->n_rechecked; out4[1] = c->n_flipped; out4[2] = c->n_desc_redo; out4[3] = 0;
+    return S3D_OK;
+}
 
 int s3d_get_timers(s3d_handle c, double* t) {
     if (!c || !t) return fail(S3D_ERR_ARG, "null argument");

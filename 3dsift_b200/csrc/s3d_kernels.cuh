@@ -12,6 +12,8 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "expf_ref.h"
 #include "sift3d_b200.h"
 
@@ -997,6 +999,29 @@ struct DescSmem {
     float red[kDescWarps + 1];
     float wt[kDescWtCap];                            // Gaussian window weight by m = i^2+j^2+k^2 (wtab_kernel)
 };
+// Fixed-point variant: ONE histogram of 32-bit counters per CTA, accumulated with native shared-memory
+// integer atomics (ATOMS.ADD; FP32 shared atomics are CAS loops on sm_100) — no staging, no replay.
+// kQCopies interleaved copies (lane & (kQCopies-1) picks one): neighbouring voxels of a row mostly hit
+// the SAME bins, and same-address atomics of one warp instruction are serialised; with the copies
+// kQCopyStride words apart (== 4 mod 32 banks) the lanes of a group also land in different banks.
+constexpr int kQCopies = 8;
+constexpr int kQCopyStride = 836;
+static_assert(kQCopyStride >= kHistStride && kQCopyStride % 32 == 4, "copy stride must cover a histogram and rotate banks");
+struct DescSmemQ {
+    uint32_t hist[kQCopies * kQCopyStride];
+    uint32_t queue[kDescWarps][64];
+    MeshConst M;
+    s3d_keypoint kp;
+    float red[kDescWarps + 1];
+    float wt[kDescWtCap];
+    int overflow;
+};
+// Fixed-point scale: every contribution is mag * (trilinear weight <= 1) * (barycentric <= 1), so it is
+// bounded by mag.  With qscale chosen so that mag * qscale <= kQCap for every voxel, a bin — which at
+// most (2*cell+2)^3 <= 28^3 voxels can touch — stays below 28^3 * kQCap < 2^32: no wrap-around.  A voxel
+// that exceeds the cap raises the CTA's overflow flag and the keypoint is redone by the FP32 kernel.
+constexpr float kQCap = 190000.0f;
+constexpr float kQMargin = 8.0f;   // qscale = kQCap / (kQMargin * sampled max of mag)
 
 // One CTA per surviving keypoint, 7 warps, 3 CTAs per SM.
 //  * Pairs of adjacent rows (y, y+1 at fixed z) of the window are dealt round-robin to the warps,
@@ -1010,15 +1035,29 @@ struct DescSmem {
 //  * Replay: the warp walks the staged voxels in order, lane l < 24 adding contribution l into
 //    the warp-private histogram — plain LDS/FADD/STS, no atomics (shared FP32 atomics are CAS
 //    loops on sm_100).  Warp histograms are summed in fixed order at the end.
+//
+// Q = true is the production variant: contributions are accumulated in FIXED POINT with native
+// integer shared-memory atomics into one per-CTA histogram (order-independent, hence still
+// run-to-run deterministic); the scale comes from a 900-sample estimate of the largest gradient
+// magnitude in the window, and a keypoint whose contributions would exceed the overflow-safe cap is
+// reported in redo_list for the FP32 variant (Q = false: the staged, ordered replay described
+// above), which takes its keypoints from klist when given.  Inclusion tests, face selection and
+// all per-voxel arithmetic are identical in both variants.
+template <bool Q>
 __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_keypoint* __restrict__ extre,
                                                                    const int* __restrict__ surv, int nkp, LevelTable tab,
                                                                    const MeshConst* __restrict__ meshp,
                                                                    s3d_keypoint* __restrict__ kps_out,
-                                                                   float* __restrict__ desc_out) {
+                                                                   float* __restrict__ desc_out,
+                                                                   const int* __restrict__ klist,
+                                                                   const int* __restrict__ nkp_dev,
+                                                                   int* __restrict__ redo_list, int* redo_count,
+                                                                   float qmargin) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DescSmem& S = *reinterpret_cast<DescSmem*>(smem_raw);
-    const int k = blockIdx.x;
-    if (k >= nkp) return;
+    typedef typename std::conditional<Q, DescSmemQ, DescSmem>::type Smem;
+    Smem& S = *reinterpret_cast<Smem*>(smem_raw);
+    if ((int)blockIdx.x >= (nkp_dev ? min(*nkp_dev, nkp) : nkp)) return;  // nkp_dev: a count produced on the device
+    const int k = klist ? klist[blockIdx.x] : (int)blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     {
         const int* src = reinterpret_cast<const int*>(extre + surv[k]);
@@ -1027,7 +1066,12 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
         const int* ms = reinterpret_cast<const int*>(meshp);
         int* md = reinterpret_cast<int*>(&S.M);
         for (int i = tid; i < (int)(sizeof(MeshConst) / 4); i += kDescThreads) md[i] = ms[i];
-        for (int i = tid; i < kDescWarps * kHistStride; i += kDescThreads) (&S.hist[0][0])[i] = 0.0f;
+        if constexpr (Q) {
+            for (int i = tid; i < kQCopies * kQCopyStride; i += kDescThreads) S.hist[i] = 0u;
+            if (tid == 0) S.overflow = 0;
+        } else {
+            for (int i = tid; i < kDescWarps * kHistStride; i += kDescThreads) (&S.hist[0][0])[i] = 0.0f;
+        }
     }
     __syncthreads();
     const MeshConst& M = S.M;
@@ -1062,10 +1106,38 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
     const int wyp = (wyn + 1) >> 1;  // row pairs per z slice
     const int npairs = (wyn > 0 && wzn > 0) ? wyp * wzn : 0;
     const ll ys = nx, zs = (ll)nx * ny;
-    float* myh = S.hist[wid];
-    uint2(*stg)[kStageCols] = S.stage[wid];
     uint32_t* que = S.queue[wid];
     const float iu = 1.0f / u, inv_u2 = iu * iu;
+    // ---- Q: fixed-point scale from a 10 x 10 x 9 lattice of window samples -----------------------
+    float qscale = 0.0f;
+    if constexpr (Q) {
+        float gm = 0.0f;
+        const int wxn_ = xe - xs + 1, wyn_ = y1 - y0 + 1, wzn_ = z1 - z0 + 1;
+        if (wxn_ > 0 && wyn_ > 0 && wzn_ > 0)
+            for (int sidx = tid; sidx < 900; sidx += kDescThreads) {
+                const int sx = sidx % 10, sy = (sidx / 10) % 10, sz = sidx / 100;
+                const int xx = xs + ((2 * sx + 1) * wxn_) / 20, yy = y0 + ((2 * sy + 1) * wyn_) / 20, zz = z0 + ((2 * sz + 1) * wzn_) / 18;
+                const float dx = ((float)xx - cx) * u, dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
+                const float sq = dx * dx + dy * dy + dz * dz;
+                if (sq > r2) continue;
+                const int mi = (int)(sq * inv_u2);
+                const float weight = wt_s ? S.wt[mi] : wt_g[mi];
+                const ll i = (ll)xx + (ll)yy * ys + (ll)zz * zs;
+                const float gx = 0.5f * (g[i + 1] - g[i - 1]), gy = 0.5f * (g[i + ys] - g[i - ys]), gz = 0.5f * (g[i + zs] - g[i - zs]);
+                gm = fmaxf(gm, (gx * gx + gy * gy + gz * gz) * (weight * weight));
+            }
+        gm = warp_max(gm);
+        if (lane == 0) S.red[wid] = gm;
+        __syncthreads();
+        gm = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kDescWarps; ++w) gm = fmaxf(gm, S.red[w]);
+        __syncthreads();
+        const float gest = sqrtf(gm) * iu;  // largest sampled |gradient| * weight
+        if (gest > 1e-30f) qscale = kQCap / (qmargin * gest);
+        else if (tid == 0) S.overflow = 1;  // nothing sampled: let the FP32 variant decide
+    }
+    bool q_over = false;
     // conservative clip of a row to the rotated grid: |R_k . disp| < slab for k = 0..2, with
     // R_k . disp = a_k * (x - cx) + (R_k1*dy + R_k2*dz); the reciprocals are per keypoint
     const float slab = desc_hw * 1.001f + 1e-3f;
@@ -1109,6 +1181,37 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
                 }
             }
         }
+        if constexpr (Q) {
+            if (contrib) {
+                // Trilinear_interpolation_over_desc_debug :1466-1522, contributions in fixed point
+                const float msq = mag * qscale;
+                q_over |= msq > kQCap;
+                const int ib0 = (int)vb0, ib1 = (int)vb1, ib2 = (int)vb2;  // truncation, Q12
+                const float dv0 = vb0 - floorf(vb0), dv1 = vb1 - floorf(vb1), dv2 = vb2 - floorf(vb2);
+                const float wx[2] = {1.0f - dv0, dv0}, wy[2] = {1.0f - dv1, dv1}, wz[2] = {1.0f - dv2, dv2};
+                const bool okx[2] = {ib0 >= 0 && ib0 <= 3, ib0 >= -1 && ib0 <= 2};
+                const bool oky[2] = {ib1 >= 0 && ib1 <= 3, ib1 >= -1 && ib1 <= 2};
+                const bool okz[2] = {ib2 >= 0 && ib2 <= 3, ib2 >= -1 && ib2 <= 2};
+                const int ax[2] = {ib0 * 12, ib0 * 12 + 12}, ay[2] = {ib1 * 48, ib1 * 48 + 48}, az[2] = {ib2 * kHistZ, ib2 * kHistZ + kHistZ};
+                const int i0 = M.idx[face][0], i1 = M.idx[face][1], i2 = M.idx[face][2];
+                const float qb0 = msq * b[0], qb1 = msq * b[1], qb2 = msq * b[2];
+                uint32_t* hq = S.hist + (lane & (kQCopies - 1)) * kQCopyStride;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int ddx = (c >> 2) & 1, ddy = (c >> 1) & 1, ddz = c & 1;
+                    if (okx[ddx] && oky[ddy] && okz[ddz]) {
+                        const float wt = wx[ddx] * wy[ddy] * wz[ddz];
+                        const int base = ax[ddx] + ay[ddy] + az[ddz];
+                        // round-to-nearest via the 2^23 trick (values are < 2^23): full-rate FFMA + IADD instead of F2I
+                        atomicAdd(&hq[base + i0], __float_as_uint(__fmaf_rn(wt, qb0, 8388608.0f)) - 0x4B000000u);
+                        atomicAdd(&hq[base + i1], __float_as_uint(__fmaf_rn(wt, qb1, 8388608.0f)) - 0x4B000000u);
+                        atomicAdd(&hq[base + i2], __float_as_uint(__fmaf_rn(wt, qb2, 8388608.0f)) - 0x4B000000u);
+                    }
+                }
+            }
+        } else {
+        float* myh = S.hist[wid];
+        uint2(*stg)[kStageCols] = S.stage[wid];
         const unsigned mc = __ballot_sync(0xffffffffu, contrib);
         if (contrib) {
             // Trilinear_interpolation_over_desc_debug :1466-1522
@@ -1156,6 +1259,7 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
                 if (lane < 24) myh[e0.x] += __uint_as_float(e0.y);
                 __syncwarp();
             }
+        }
         }
     };
 
@@ -1215,7 +1319,16 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
         }
     }
     if (qn > 0) heavy(que[(qhead + lane) & 63], lane < qn);
+    if constexpr (Q) {
+        if (q_over) S.overflow = 1;
+    }
     __syncthreads();
+    if constexpr (Q) {
+        if (S.overflow) {  // CTA-uniform: hand this keypoint to the FP32 variant
+            if (tid == 0) redo_list[atomicAdd(redo_count, 1)] = k;
+            return;
+        }
+    }
     // fixed-order sum over the per-warp histograms, then normalise / clamp / normalise (:1350-1358)
     constexpr int kPer = (S3D_DESC_LEN + kDescThreads - 1) / kDescThreads;
     float v[kPer];
@@ -1226,8 +1339,15 @@ __global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_key
         float a = 0.0f;
         if (i < S3D_DESC_LEN) {
             const int hz = i / 192, hr = i - hz * 192;  // -> padded histogram address
+            if constexpr (Q) {
+                uint32_t acc = 0;  // the copies together stay below 2^32 (see kQCap)
 #pragma unroll
-            for (int w = 0; w < kDescWarps; ++w) a += S.hist[w][hz * kHistZ + hr];
+                for (int cp = 0; cp < kQCopies; ++cp) acc += S.hist[cp * kQCopyStride + hz * kHistZ + hr];
+                a = (float)acc;  // in units of 1/qscale; the normalisation below removes the scale
+            } else {
+#pragma unroll
+                for (int w = 0; w < kDescWarps; ++w) a += S.hist[w][hz * kHistZ + hr];
+            }
         }
         v[e] = a;
         ss += a * a;

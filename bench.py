@@ -206,6 +206,8 @@ def main():
     def upload():
         return s3d.CSIFT3DFactory.CreateCSIFT3D(h_vol, x_dim=n, y_dim=n, z_dim=n, device=local, async_upload=True)
 
+    e2e_split = {}
+
     def e2e_steps(k_steps):
         k = 0
         cur = upload()
@@ -214,6 +216,8 @@ def main():
             cur.KpSiftAlgorithm()
             k = cur.num_keypoints()
             s3d.check(L.s3d_get_keypoints(cur._h, h_kp.data_ptr(), h_desc.data_ptr()))
+            t = cur.m_timer
+            e2e_split.update(h2d_ms=t["d_h2d"] * 1e3, d2h_ms=t["d_d2h"] * 1e3, device_ms=t["d_TotalTime"] * 1e3)
             cur.close()
             cur = nxt
         return k
@@ -341,7 +345,11 @@ def main():
                        "parallelism": f"dp{world} (one volume per GPU, no collective on the data path)"},
             "clocks": sampler.summary(windows),
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(vol.nbytes),
-                    "d2h_bytes_per_step": int(k * (176 + 768 * 4))},
+                    "d2h_bytes_per_step": int(k * (176 + 768 * 4)),
+                    "last_step_split_ms": e2e_split,
+                    "note": "pinned host volume -> CreateCSIFT3D (H2D on the handle's stream, enqueued one step ahead) -> "
+                            "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors); when the copy of the next "
+                            "volume is slower than one extraction the leg is bound by the host link (h2d_ms)"},
             "gpu_launches": int(launches),
             "roofline": roof,
             "dense_pipeline": {"alg_bytes": b_dense, "ms": dense_ms,

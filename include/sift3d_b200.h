@@ -137,6 +137,16 @@ S3D_API int s3d_get_thresholds(s3d_handle h, float* out, int n);
  * t[0]=alloc t[1]=gss t[2]=dog t[3]=detect t[4]=orient t[5]=describe t[6]=release t[7]=total
  * (seconds, from CUDA events on the handle's stream; t[8]=h2d, t[9]=d2h). */
 S3D_API int s3d_get_timers(s3d_handle h, double* t10);
+/* Bookkeeping of the exactness safeguards of one run: out4[0] = detections re-evaluated in the
+ * reference's serial FP32 order (orientation), [1] = accept/reject codes that changed, [2] = keypoints
+ * whose descriptor the fixed-point kernel handed to the FP32 kernel, [3] = reserved. */
+S3D_API int s3d_get_counters(s3d_handle h, int* out4);
+/* Descriptor accumulation (Extract_Descriptor_Imp Src/cSIFT3D.cc:1152-1381 adds 24 weighted
+ * contributions per voxel into the 768-bin histogram): 0 = fixed point with native shared-memory
+ * integer atomics + FP32 redo of keypoints that exceed the overflow-safe cap (default), 1 = FP32
+ * staged/ordered accumulation for every keypoint, 2 = as 0 with a deliberately small scale margin
+ * (exercises the redo path).  All paths meet the descriptor tolerance (cosine >= 0.9999). */
+S3D_API int s3d_set_describe_path(int path);
 
 /* Per-kernel-class device times of the last s3d_run (needs params.profile = 1): for class c <
  * *n_classes, ms[c] = summed CUDA-event time, launches[c], alg_bytes[c] = algorithmic bytes moved
