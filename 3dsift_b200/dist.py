@@ -41,6 +41,8 @@ class CudaOps:
         self.dev = torch.device("cuda", torch.cuda.current_device())
 
     def to_device(self, a):
+        if self.torch.is_tensor(a):  # already a (device-resident) descriptor block: no host round trip
+            return a.to(self.dev, dtype=self.torch.float32).contiguous()
         return self.torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(self.dev)
 
     def _stream(self):
@@ -345,7 +347,7 @@ def merge_shard_results(parts, num_kp_levels=3):
     return out
 
 
-def extract_slabs(volume, shards=None, group=None, params=None, keep=False):
+def extract_slabs(volume, shards=None, group=None, params=None, keep=False, timing=None):
     """Full extraction of ONE volume split into z-slabs.
 
     * distributed (torch.distributed initialised, ``shards`` None): one shard per rank of ``group``;
@@ -354,9 +356,25 @@ def extract_slabs(volume, shards=None, group=None, params=None, keep=False):
     * single process (``shards`` = G): G logical shards on the current device, same code path with
       device copies instead of send/recv — the CI check that sharded == unsharded.
 
+    ``timing`` (a dict) receives device-synchronised wall seconds per phase: upload, pyramid (blur
+    chain + seed halo exchanges + scalar all-reduces), halo (descriptor-window planes), sparse, gather.
+
     Returns dict(kp, desc, extrema, codes, xyz5[, shards]) in the reference's order."""
+    import time
+
     import torch
     import torch.distributed as dist
+
+    def tick(name, _t=[None]):
+        if timing is None:
+            return
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if name is not None and _t[0] is not None:
+            timing[name] = timing.get(name, 0.0) + now - _t[0]
+        _t[0] = now
+
+    tick(None)
     distributed = shards is None and dist.is_initialized() and dist.get_world_size(group) > 1
     if distributed:
         world, me = dist.get_world_size(group), dist.get_rank(group)
@@ -391,6 +409,7 @@ def extract_slabs(volume, shards=None, group=None, params=None, keep=False):
         za, zb, _, _ = ext_of(g, 0)
         sh[g] = SlabShard(g, np.ascontiguousarray(volume[za:zb], dtype=np.float32), (nx, ny, nz), (bounds[g], bounds[g + 1]),
                           params, device=torch.cuda.current_device(), stream=stream)
+    tick("upload")
     # global max|v| (data_scale, Src/cUtil.cc:538-550)
     m = max([sh[g].local_max() for g in held] or [0.0])
     if distributed:
@@ -424,15 +443,18 @@ def extract_slabs(volume, shards=None, group=None, params=None, keep=False):
         mx = t.cpu().numpy()
     for g in held:
         sh[g].set_maxima(mx)
+    tick("pyramid")
     # descriptor windows reach into the neighbours' planes: fill the halos of levels 1..L of every octave
     for o in range(noct):
         exts = [ext_of(g, o) for g in range(G)]
         for i in range(1, nlev + 1):
             lv = {g: sh[g].level(0, o * Gl + i)[0] for g in held}
             exchange_halos(lv, exts, owner, me, group)
+    tick("halo")
     for g in held:
         sh[g].finish()
     mine = [(g, sh[g].results()) for g in held]
+    tick("sparse")
     if distributed:
         gathered = [None] * world
         dist.all_gather_object(gathered, mine, group=group)
@@ -440,6 +462,7 @@ def extract_slabs(volume, shards=None, group=None, params=None, keep=False):
     else:
         allp = mine
     out = merge_shard_results([r for _, r in allp], nlev)
+    tick("gather")
     if keep:
         out["shards"] = sh
         out["bounds"] = bounds
