@@ -220,9 +220,9 @@ static void launch_march(const float* src, float* dst, int nx, int n, ll st_m, i
 }
 
 // ---- per-kernel-class device timing (params.profile) ---------------------------------------
-enum KCls { K_MAXABS, K_NORMALIZE, K_BLUR_X, K_BLUR_Y, K_BLUR_Z_DOG, K_BLUR_GENERIC, K_DOWNSAMPLE, K_DETECT, K_COMPACT,
+enum KCls { K_MAXABS, K_NORMALIZE, K_BLUR_X, K_BLUR_Y, K_BLUR_XY, K_BLUR_Z_DOG, K_BLUR_GENERIC, K_DOWNSAMPLE, K_DETECT, K_COMPACT,
             K_ORIENT, K_ORIENT_EXACT, K_SURVIVORS, K_DESCRIBE, K_DESCRIBE_REDO, K_NCLS };
-static const char* kClsName[K_NCLS] = {"maxabs", "normalize", "blur_x", "blur_y", "blur_z_dog", "blur_generic", "downsample",
+static const char* kClsName[K_NCLS] = {"maxabs", "normalize", "blur_x", "blur_y", "blur_xy", "blur_z_dog", "blur_generic", "downsample",
                                        "detect", "compact", "orient", "orient_exact", "survivors", "describe", "describe_redo"};
 struct Prof {
     bool on = false;
@@ -299,6 +299,37 @@ static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int 
         S3D_HW_SWITCH(t.hw, CALLZ)
 #undef CALLZ
     }
+}
+
+// Fused X + Y pass (blur_xy_kernel) when the shape allows it; returns false when the caller must run
+// the two separate passes.  S3D_BLUR_XY=0 in the environment disables the fused kernel.
+static int xy_seg_override() {
+    const char* e = getenv("S3D_BLUR_XY_SEG");
+    return e ? atoi(e) : 0;
+}
+static bool blur_xy_pass(const float* src, float* dst, int nx, int ny, int nz, const Taps& t0, cudaStream_t st, Prof* prof) {
+    static const bool enabled = !(getenv("S3D_BLUR_XY") && getenv("S3D_BLUR_XY")[0] == '0');
+    static const int seg_env = xy_seg_override();
+    const int hw = t0.hw, T = nx >> 2;
+    // measured on B200 (profiles/r01_ncu_blur_xy.txt): the fused kernel beats X + Y for hw <= 6 (octave 0:
+    // 191/241/339/385/542 us against 412/434/460/515/645); at hw = 8 its two CTA barriers per row cost
+    // more than the saved round trip (881 against 767 us), so the widest level keeps the separate passes
+    if (!enabled || hw > 6 || nx % 4 != 0 || T < 1 || T > 128 || 128 % T != 0 || T <= hw + 1 || !supported_fast_hw(hw) ||
+        nx < 2 * hw + 2 || ny < 2 * hw + 2 || (ll)nx * ny * nz < 4096)
+        return false;
+    const Taps tx = with_ext(t0, nx), ty = with_ext(t0, ny);
+    const int lpc = 128 / T, zgroups = (nz + lpc - 1) / lpc;
+    // y segment: long enough to amortise the 2*hw-row prologue, short enough for >= ~2 waves of CTAs
+    int seg = seg_env > 0 ? seg_env : 128;
+    if (seg_env <= 0)
+        while (seg > 32 && (ll)zgroups * ((ny + seg - 1) / seg) < 148 * 4 * 2) seg >>= 1;
+    const int nseg = (ny + seg - 1) / seg;
+    const size_t smem = (size_t)lpc * kXYBufs * (nx + 2 * ((hw + 3) / 4 * 4)) * sizeof(float);
+    ProfScope ps(prof, K_BLUR_XY, 8.0 * (double)nx * ny * nz);
+#define CALLXY(H) S3D_LAUNCH(blur_xy_kernel<H>, (unsigned)(zgroups * nseg), 128, smem, st, src, dst, nx, ny, nz, seg, tx, ty)
+    S3D_HW_SWITCH(hw, CALLXY)
+#undef CALLXY
+    return true;
 }
 
 }  // namespace s3d
@@ -655,8 +686,10 @@ static int stage_octave(s3d_ctx* c, int o) {
         float* dst = c->gss[o * G + i];
         const float* src = (o == 0 && i == 0) ? c->d_input : c->gss[o * G + i - 1];
         const Taps& t = c->taps[i];
-        blur_pass(src, c->d_tmp[0], nx, ny, nz, 0, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
-        blur_pass(c->d_tmp[0], c->d_tmp[1], nx, ny, nz, 1, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
+        if (!blur_xy_pass(src, c->d_tmp[1], nx, ny, nz, t, st, &c->prof)) {
+            blur_pass(src, c->d_tmp[0], nx, ny, nz, 0, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
+            blur_pass(c->d_tmp[0], c->d_tmp[1], nx, ny, nz, 1, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
+        }
         if (i >= 1) {
             unsigned* slot = c->d_slots + 1 + o * D + i - 1;
             blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, src, c->dog[o * D + i - 1], c->slab ? scratch_slot : slot, st,

@@ -302,6 +302,144 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict
     }
 }
 
+// Fused X + Y pass.  The reference blurs along X over the whole volume, then along Y over the result
+// (GaussianSmooth_3D Src/cSIFT3D.cc:609-617, through two Im_permute transposes); every Y output only
+// needs the 2*HW+1 X-blurred rows around it, so one kernel can produce them on the fly and the
+// X-blurred volume is never written to HBM (8 B/voxel instead of 16 for the two passes).
+//   * A LINE is one x-row position marching along y over a segment of one z plane: nx/4 threads, each
+//     owning a float4 column (4 consecutive x).  A CTA of 128 threads runs 128/(nx/4) lines of
+//     consecutive z planes and the same y segment, so control flow is CTA-uniform.
+//   * X(r): the line's threads park raw row r in shared memory (double-buffered), the edge threads add
+//     the reference's extended-line samples (mirror on the left :747-750, 0.1/0.9-style blend on the
+//     right :751-764, same FP32 operations as ext_sample1), and every thread takes its 4 outputs as the
+//     ordered correlation over its window — the arithmetic of blur_x_kernel, bit for bit.
+//   * The X-blurred float4 goes into a register ring of the last 2*HW+1 rows (static slot indices
+//     through a (2*HW+1)-way unrolled loop, as in blur_march_kernel); the Y output is the ordered
+//     correlation over the ring.  Rows beyond the ends of the y line are the extended-line samples of
+//     the X-BLURRED rows (ext_il/ext_frac of the y axis), as in the reference's second sweep.
+// Requires nx % 4 == 0, (nx/4) a divisor of 128 and > HW + 1, nx and ny >= 2*HW+2.
+constexpr int kXYBufs = 4;  // shared-memory row ring of the fused X+Y pass (cp.async runs kXYBufs-1 rows ahead)
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int HW>
+__global__ void __launch_bounds__(128, 4) blur_xy_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny,
+                                                         int nz, int seg, Taps tx, Taps ty) {
+    constexpr int PAD = (HW + 3) / 4 * 4;
+    constexpr int NV = (2 * PAD + 4) / 4;
+    constexpr int WR = 2 * HW + 1;
+    constexpr int NB = kXYBufs;
+    extern __shared__ __align__(16) float xy_sm[];
+    const int T = nx >> 2, lpc = 128 / T;
+    const int line = threadIdx.x / T, x4 = threadIdx.x - line * T;
+    const int zgroups = (nz + lpc - 1) / lpc;
+    const int s = blockIdx.x / zgroups, zg = blockIdx.x - s * zgroups;
+    const int zraw = zg * lpc + line;
+    const bool zok = zraw < nz;
+    const int z = zok ? zraw : nz - 1;  // surplus lines of the last group shadow the last plane (no stores)
+    const int p0 = s * seg, p1 = min(ny, p0 + seg);
+    const int rowlen = nx + 2 * PAD;
+    float* const bufs = xy_sm + (size_t)line * NB * rowlen;
+    const float* const plane = src + (size_t)z * nx * ny;
+    float* const oplane = dst + (size_t)z * nx * ny;
+
+    // The segment consumes the extended-line samples q = p0-HW .. p1-1+HW of the X-blurred y line.
+    // Samples q < ny-1 need one X-blurred row (|q|); the others are blends of two (ext_il, ext_il+1).
+    // rowof(i) = raw row of the i-th X() call, so the cp.async producer can run ahead of the consumer.
+    const int nsamp = (p1 - 1 + HW) - (p0 - HW) + 1;
+    const int nreg = max(0, min(nsamp, (ny - 1) - (p0 - HW)));
+    const int ncalls = nreg + 2 * (nsamp - nreg);
+    auto rowof = [&](int i) -> int {
+        if (i < nreg) {
+            const int q = p0 - HW + i;
+            return q < 0 ? -q : q;
+        }
+        const int j = i - nreg;
+        return ty.ext_il[j >> 1] + (j & 1);
+    };
+    auto issue = [&](int i) {
+        if (i < ncalls) cp_async16(bufs + (i % NB) * rowlen + PAD + 4 * x4, plane + (size_t)rowof(i) * nx + 4 * x4);
+        cp_async_commit();  // an empty group keeps the group count uniform
+    };
+    int ci = 0;
+#pragma unroll
+    for (int i = 0; i < NB - 1; ++i) issue(i);
+
+    // X-blurred float4 (this thread's 4 columns) of the next row in sequence; cooperative (CTA-uniform)
+    auto X = [&]() -> float4 {
+        float* b = bufs + (ci % NB) * rowlen;
+        cp_async_wait<NB - 2>();  // this thread's piece of row ci has landed
+        __syncthreads();          // ... everyone's has; and everyone is done reading row ci-1's buffer
+        issue(ci + NB - 1);       // refill that buffer
+        ++ci;
+        // edge samples: every write below lands outside [PAD+1, PAD+nx-2], the only cells other threads
+        // read here; cell PAD+nx-1 (raw, then the e = 0 blend) is read and written by the same thread
+        if (x4 >= 1 && x4 <= HW) b[PAD - x4] = b[PAD + x4];  // left: q = -e mirrors to line[e]
+        const int e = T - 1 - x4;                             // right: q = n-1+e is the blend at (il, frac)
+        if (e <= HW) {
+            const int il = tx.ext_il[e];
+            const float frac = tx.ext_frac[e];
+            const float lo = b[PAD + il], hi = b[PAD + il + 1];
+            b[PAD + nx - 1 + e] = (1.0f - frac) * lo + frac * hi;
+        }
+        __syncthreads();
+        float v[2 * PAD + 4];
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            const float4 f = *reinterpret_cast<const float4*>(b + 4 * x4 + 4 * q);
+            v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+        }
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k <= 2 * HW; ++k) acc += tx.w[k] * v[PAD + j + HW - k];
+            o[j] = acc;
+        }
+        return make_float4(o[0], o[1], o[2], o[3]);
+    };
+    // extended-line sample q of the X-blurred y line (consumes one or two rows of the sequence)
+    auto sample = [&](int q) -> float4 {
+        if (q < ny - 1) return X();
+        const int e = q - (ny - 1);
+        const float frac = ty.ext_frac[e];
+        const float4 lo = X(), hi = X();
+        float4 r;
+        r.x = (1.0f - frac) * lo.x + frac * hi.x; r.y = (1.0f - frac) * lo.y + frac * hi.y;
+        r.z = (1.0f - frac) * lo.z + frac * hi.z; r.w = (1.0f - frac) * lo.w + frac * hi.w;
+        return r;
+    };
+
+    float4 win[WR];
+#pragma unroll
+    for (int r = 0; r < 2 * HW; ++r) win[r] = sample(p0 - HW + r);
+    win[2 * HW] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ib = 0; p0 + ib < p1; ib += WR) {
+#pragma unroll
+        for (int j = 0; j < WR; ++j) {
+            const int p = p0 + ib + j;
+            if (p < p1) {  // CTA-uniform
+                win[(j + 2 * HW) % WR] = sample(p + HW);
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k <= 2 * HW; ++k) {
+                    const float4 vv = win[(j + 2 * HW - k) % WR];  // extended-line sample p+HW-k
+                    const float w = ty.w[k];
+                    acc.x += w * vv.x; acc.y += w * vv.y; acc.z += w * vv.z; acc.w += w * vv.w;
+                }
+                if (zok) *reinterpret_cast<float4*>(oplane + (size_t)p * nx + 4 * x4) = acc;
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // K3  DownSample_3D, Src/cSIFT3D.cc:506-533: dst(n,m,k) = src(2n,2m,2k).
 __global__ void __launch_bounds__(256) downsample_kernel(const float* __restrict__ src, int sx, int sy, float* __restrict__ dst,
                                                          int dx, int dy, int dz) {
@@ -725,7 +863,7 @@ __device__ __forceinline__ void kp_init(s3d_keypoint& kp, int o, int lvl, int x,
 //     The FP32 summation order differs from the reference's serial z,y,x order; detections whose
 //     tests land within `recheck_margin` of a threshold are appended to recheck_list for the exact
 //     serial re-evaluation kernel below.
-__global__ void __launch_bounds__(256) orient_kernel(const Cand* __restrict__ cand, int ncand, LevelTable tab,
+__global__ void __launch_bounds__(256, 4) orient_kernel(const Cand* __restrict__ cand, int ncand, LevelTable tab,
                                                      s3d_keypoint* __restrict__ out, int* __restrict__ codes,
                                                      int* __restrict__ xyz5, float max_eig, float corner,
                                                      float recheck_margin, int* __restrict__ recheck_list,
@@ -1044,7 +1182,7 @@ constexpr float kQMargin = 8.0f;   // qscale = kQCap / (kQMargin * sampled max o
 // above), which takes its keypoints from klist when given.  Inclusion tests, face selection and
 // all per-voxel arithmetic are identical in both variants.
 template <bool Q>
-__global__ void __launch_bounds__(kDescThreads, 3) describe_kernel(const s3d_keypoint* __restrict__ extre,
+__global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const s3d_keypoint* __restrict__ extre,
                                                                    const int* __restrict__ surv, int nkp, LevelTable tab,
                                                                    const MeshConst* __restrict__ meshp,
                                                                    s3d_keypoint* __restrict__ kps_out,

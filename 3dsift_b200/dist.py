@@ -347,6 +347,47 @@ def merge_shard_results(parts, num_kp_levels=3):
     return out
 
 
+_RESULT_FIELDS = (("kp", np.uint8, 176), ("desc", np.float32, api.DESC_LENGTH), ("extrema", np.uint8, 176), ("codes", np.int32, 1),
+                  ("xyz5", np.int32, 5))
+
+
+def _all_gather_results(mine, me, world, group):
+    """Every rank's shard results on every rank, as NCCL all-gathers of padded device tensors (pickling
+    30 MB of descriptors through all_gather_object cost more than the whole extraction).
+    ``mine`` = [(gid, result dict)] with at most one shard per rank; returns the list sorted by gid."""
+    import torch
+    import torch.distributed as dist
+    assert len(mine) <= 1, "distributed slabs hold one shard per rank"
+    gid, res = mine[0] if mine else (-1, None)
+    k = len(res["kp"]) if res else 0
+    e = len(res["extrema"]) if res else 0
+    cnt = torch.tensor([gid, k, e], dtype=torch.int64, device="cuda")
+    cnts = torch.empty((world, 3), dtype=torch.int64, device="cuda")
+    dist.all_gather_into_tensor(cnts.view(-1), cnt, group=group)
+    cnts = cnts.cpu().numpy()
+    kmax, emax = int(cnts[:, 1].max()), int(cnts[:, 2].max())
+    got = {}
+    for name, dt, width in _RESULT_FIELDS:
+        rows = kmax if name in ("kp", "desc") else emax
+        n = k if name in ("kp", "desc") else e
+        buf = torch.zeros((max(rows, 1), width), dtype=torch.from_numpy(np.zeros(1, dt)).dtype, device="cuda")
+        if n:
+            host = np.ascontiguousarray(res[name]).view(dt).reshape(n, width)
+            buf[:n].copy_(torch.from_numpy(host), non_blocking=False)
+        out = torch.empty((world,) + tuple(buf.shape), dtype=buf.dtype, device="cuda")
+        dist.all_gather_into_tensor(out.view(-1), buf.view(-1), group=group)
+        got[name] = out.cpu().numpy()
+    parts = []
+    for r in range(world):
+        g, kr, er = (int(v) for v in cnts[r])
+        if g < 0:
+            continue
+        parts.append((g, dict(kp=got["kp"][r, :kr].copy().view(api.KP_DTYPE).reshape(-1), desc=got["desc"][r, :kr],
+                              extrema=got["extrema"][r, :er].copy().view(api.KP_DTYPE).reshape(-1),
+                              codes=got["codes"][r, :er, 0], xyz5=got["xyz5"][r, :er])))
+    return sorted(parts, key=lambda t: t[0])
+
+
 def extract_slabs(volume, shards=None, group=None, params=None, keep=False, timing=None):
     """Full extraction of ONE volume split into z-slabs.
 
@@ -456,9 +497,7 @@ def extract_slabs(volume, shards=None, group=None, params=None, keep=False, timi
     mine = [(g, sh[g].results()) for g in held]
     tick("sparse")
     if distributed:
-        gathered = [None] * world
-        dist.all_gather_object(gathered, mine, group=group)
-        allp = sorted((x for part in gathered for x in part), key=lambda t: t[0])
+        allp = _all_gather_results(mine, me, world, group)
     else:
         allp = mine
     out = merge_shard_results([r for _, r in allp], nlev)
