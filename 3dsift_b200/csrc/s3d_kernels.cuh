@@ -1082,6 +1082,26 @@ __device__ __forceinline__ bool face_bary(const MeshConst& M, int f, float gx, f
     return true;
 }
 
+// The same with fused multiply-adds and a correctly rounded FP32 reciprocal (the reference's
+// (float)(1.0/(double)det) differs from it at most in the last bit, in ~1 of 2^29 cases): used only for
+// the pre-selected face of find_face, whose result is accepted when all coordinates are comfortably
+// inside the face — 1e-4 away from any decision the last bits could change.
+__device__ __forceinline__ bool face_bary_fast(const MeshConst& M, int f, float gx, float gy, float gz, float bary_eps,
+                                               float& b0, float& b1, float& b2, float& k) {
+    const float e2x = M.e2[f][0], e2y = M.e2[f][1], e2z = M.e2[f][2];
+    const float px = __fmaf_rn(gy, e2z, -__fmul_rn(gz, e2y));
+    const float py = __fmaf_rn(gz, e2x, -__fmul_rn(gx, e2z));
+    const float pz = __fmaf_rn(gx, e2y, -__fmul_rn(gy, e2x));
+    const float det = __fmaf_rn(M.e1[f][0], px, __fmaf_rn(M.e1[f][1], py, __fmul_rn(M.e1[f][2], pz)));
+    if (fabsf(det) < bary_eps) return false;
+    const float det_inv = __frcp_rn(det);
+    b1 = det_inv * __fmaf_rn(px, M.t[f][0], __fmaf_rn(py, M.t[f][1], __fmul_rn(pz, M.t[f][2])));
+    b2 = det_inv * __fmaf_rn(gx, M.q[f][0], __fmaf_rn(gy, M.q[f][1], __fmul_rn(gz, M.q[f][2])));
+    b0 = 1 - b1 - b2;
+    k = det_inv * M.qe2[f];
+    return true;
+}
+
 // Check_intersect_faces, Src/cSIFT3D.cc:1542-1573: the FIRST face (index order) whose barycentric
 // coordinates are all >= -bary_eps with k >= 0 wins (App. B Q14).
 // Fast path: the faces of a regular icosahedron are the spherical Voronoi cells of their
@@ -1106,7 +1126,7 @@ __device__ __forceinline__ int find_face(const MeshConst& M, float gx, float gy,
     const int fs = (key & 1u) ? M.neg[fi] : M.pos[fi];
     float k;
     const float margin = 1e-4f;
-    if (face_bary(M, fs, gx, gy, gz, bary_eps, b0, b1, b2, k) && b0 > margin && b1 > margin && b2 > margin && k > 0.0f)
+    if (face_bary_fast(M, fs, gx, gy, gz, bary_eps, b0, b1, b2, k) && b0 > margin && b1 > margin && b2 > margin && k > 0.0f)
         return fs;
     for (int f = 0; f < 20; ++f) {
         float c0, c1, c2, kk;
@@ -1310,7 +1330,7 @@ __global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const
             const float rx = R0 * gx + R1 * gy + R2 * gz;
             const float ry = R3 * gx + R4 * gy + R5 * gz;
             const float rz = R6 * gx + R7 * gy + R8 * gz;
-            const float n2 = rx * rx + ry * ry + rz * rz;
+            const float n2 = rx * rx + ry * ry + rz * rz;  // exact form: input of the reference's |grad|^2 floor
             if (!(n2 < bary_eps)) {  // Check_intersect_faces :1544
                 face = find_face(M, rx, ry, rz, bary_eps, b[0], b[1], b[2]);
                 if (face >= 0) {

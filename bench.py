@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=512, help="cube edge of the synthetic volume")
-    ap.add_argument("--match-n", type=int, default=20000, help="keypoints per side for the matching leg (0 = skip)")
+    ap.add_argument("--match-n", type=int, default=1000000,
+                    help="keypoints per side for the matching leg (BASELINE.json metric: 1 M; 0 = skip)")
     ap.add_argument("--cpu-sample", type=int, default=128, help="cube edge of the CPU-baseline sample volume")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed steps")
@@ -209,9 +210,12 @@ def main():
         return s3d.CSIFT3DFactory.CreateCSIFT3D(h_vol, x_dim=n, y_dim=n, z_dim=n, device=local, async_upload=True)
 
     e2e_split = {}
+    e2e_step_ms = []
 
     def e2e_steps(k_steps):
         k = 0
+        del e2e_step_ms[:]
+        t_prev = time.perf_counter()
         cur = upload()
         for i in range(k_steps):
             nxt = upload() if i + 1 < k_steps else None
@@ -222,6 +226,9 @@ def main():
             e2e_split.update(h2d_ms=t["d_h2d"] * 1e3, d2h_ms=t["d_d2h"] * 1e3, device_ms=t["d_TotalTime"] * 1e3)
             cur.close()
             cur = nxt
+            now = time.perf_counter()
+            e2e_step_ms.append(round((now - t_prev) * 1e3, 2))
+            t_prev = now
         return k
 
     for _ in range(a.warmup):
@@ -273,18 +280,23 @@ def main():
     # ---- matching leg (secondary metric): enhancedMatch on HBM-resident descriptor sets ----------------
     match = None
     if a.match_n > 0:
-        ref, tar, _ = synth.d_synth_pair(a.match_n, seed=100 + rank)
-        d_ref, d_tar = torch.from_numpy(ref).cuda(), torch.from_numpy(tar).cuda()
-        nr, nt = len(ref), len(tar)
+        if a.match_n >= 200000:   # generated on the device: numpy would need minutes for 2 x 1 M x 768
+            d_ref, d_tar, d_truth = synth.d_synth_pair_device(a.match_n, seed=100 + rank)
+        else:
+            ref, tar, truth = synth.d_synth_pair(a.match_n, seed=100 + rank)
+            d_ref, d_tar, d_truth = torch.from_numpy(ref).cuda(), torch.from_numpy(tar).cuda(), torch.from_numpy(truth).cuda()
+        nr, nt = len(d_ref), len(d_tar)
         I = lambda m: torch.empty(max(m, 1), dtype=torch.int32, device="cuda")
         F = lambda m: torch.empty(max(m, 1), dtype=torch.float32, device="cuda")
         bufs = [I(nr), F(nr), I(nr), F(nr), I(nt), F(nt), I(nt), F(nt), I(nr), I(nr), I(1)]
 
         def match_step():
             s3d.check(L.s3d_match_device(3, d_ref.data_ptr(), nr, d_tar.data_ptr(), nt, 0.85, *[b.data_ptr() for b in bufs], stream))
-        for _ in range(min(a.warmup, 2)):
+        big = a.match_n >= 200000
+        for _ in range(1 if big else min(a.warmup, 2)):
             match_step()
-        msteps = max(1, min(a.steps, 3))
+        msteps = 2 if big else max(1, min(a.steps, 3))
+        s3d.match_stats(reset=True)
         barrier()
         w0 = time.time()
         ev0.record()
@@ -294,13 +306,26 @@ def main():
         barrier()
         windows.append((w0, time.time()))
         ms_match = ev0.elapsed_time(ev1) / msteps
+        tc_rows, fb_rows = s3d.match_stats()
         rev_rows = int((bufs[4] != -1).sum().item())
-        match = {"metric": "match pairs/s (enhancedMatch, thr 0.85)", "n_ref": nr, "n_tar": nt, "ms": ms_match,
-                 "pairs_per_s": nr * nt / (ms_match * 1e-3), "matches": int(bufs[10].item()), "reverse_rows_searched": rev_rows,
-                 "algorithmic_tflops": 2 * 768 * (nr * nt + rev_rows * nr) / (ms_match * 1e-3) / 1e12,
-                 "path": "tcgen05 FP16 candidate pass (top-8 per row) + exact FP32-product/FP64-sum re-rank with guard; "
-                         "rows on the tensor-core path / exact-fallback rows since start: %d / %d" % s3d.match_stats()}
-
+        npairs = int(bufs[10].item())
+        pr_, pt_ = bufs[8][:npairs].long(), bufs[9][:npairs].long()
+        true_frac = float((d_truth[pr_] == pt_).float().mean().item()) if npairs else 0.0
+        mt = torch.tensor([ms_match], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        ms_match = float(mt[0])
+        flops = 2.0 * 768 * (nr * nt + rev_rows * nr)
+        match = {"metric": "match pairs/s (enhancedMatch, thr 0.85)", "n_ref": nr, "n_tar": nt, "ms": ms_match, "steps": msteps,
+                 "pairs_per_s": world * nr * nt / (ms_match * 1e-3), "matches": npairs, "true_pair_fraction": true_frac,
+                 "reverse_rows_searched": rev_rows, "algorithmic_tflops_per_gpu": flops / (ms_match * 1e-3) / 1e12,
+                 "scaling": "weak (every GPU matches its own pair of sets; the database-sharded single-problem path is "
+                            "3dsift_b200/dist.py match_sharded, timed by scripts/multi_gpu_check.py)",
+                 "data": "D-synth(K) generated on the device (torch)" if big else "D-synth(K) (numpy)",
+                 "path": "tcgen05 FP16 candidate pass (running top-8 per query row in the epilogue) + exact FP32-product/FP64-sum "
+                         "re-rank with guard",
+                 "rows_tensor_core": tc_rows // msteps, "rows_exact_fallback": fb_rows // msteps}
+        del d_ref, d_tar, bufs
     time.sleep(0.3)
     sampler.stop()
 
@@ -319,6 +344,11 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        tc_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+        try:   # dram bytes per launch from the committed ncu capture of the same command (profiles/)
+            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            traffic_tab = {}
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "B200_PROFILING.md fallback 6650 GB/s"
         kernels = {}
         for name, s in kstats.items():
@@ -333,7 +363,10 @@ def main():
             top = max(dense, key=lambda k: kernels[k]["ms_per_step"])
             kk = kernels[top]
             roof = {"kernel": top, "bound": "hbm", "achieved": kk["alg_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": kk["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                    "frac": kk["frac_hbm"],
+                    "traffic": (traffic_tab[top]["dram_bytes_per_step"] / max(kk["launches"], 1)) if top in traffic_tab else None,
+                    "alg_bytes_per_launch": kk["alg_bytes"] / max(kk["launches"], 1), "launches": kk["launches"],
+                    "traffic_source": traffic_tab.get(top, {}).get("source"), "peak_source": peak_src,
                     "note": "achieved = algorithmic bytes of all launches of this kernel class in a step / their summed "
                             "CUDA-event time; see profiles/ for ncu dram bytes"}
         b_dense = 105.0 * nvox
@@ -347,10 +380,10 @@ def main():
                        "volumes_per_step": world, "keypoints_per_volume": nkp, "detections_per_volume": n_extre,
                        "l2": f"inputs ({vol.nbytes >> 20} MiB/volume) are larger than L2; no flush needed",
                        "parallelism": f"dp{world} (one volume per GPU, no collective on the data path)"},
-            "clocks": sampler.summary(windows),
+            "clocks": sampler.summary(windows[:2]),   # the two extraction legs (value, e2e)
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(vol.nbytes),
                     "d2h_bytes_per_step": int(k * (176 + 768 * 4)),
-                    "last_step_split_ms": e2e_split,
+                    "last_step_split_ms": e2e_split, "host_wall_ms_per_step": list(e2e_step_ms),
                     "note": "pinned host volume -> CreateCSIFT3D (H2D on the handle's stream, enqueued one step ahead) -> "
                             "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors); when the copy of the next "
                             "volume is slower than one extraction the leg is bound by the host link (h2d_ms)"},
@@ -363,6 +396,14 @@ def main():
             "kernels": kernels,
             "match": match,
         }
+        if match:
+            match["clocks"] = sampler.summary(windows[2:])   # a 1 M x 1 M search runs into the 1 kW power cap
+            match["roofline"] = {"bound": "tensor", "achieved": match["algorithmic_tflops_per_gpu"], "peak": tc_peak, "unit": "TFLOP/s",
+                                 "frac": match["algorithmic_tflops_per_gpu"] / tc_peak,
+                                 "peak_source": ("MEASURED_PEAKS.json bf16 cuBLAS (sustained)" if peaks else
+                                                 "B200_PROFILING.md fallback 1.4 PFLOP/s sustained (1.59 burst)"),
+                                 "note": "achieved = 2*768*(rows searched forward + reverse) / whole enhancedMatch time (candidate "
+                                         "kernel + re-rank + filters); ncu tensor-pipe utilisation of the candidate kernel is in profiles/"}
         if world == 1 and not a.no_cpu_baseline:
             val, sec, kind, threads, nk = time_reference(a.cpu_sample, 2, 0)
             model, _ = cpu_info()
