@@ -95,6 +95,10 @@ def lib():
     L.s3d_pairs_device.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.s3d_match_ex.argtypes = [C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_double] + [vp] * 12
     L.s3d_set_match_path.argtypes = [C.c_int]
+    L.s3d_read_nii.restype = C.POINTER(C.c_float)
+    L.s3d_read_nii.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.s3d_free_host.restype = None
+    L.s3d_free_host.argtypes = [C.POINTER(C.c_float)]
     L.s3d_set_describe_path.argtypes = [C.c_int]
     L.s3d_get_counters.argtypes = [vp, C.POINTER(C.c_int)]
     L.s3d_match_stats.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong), C.c_int]
@@ -154,6 +158,20 @@ def set_match_path(path):
     """0 auto / 1 exact CUDA-core kernel / 2 tensor-core candidate pass (variant by size) / 3 tensor cores,
     one CTA per tile / 4 tensor cores, CTA pairs with resident query tile (results are identical)."""
     check(lib().s3d_set_match_path(int(path)))
+
+
+def readNiiFile(path):
+    """readNiiFile (Include/Util/readNii.h:6): NIfTI-1/-2 (.nii / .nii.gz) -> float32 volume [nz, ny, nx].
+    Needs no GPU.  Raises S3DError when the file cannot be read."""
+    nx, ny, nz = C.c_int(), C.c_int(), C.c_int()
+    p = lib().s3d_read_nii(os.fsencode(path), C.byref(nx), C.byref(ny), C.byref(nz))
+    if not p:
+        raise S3DError(f"readNiiFile({path}) failed")
+    try:
+        n = nx.value * ny.value * nz.value
+        return np.ctypeslib.as_array(p, shape=(n,)).reshape(nz.value, ny.value, nx.value).copy()
+    finally:
+        lib().s3d_free_host(p)
 
 
 DESC_FIXED, DESC_FP32, DESC_FORCE_REDO = 0, 1, 2

@@ -72,7 +72,7 @@ def build(force=False, verbose=False):
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
     if force or _stale(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda", "-lz"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

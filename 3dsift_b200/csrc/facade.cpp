@@ -10,6 +10,12 @@
 #include <sstream>
 #include <string>
 
+#include <zlib.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "3dsift/Util/readNii.h"
 #include "3dsift/cMatcher.h"
 #include "3dsift/cSIFT3D.h"
 #include "sift3d_b200.h"
@@ -367,3 +373,118 @@ void read_sift_kp(const char* file_name, std::vector<Cvec>& kp) {
 }
 
 }  // namespace CPUSIFT
+
+// ---- NIfTI ingest (reference: Src/Util/readNii.cpp:5-39 over layNii; own parser here) ---------------
+namespace {
+
+template <class T>
+T nii_get(const unsigned char* p, bool swap) {
+    unsigned char b[sizeof(T)];
+    for (size_t i = 0; i < sizeof(T); ++i) b[i] = swap ? p[sizeof(T) - 1 - i] : p[i];
+    T v;
+    memcpy(&v, b, sizeof(T));
+    return v;
+}
+
+template <class T>
+void nii_convert(const unsigned char* src, size_t n, bool swap, float* dst) {
+    for (size_t i = 0; i < n; ++i) dst[i] = static_cast<float>(nii_get<T>(src + i * sizeof(T), swap));
+}
+
+bool nii_fail(const char* fname, const char* why) {
+    std::cerr << "[sift3d_b200] readNiiFile(" << fname << "): " << why << std::endl;
+    return false;
+}
+
+}  // namespace
+
+float* readNiiFile(const char* fname, int& nx, int& ny, int& nz) {
+    nx = ny = nz = 0;
+    // gzopen reads plain files transparently, so .nii and .nii.gz share one path
+    gzFile f = gzopen(fname, "rb");
+    if (!f) { nii_fail(fname, "cannot open"); return nullptr; }
+    gzbuffer(f, 1 << 20);
+    unsigned char hdr[540];
+    if (gzread(f, hdr, 348) != 348) { gzclose(f); nii_fail(fname, "short header"); return nullptr; }
+    int32_t sz = nii_get<int32_t>(hdr, false);
+    bool swap = false;
+    if (sz != 348 && sz != 540) {
+        sz = nii_get<int32_t>(hdr, true);
+        swap = true;
+    }
+    int64_t dim[8] = {0};
+    int datatype = 0;
+    int64_t vox_offset = 0;
+    if (sz == 348) {  // NIfTI-1: dim[8] int16 @40, datatype int16 @70, vox_offset float @108, magic @344
+        if (!(hdr[344] == 'n' && hdr[345] == '+' && hdr[346] == '1')) { gzclose(f); nii_fail(fname, "not a single-file NIfTI-1 (magic n+1)"); return nullptr; }
+        for (int i = 0; i < 8; ++i) dim[i] = nii_get<int16_t>(hdr + 40 + 2 * i, swap);
+        datatype = nii_get<int16_t>(hdr + 70, swap);
+        vox_offset = (int64_t)nii_get<float>(hdr + 108, swap);
+    } else if (sz == 540) {  // NIfTI-2: magic @4, datatype int16 @12, dim[8] int64 @16, vox_offset int64 @168
+        if (gzread(f, hdr + 348, 540 - 348) != 540 - 348) { gzclose(f); nii_fail(fname, "short NIfTI-2 header"); return nullptr; }
+        if (!(hdr[4] == 'n' && hdr[5] == '+' && hdr[6] == '2')) { gzclose(f); nii_fail(fname, "not a single-file NIfTI-2 (magic n+2)"); return nullptr; }
+        datatype = nii_get<int16_t>(hdr + 12, swap);
+        for (int i = 0; i < 8; ++i) dim[i] = nii_get<int64_t>(hdr + 16 + 8 * i, swap);
+        vox_offset = nii_get<int64_t>(hdr + 168, swap);
+    } else {
+        gzclose(f);
+        nii_fail(fname, "sizeof_hdr is neither 348 nor 540");
+        return nullptr;
+    }
+    if (dim[0] < 1 || dim[0] > 7 || dim[1] < 1) { gzclose(f); nii_fail(fname, "bad dim[]"); return nullptr; }
+    const int64_t dx = dim[1], dy = dim[0] >= 2 ? dim[2] : 1, dz = dim[0] >= 3 ? dim[3] : 1;
+    if (dx < 1 || dy < 1 || dz < 1 || dx > 0x7fffffff || dy > 0x7fffffff || dz > 0x7fffffff) { gzclose(f); nii_fail(fname, "bad volume dimensions"); return nullptr; }
+    size_t bpv = 0;
+    switch (datatype) {  // the types copy_nifti_as_float32 handles (laynii_lib.cpp:249-310) + float32 itself
+        case 2: case 256: bpv = 1; break;             // uint8, int8
+        case 4: case 512: bpv = 2; break;             // int16, uint16
+        case 8: case 768: case 16: bpv = 4; break;    // int32, uint32, float32
+        case 1024: case 1280: case 64: bpv = 8; break;  // int64, uint64, float64
+        default: gzclose(f); nii_fail(fname, "unsupported datatype"); return nullptr;
+    }
+    const int64_t have = sz;
+    if (vox_offset < have) vox_offset = have == 348 ? 352 : 544;
+    {   // skip the header extension up to vox_offset
+        std::vector<unsigned char> skip((size_t)(vox_offset - have));
+        if (!skip.empty() && gzread(f, skip.data(), (unsigned)skip.size()) != (int)skip.size()) { gzclose(f); nii_fail(fname, "short file (extension)"); return nullptr; }
+    }
+    const size_t n = (size_t)dx * dy * dz;
+    std::vector<unsigned char> raw(n * bpv);
+    size_t got = 0;
+    while (got < raw.size()) {
+        const unsigned want = (unsigned)std::min<size_t>(raw.size() - got, 1u << 30);
+        const int r = gzread(f, raw.data() + got, want);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    gzclose(f);
+    if (got != raw.size()) { nii_fail(fname, "short file (voxel data)"); return nullptr; }
+    float* out = new float[n];
+    switch (datatype) {
+        case 2: nii_convert<uint8_t>(raw.data(), n, swap, out); break;
+        case 256: nii_convert<int8_t>(raw.data(), n, swap, out); break;
+        case 4: nii_convert<int16_t>(raw.data(), n, swap, out); break;
+        case 512: nii_convert<uint16_t>(raw.data(), n, swap, out); break;
+        case 8: nii_convert<int32_t>(raw.data(), n, swap, out); break;
+        case 768: nii_convert<uint32_t>(raw.data(), n, swap, out); break;
+        case 16: nii_convert<float>(raw.data(), n, swap, out); break;
+        case 1024: nii_convert<int64_t>(raw.data(), n, swap, out); break;
+        case 1280: nii_convert<uint64_t>(raw.data(), n, swap, out); break;
+        case 64: nii_convert<double>(raw.data(), n, swap, out); break;
+    }
+    nx = (int)dx; ny = (int)dy; nz = (int)dz;
+    return out;
+}
+
+// C entry points for harnesses that cannot call the C++ signature (ctypes)
+extern "C" {
+S3D_API float* s3d_read_nii(const char* path, int* nx, int* ny, int* nz) {
+    int a = 0, b = 0, c = 0;
+    float* p = readNiiFile(path, a, b, c);
+    if (nx) *nx = a;
+    if (ny) *ny = b;
+    if (nz) *nz = c;
+    return p;
+}
+S3D_API void s3d_free_host(float* p) { delete[] p; }
+}

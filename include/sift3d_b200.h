@@ -264,6 +264,14 @@ S3D_API int s3d_biject_filter_device(int* d_gIdx, int n_ref, const int* d_mask, 
 S3D_API int s3d_pairs_device(const int* d_gIdx, int n_ref, int* d_pair_ref, int* d_pair_tar, int* d_n_pairs,
                              void* stream);
 
+/* ---- volume ingest --------------------------------------------------------- */
+/* readNiiFile (Include/Util/readNii.h:6, Src/Util/readNii.cpp:5-39): single-file NIfTI-1/-2, plain
+ * or gzip, any scalar datatype cast to float32 as stored (no scl_slope/scl_inter, like the
+ * reference).  Returns a host buffer of nx*ny*nz floats (x fastest) to release with s3d_free_host,
+ * or NULL. */
+S3D_API float* s3d_read_nii(const char* path, int* nx, int* ny, int* nz);
+S3D_API void s3d_free_host(float* p);
+
 #ifdef __cplusplus
 }
 #endif
