@@ -161,15 +161,20 @@ static void host_mesh(MeshConst* M) {
 // Extended-line table of a pass along an axis of length n (Src/cSIFT3D.cc:751-760): for tap
 // coordinate c = q = n-1+e the reference samples at c' = 2(n-1) - c - 0.1f, lo = (int)c',
 // frac = c' - lo.  Same FP32 operations as the reference (volatile: no wider evaluation).
-static Taps with_ext(const Taps& t0, int n) {
+// A z-slab shard passes the GLOBAL line length and the global coordinate of its first local plane:
+// frac is "whatever FP32 gives" for c' (App. A.2), so it depends on the magnitude of n — a shard that
+// holds the top of the volume must blend with the global c' (and address il relative to its buffer).
+static Taps with_ext(const Taps& t0, int n, int n_glob = -1, int off = 0) {
     Taps t = t0;
+    const bool top_is_global = n_glob > 0 && off + n == n_glob;
+    const int ng = top_is_global ? n_glob : n;
     for (int e = 0; e <= kMaxHW; e++) {
-        volatile float c = (float)(2 * (n - 1));
-        c = c - (float)(n - 1 + e);
+        volatile float c = (float)(2 * (ng - 1));
+        c = c - (float)(ng - 1 + e);
         c = c - 0.1f;
         int il = (int)c;
         volatile float fr = c - (float)il;
-        t.ext_il[e] = il;
+        t.ext_il[e] = top_is_global ? il - off : il;
         t.ext_frac[e] = fr;
     }
     return t;
@@ -271,11 +276,14 @@ struct ProfScope {
 
 // One separable pass.  variant 0 = generic kernel; 1 = fast kernels when eligible.
 // prev/dog/slot non-null fuses the DoG subtraction + max|DoG| (only meaningful on the last pass).
+// nz_glob / z_off (z passes of a z-slab shard): global plane count and global index of local plane 0.
 static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int axis, const Taps& t0, int variant,
-                      const float* prev, float* dog, unsigned* slot, cudaStream_t st, Prof* prof = nullptr) {
+                      const float* prev, float* dog, unsigned* slot, cudaStream_t st, Prof* prof = nullptr, int nz_glob = -1,
+                      int z_off = 0) {
     const ll total = (ll)nx * ny * nz;
     const int n = axis == 0 ? nx : (axis == 1 ? ny : nz);
-    const Taps t = with_ext(t0, n);
+    const bool partial = axis == 2 && nz_glob > 0 && (z_off != 0 || nz != nz_glob);
+    const Taps t = partial ? with_ext(t0, n, nz_glob, z_off) : with_ext(t0, n);
     const bool fast = variant == 1 && (nx % 4 == 0) && supported_fast_hw(t.hw) && n >= 2 * t.hw + 2 && total >= 4096 &&
                       !(axis == 0 && dog);
     // algorithmic bytes: read src + write dst (+ read prev + write dog on the fused pass)
@@ -283,7 +291,7 @@ static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int 
                  (dog ? 16.0 : 8.0) * (double)total);
     if (!fast) {
         S3D_LAUNCH(blur_generic_kernel, s3d_blocks((size_t)total, 256), 256, 0, st, src, dst, nx, ny, nz, axis, t, prev,
-                   dog, slot);
+                   dog, slot, partial ? nz_glob : 0, partial ? z_off : 0);
         return;
     }
     if (axis == 0) {
@@ -693,7 +701,7 @@ static int stage_octave(s3d_ctx* c, int o) {
         if (i >= 1) {
             unsigned* slot = c->d_slots + 1 + o * D + i - 1;
             blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, src, c->dog[o * D + i - 1], c->slab ? scratch_slot : slot, st,
-                      &c->prof);
+                      &c->prof, c->dims[o][2], c->za[o]);
             if (c->slab && c->p1[o] > c->p0[o]) {
                 const size_t n = (size_t)(c->p1[o] - c->p0[o]) * c->plane(o);
                 const float* own = c->dog[o * D + i - 1] + (size_t)(c->p0[o] - c->za[o]) * c->plane(o);
@@ -701,7 +709,7 @@ static int stage_octave(s3d_ctx* c, int o) {
                 S3D_LAUNCH(maxabs_kernel, (unsigned)std::min<size_t>(s3d_blocks(n / 4 + 1, 256), 148 * 16), 256, 0, st, own, n, slot);
             }
         } else {
-            blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
+            blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, nullptr, nullptr, nullptr, st, &c->prof, c->dims[o][2], c->za[o]);
         }
     }
     S3D_CUDA(cudaGetLastError());

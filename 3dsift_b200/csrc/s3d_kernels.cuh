@@ -158,7 +158,11 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) blur_generic_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
                                                            int ny, int nz, int axis, Taps t,
                                                            const float* __restrict__ prev, float* __restrict__ dog,
-                                                           unsigned* maxslot) {
+                                                           unsigned* maxslot, int gn, int goff) {
+    // gn > 0: the buffer holds planes [goff, goff+nz) of a z line of gn planes (a z-slab shard whose
+    // local extent is not the whole line).  The boundary rule is then evaluated in GLOBAL coordinates
+    // (its FP32 blend fraction depends on the magnitude of the coordinate) and samples are fetched
+    // from the local planes, clamped — clamped samples only feed planes inside the shard's halo margin.
     const ll total = (ll)nx * ny * nz;
     const ll idx = (ll)blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.0f;
@@ -169,7 +173,21 @@ __global__ void __launch_bounds__(256) blur_generic_kernel(const float* __restri
         const ll st = axis == 0 ? 1 : (axis == 1 ? (ll)nx : (ll)nx * ny);
         const ll line0 = idx - (ll)p * st;
         float acc;
-        if (blur_is_interior(p, n, t.hw)) {
+        if (gn > 0 && axis == 2) {
+            acc = 0.0f;
+            const int dim_end = gn - 1;
+            for (int d = -t.hw; d <= t.hw; ++d) {
+                float c = (float)(p + goff) - (float)d;
+                if (c < 0)
+                    c = -1 * c;
+                else if (c >= dim_end)
+                    c = (float)(2 * dim_end) - c - 0.1f;
+                const int il = (int)c;
+                const float frac = c - (float)il;
+                const int l0 = min(max(il - goff, 0), nz - 1), l1 = min(max(il + 1 - goff, 0), nz - 1);
+                acc += t.w[d + t.hw] * ((1.0f - frac) * src[line0 + (ll)l0 * st] + frac * src[line0 + (ll)l1 * st]);
+            }
+        } else if (blur_is_interior(p, n, t.hw)) {
             acc = 0.0f;
             for (int d = -t.hw; d <= t.hw; ++d) acc += t.w[d + t.hw] * src[line0 + (ll)(p - d) * st];
         } else {

@@ -23,7 +23,12 @@ def _same_records(a, b):
     return all(np.array_equal(a[f], b[f]) for f in fields)
 
 
-@pytest.mark.parametrize("shape,shards", [((96, 64, 72), 2), ((96, 64, 72), 3), ((128, 48, 64), 4), ((70, 66, 68), 2)])
+# (160, ...) with 4 or 3 shards: the top shard's local plane count (78 / 92) lies in another FP32 binade than
+# the global 160, so the right-edge blend fraction of the z pass (c' = 2(n-1) - c - 0.1f, "whatever FP32
+# gives") only matches the reference when it is evaluated in GLOBAL coordinates; (.., 46, 50) takes the
+# generic kernel (nx % 4 != 0).
+@pytest.mark.parametrize("shape,shards", [((96, 64, 72), 2), ((96, 64, 72), 3), ((128, 48, 64), 4), ((70, 66, 68), 2),
+                                          ((160, 48, 64), 4), ((160, 46, 50), 3)])
 def test_slabs_equal_unsharded(s3d, synth, shape, shards):
     d = importlib.import_module("3dsift_b200.dist")
     vol = synth.v_blobs(shape, seed=11)
