@@ -105,6 +105,7 @@ def lib():
     L.s3d_match_stats.restype = None
     L.s3d_level_info.argtypes = [vp, C.c_int, C.c_int, vp, vp]
     L.s3d_device_descriptors.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int)]
+    L.s3d_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     ip = C.POINTER(C.c_int)
     L.s3d_slab_extent.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.c_int, ip]
     L.s3d_slab_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]

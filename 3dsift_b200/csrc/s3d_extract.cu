@@ -1199,6 +1199,15 @@ int s3d_device_descriptors(s3d_handle c, const float** d_desc, int* n) {
     return S3D_OK;
 }
 
+int s3d_device_results(s3d_handle c, const void** d_ptrs5, int* n_kps, int* n_extre) {
+    if (!c || !d_ptrs5 || !n_kps || !n_extre) return fail(S3D_ERR_ARG, "null argument");
+    if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
+    d_ptrs5[0] = c->d_kps; d_ptrs5[1] = c->d_desc; d_ptrs5[2] = c->d_extre; d_ptrs5[3] = c->d_codes; d_ptrs5[4] = c->d_xyz5;
+    *n_kps = c->n_kps;
+    *n_extre = c->n_extre;
+    return S3D_OK;
+}
+
 int s3d_get_input(s3d_handle c, float* out) {
     clear_error();
     if (!c || !out) return fail(S3D_ERR_ARG, "null argument");

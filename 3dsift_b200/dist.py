@@ -184,8 +184,8 @@ def needed_from(ext_src, ext_dst):
 class _DevMem:
     """Zero-copy view of raw device memory for torch (``torch.as_tensor(_DevMem(...), device='cuda')``)."""
 
-    def __init__(self, ptr, nelem):
-        self.__cuda_array_interface__ = {"shape": (int(nelem),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+    def __init__(self, ptr, nelem, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (int(nelem),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 class SlabShard:
@@ -270,6 +270,24 @@ class SlabShard:
         api.check(L.s3d_get_extrema(self._h, api._ptr(ex), api._ptr(codes), api._ptr(xyz5)))
         return dict(kp=kp[:k], desc=desc[:k], extrema=ex[:e], codes=codes[:e], xyz5=xyz5[:e])
 
+    def device_results(self):
+        """The shard's result arrays as torch tensors aliasing device memory (valid until close()):
+        dict(kp uint8 [k,176], desc float32 [k,768], extrema uint8 [e,176], codes int32 [e,1], xyz5 int32 [e,5])."""
+        import torch
+        ptrs = (C.c_void_p * 5)()
+        k, e = C.c_int(), C.c_int()
+        api.check(api.lib().s3d_device_results(self._h, ptrs, C.byref(k), C.byref(e)))
+        k, e = k.value, e.value
+        spec = (("kp", k, 176, "|u1", torch.uint8), ("desc", k, api.DESC_LENGTH, "<f4", torch.float32),
+                ("extrema", e, 176, "|u1", torch.uint8), ("codes", e, 1, "<i4", torch.int32), ("xyz5", e, 5, "<i4", torch.int32))
+        out = {}
+        for (name, n, w, ts, dt), p in zip(spec, ptrs):
+            if n > 0 and p:
+                out[name] = torch.as_tensor(_DevMem(p, n * w, ts), device="cuda").view(n, w)
+            else:
+                out[name] = torch.empty((0, w), dtype=dt, device="cuda")
+        return out
+
     def get_level_host(self, which, idx):
         t, ext = self.level(which, idx)
         return (None if t is None else t.cpu().numpy()), ext
@@ -347,48 +365,76 @@ def merge_shard_results(parts, num_kp_levels=3):
     return out
 
 
-_RESULT_FIELDS = (("kp", np.uint8, 176), ("desc", np.float32, api.DESC_LENGTH), ("extrema", np.uint8, 176), ("codes", np.int32, 1),
-                  ("xyz5", np.int32, 5))
+_PINNED = {}
 
 
-def _all_gather_results(mine, me, world, group):
-    """Every rank's shard results on every rank, as NCCL all-gathers of padded device tensors (pickling
-    30 MB of descriptors through all_gather_object cost more than the whole extraction).
-    ``mine`` = [(gid, result dict)] with at most one shard per rank; returns the list sorted by gid."""
+def _to_host(t):
+    """Device tensor -> fresh numpy array through a cached pinned staging buffer (a pageable .cpu() of the
+    30 MB descriptor block runs at a few GB/s; pinned D2H + one host memcpy is several times faster)."""
+    import torch
+    n = t.numel() * t.element_size()
+    if n == 0:
+        return t.cpu().numpy()
+    buf = _PINNED.get("buf")
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1 << 22), dtype=torch.uint8).pin_memory()
+        _PINNED["buf"] = buf
+    view = buf[:n].view(t.dtype).view(t.shape)
+    view.copy_(t.contiguous(), non_blocking=False)
+    return view.numpy().copy()
+
+
+def _gather_merge_device(shard_results, world, group, num_kp_levels, with_extrema=True):
+    """All ranks' shard results merged in the reference's order (octave, level, z, y, x), on the GPU:
+    padded all-gathers of the device result arrays over NCCL, a stable sort of the per-row unit key
+    (rows arrive shard-major and in raster order inside a shard, so a STABLE sort by unit is the whole
+    merge, App. B Q16), one gather, one device->host copy per array.
+    shard_results: list of device_results() dicts of the shards held by this process, in shard order."""
     import torch
     import torch.distributed as dist
-    assert len(mine) <= 1, "distributed slabs hold one shard per rank"
-    gid, res = mine[0] if mine else (-1, None)
-    k = len(res["kp"]) if res else 0
-    e = len(res["extrema"]) if res else 0
-    cnt = torch.tensor([gid, k, e], dtype=torch.int64, device="cuda")
-    cnts = torch.empty((world, 3), dtype=torch.int64, device="cuda")
-    dist.all_gather_into_tensor(cnts.view(-1), cnt, group=group)
-    cnts = cnts.cpu().numpy()
-    kmax, emax = int(cnts[:, 1].max()), int(cnts[:, 2].max())
-    got = {}
-    for name, dt, width in _RESULT_FIELDS:
-        rows = kmax if name in ("kp", "desc") else emax
-        n = k if name in ("kp", "desc") else e
-        buf = torch.zeros((max(rows, 1), width), dtype=torch.from_numpy(np.zeros(1, dt)).dtype, device="cuda")
-        if n:
-            host = np.ascontiguousarray(res[name]).view(dt).reshape(n, width)
-            buf[:n].copy_(torch.from_numpy(host), non_blocking=False)
-        out = torch.empty((world,) + tuple(buf.shape), dtype=buf.dtype, device="cuda")
-        dist.all_gather_into_tensor(out.view(-1), buf.view(-1), group=group)
-        got[name] = out.cpu().numpy()
-    parts = []
-    for r in range(world):
-        g, kr, er = (int(v) for v in cnts[r])
-        if g < 0:
+    cat = {n: torch.cat([r[n] for r in shard_results]) if shard_results else None for n in ("kp", "desc", "extrema", "codes", "xyz5")}
+    k = int(cat["kp"].shape[0]) if shard_results else 0
+    e = int(cat["extrema"].shape[0]) if shard_results else 0
+    if world > 1:
+        cnt = torch.tensor([k, e], dtype=torch.int64, device="cuda")
+        cnts = torch.empty((world, 2), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(cnts.view(-1), cnt, group=group)
+        cnts = cnts.cpu()
+        kmax, emax = int(cnts[:, 0].max()), int(cnts[:, 1].max())
+    widths = dict(kp=(176, torch.uint8), desc=(api.DESC_LENGTH, torch.float32), extrema=(176, torch.uint8), codes=(1, torch.int32),
+                  xyz5=(5, torch.int32))
+    out = {}
+    names = ("kp", "desc", "extrema", "codes", "xyz5") if with_extrema else ("kp", "desc")
+    flat = {}
+    for name in names:
+        w, dt = widths[name]
+        mine = cat[name] if shard_results else torch.empty((0, w), dtype=dt, device="cuda")
+        if world == 1:
+            flat[name] = mine
             continue
-        parts.append((g, dict(kp=got["kp"][r, :kr].copy().view(api.KP_DTYPE).reshape(-1), desc=got["desc"][r, :kr],
-                              extrema=got["extrema"][r, :er].copy().view(api.KP_DTYPE).reshape(-1),
-                              codes=got["codes"][r, :er, 0], xyz5=got["xyz5"][r, :er])))
-    return sorted(parts, key=lambda t: t[0])
+        is_k = name in ("kp", "desc")
+        rows, n = (kmax, k) if is_k else (emax, e)
+        buf = torch.zeros((max(rows, 1), w), dtype=dt, device="cuda")
+        buf[:n] = mine
+        allb = torch.empty((world,) + tuple(buf.shape), dtype=dt, device="cuda")
+        dist.all_gather_into_tensor(allb.view(-1), buf.view(-1), group=group)
+        valid = (torch.arange(max(rows, 1), device="cuda")[None, :] < cnts[:, 0 if is_k else 1].cuda()[:, None]).view(-1)
+        flat[name] = allb.view(-1, w)[valid]
+    # unit keys: octave and level sit at int32 words 4 and 5 of a keypoint record; xyz5 carries them as columns 3, 4
+    kw = flat["kp"].contiguous().view(torch.int32).view(-1, 44)
+    ko = torch.sort(kw[:, 4].long() * (num_kp_levels + 1) + kw[:, 5].long(), stable=True).indices
+    out["kp"] = _to_host(flat["kp"][ko]).view(api.KP_DTYPE).reshape(-1)
+    out["desc"] = _to_host(flat["desc"][ko])
+    if with_extrema:
+        x5 = flat["xyz5"]
+        eo = torch.sort(x5[:, 3].long() * (num_kp_levels + 1) + x5[:, 4].long(), stable=True).indices
+        out["extrema"] = _to_host(flat["extrema"][eo]).view(api.KP_DTYPE).reshape(-1)
+        out["codes"] = _to_host(flat["codes"][eo]).reshape(-1)
+        out["xyz5"] = _to_host(x5[eo])
+    return out
 
 
-def extract_slabs(volume, shards=None, group=None, params=None, keep=False, timing=None):
+def extract_slabs(volume, shards=None, group=None, params=None, keep=False, timing=None, with_extrema=True):
     """Full extraction of ONE volume split into z-slabs.
 
     * distributed (torch.distributed initialised, ``shards`` None): one shard per rank of ``group``;
@@ -397,6 +443,7 @@ def extract_slabs(volume, shards=None, group=None, params=None, keep=False, timi
     * single process (``shards`` = G): G logical shards on the current device, same code path with
       device copies instead of send/recv — the CI check that sharded == unsharded.
 
+    ``with_extrema`` = False skips gathering the per-detection debug records (extrema, codes, xyz5).
     ``timing`` (a dict) receives device-synchronised wall seconds per phase: upload, pyramid (blur
     chain + seed halo exchanges + scalar all-reduces), halo (descriptor-window planes), sparse, gather.
 
@@ -494,13 +541,9 @@ def extract_slabs(volume, shards=None, group=None, params=None, keep=False, timi
     tick("halo")
     for g in held:
         sh[g].finish()
-    mine = [(g, sh[g].results()) for g in held]
     tick("sparse")
-    if distributed:
-        allp = _all_gather_results(mine, me, world, group)
-    else:
-        allp = mine
-    out = merge_shard_results([r for _, r in allp], nlev)
+    # results stay on the device until they are merged: all-gather + stable sort + one D2H per array
+    out = _gather_merge_device([sh[g].device_results() for g in held], world if distributed else 1, group, nlev, with_extrema)
     tick("gather")
     if keep:
         out["shards"] = sh

@@ -129,6 +129,11 @@ S3D_API int s3d_level_info(s3d_handle h, int which, int idx, int* dims3, float* 
 /* Device address of the K x 768 descriptor block of a finished extraction (valid until
  * s3d_destroy): lets a matcher consume descriptors without the host round trip. */
 S3D_API int s3d_device_descriptors(s3d_handle h, const float** d_desc, int* n);
+/* Device pointers of every result array of a finished run (valid until s3d_destroy), for consumers
+ * that gather / merge on the GPU (z-slab shards): d_ptrs5 = {keypoint records (n_kps x 176 B, desc
+ * pointer null), descriptors (n_kps x 768 float), detection records (n_extre x 176 B), accept codes
+ * (n_extre int), xyz5 (n_extre x 5 int: x, y, z, octave, level)}. */
+S3D_API int s3d_device_results(s3d_handle h, const void** d_ptrs5, int* n_kps, int* n_extre);
 /* The normalised input (Host_Im after data_scale, Src/cSIFT3D.cc:162). */
 S3D_API int s3d_get_input(s3d_handle h, float* out);
 /* Per-level detection thresholds peak_thresh*max|DoG| (Src/cSIFT3D.cc:384-385), o*L + (i-1). */

@@ -83,11 +83,11 @@ if rank == 0:
 
 # ---- 3. timings ------------------------------------------------------------------------------------
 big = torch.from_numpy(synth.v_blobs(a.big, seed=0)).pin_memory().numpy()   # numpy view of pinned host memory
-res, sec = timed(lambda: D.extract_slabs(big))
+res, sec = timed(lambda: D.extract_slabs(big, with_extrema=False), reps=3)
 phases = {}
-D.extract_slabs(big, timing=phases)
+D.extract_slabs(big, timing=phases, with_extrema=False)
 out["slab_timing"] = {"size": a.big, "seconds": sec, "phases_s": {k: round(v, 4) for k, v in phases.items()}, "mvoxels_per_s": big.size / sec / 1e6, "keypoints": int(len(res["kp"])),
-                      "note": "host volume in, merged host results out (includes the per-shard upload and the result gather)"}
+                      "note": "pinned host volume in, merged keypoints + descriptors out on the host of every rank (includes the per-shard upload and the NCCL result gather)"}
 del res
 dr, dt_, _ = synth.d_synth_pair_device(a.match_big, seed=9)   # same seed on every rank: replicated, HBM-resident sets
 res, sec = timed(lambda: D.match_sharded(3, dr, dt_, 0.85))
