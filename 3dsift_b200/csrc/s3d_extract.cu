@@ -156,6 +156,46 @@ static void host_mesh(MeshConst* M) {
         M->neg[np] = opp >= 0 ? opp : i;
         np++;
     }
+    // Octant pre-selection tables, derived from the mesh itself (vertex positions V0 = -t, V1 = V0+e1, V2 = V0+e2).
+    auto vtx = [&](int f, int j, double* out) {
+        for (int c = 0; c < 3; c++) out[c] = -(double)M->t[f][c] + (j == 1 ? (double)M->e1[f][c] : (j == 2 ? (double)M->e2[f][c] : 0.0));
+    };
+    auto same = [](const double* a, const double* b) { return fabs(a[0] - b[0]) + fabs(a[1] - b[1]) + fabs(a[2] - b[2]) < 1e-4; };
+    for (int o = 0; o < 8; o++) {
+        const double sg[3] = {(o & 1) ? -1.0 : 1.0, (o & 2) ? -1.0 : 1.0, (o & 4) ? -1.0 : 1.0};
+        // the octant face: all three vertices inside the closed octant
+        int fo = 0;
+        for (int f = 0; f < 20; f++) {
+            bool in = true;
+            for (int j = 0; j < 3 && in; j++) {
+                double v[3];
+                vtx(f, j, v);
+                for (int c = 0; c < 3; c++) in = in && v[c] * sg[c] > -1e-6;
+            }
+            if (in) fo = f;
+        }
+        M->octface[o][0] = fo;
+        for (int k = 0; k < 3; k++) {  // edge k joins vertices k and (k+1)%3; the third vertex is inside
+            double a[3], b[3], cth[3];
+            vtx(fo, k, a); vtx(fo, (k + 1) % 3, b); vtx(fo, (k + 2) % 3, cth);
+            double n[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+            if (n[0] * cth[0] + n[1] * cth[1] + n[2] * cth[2] < 0) for (int c = 0; c < 3; c++) n[c] = -n[c];
+            for (int c = 0; c < 3; c++) M->octn[o][k][c] = (float)n[c];
+            int nb = fo;
+            for (int f = 0; f < 20; f++) {  // the other face that contains both a and b
+                if (f == fo) continue;
+                bool ha = false, hb = false;
+                for (int j = 0; j < 3; j++) {
+                    double v[3];
+                    vtx(f, j, v);
+                    ha = ha || same(v, a);
+                    hb = hb || same(v, b);
+                }
+                if (ha && hb) nb = f;
+            }
+            M->octface[o][1 + k] = nb;
+        }
+    }
 }
 
 // Extended-line table of a pass along an axis of length n (Src/cSIFT3D.cc:751-760): for tap

@@ -1080,6 +1080,12 @@ struct MeshConst {
     float cen10[10][3];                              // centroid of one face of each antipodal pair
     int pos[10], neg[10];                            // face with centroid +cen10[i] / -cen10[i]
     int idx[20][3];                                  // vertex ids (NOT swapped, App. B Q13)
+    // Octant pre-selection (host_mesh): an octant of direction space is covered by ONE whole face (a
+    // vertex on each coordinate plane) and the halves of the three faces across its edges.  octn[o][k]
+    // is the inward normal of edge k's plane through the origin, octface[o] = {octant face, neighbour
+    // across edge 0, 1, 2}.  o = (gx<0) | (gy<0)<<1 | (gz<0)<<2.
+    float octn[8][3][3];
+    int octface[8][4];
 };
 
 // cart2bary for one face, Src/cSIFT3D.cc:1592-1637, with the face-only terms precomputed on the
@@ -1122,26 +1128,23 @@ __device__ __forceinline__ bool face_bary_fast(const MeshConst& M, int f, float 
 
 // Check_intersect_faces, Src/cSIFT3D.cc:1542-1573: the FIRST face (index order) whose barycentric
 // coordinates are all >= -bary_eps with k >= 0 wins (App. B Q14).
-// Fast path: the faces of a regular icosahedron are the spherical Voronoi cells of their
-// centroids, so the face hit by a direction is argmax_f <cen_f, g>; faces come in antipodal
-// pairs, so 10 dot products (fused: this is only a pre-selection) decide among 20 faces.  If the
-// selected face's barycentric coordinates are all comfortably positive, no other face can pass
-// the reference's tolerance test and (face, bary) is exactly what the sequential scan returns
-// (same FP32 formula for the same face).  Directions within `margin` of an edge/vertex take the
-// reference's scan.
+// Fast path: the icosahedron's vertices lie on the coordinate planes, so each octant of direction
+// space holds one whole face and halves of the three faces across its edges: the sign bits and
+// three plane tests (fused: this is only a pre-selection) name the face.  If the selected face's
+// barycentric coordinates are all comfortably positive, no other face can pass the reference's
+// tolerance test and (face, bary) is what the sequential scan returns.  Directions within `margin`
+// of an edge/vertex — and any direction the pre-selection got wrong — take the reference's scan.
 __device__ __forceinline__ int find_face(const MeshConst& M, float gx, float gy, float gz, float bary_eps, float& b0,
                                          float& b1, float& b2) {
-    // key = |d| bits with the low 5 mantissa bits replaced by (pair index << 1 | sign): one max
-    // per pair instead of compare + three selects (a pre-selection only; see the margin test)
-    unsigned key = 0;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-        const float d = __fmaf_rn(M.cen10[i][0], gx, __fmaf_rn(M.cen10[i][1], gy, __fmul_rn(M.cen10[i][2], gz)));
-        const unsigned u = __float_as_uint(d);
-        key = max(key, ((u & 0x7fffffe0u) | (unsigned)(i << 1)) | (u >> 31));
-    }
-    const int fi = (int)((key >> 1) & 15u);
-    const int fs = (key & 1u) ? M.neg[fi] : M.pos[fi];
+    // three plane tests against the edges of the direction's octant face pick one of four faces (a
+    // pre-selection only: the margin test below decides whether it stands)
+    const int oct = (gx < 0.0f ? 1 : 0) | (gy < 0.0f ? 2 : 0) | (gz < 0.0f ? 4 : 0);
+    const float(*N)[3] = M.octn[oct];
+    const float d0 = __fmaf_rn(N[0][0], gx, __fmaf_rn(N[0][1], gy, __fmul_rn(N[0][2], gz)));
+    const float d1 = __fmaf_rn(N[1][0], gx, __fmaf_rn(N[1][1], gy, __fmul_rn(N[1][2], gz)));
+    const float d2 = __fmaf_rn(N[2][0], gx, __fmaf_rn(N[2][1], gy, __fmul_rn(N[2][2], gz)));
+    const int region = d0 < 0.0f ? 1 : (d1 < 0.0f ? 2 : (d2 < 0.0f ? 3 : 0));
+    const int fs = M.octface[oct][region];
     float k;
     const float margin = 1e-4f;
     if (face_bary_fast(M, fs, gx, gy, gz, bary_eps, b0, b1, b2, k) && b0 > margin && b1 > margin && b2 > margin && k > 0.0f)
