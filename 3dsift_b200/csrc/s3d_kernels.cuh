@@ -1326,6 +1326,15 @@ __global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const
     const int half = lane >> 4, hl = lane & 15;
     const unsigned lt_mask = (1u << lane) - 1u;
     const int l24 = lane < 24 ? lane : 0;
+    // Q: grid coordinates through fused multiply-adds, vb_k ~ Rf_k . disp + (hw*f - 0.5).  They differ from
+    // the reference's unfused evaluation by < 1e-5; a voxel whose coordinate lies within 1e-4 of an
+    // inclusion threshold (-0.5 / 3.5) is decided by the exact expression instead, so the SET of
+    // contributing voxels is still the reference's.  (sq needs no such care: dx, dy, dz are integers times
+    // a power of two and sq < 2^24, so it is exact in any evaluation order.)
+    const float Rf0 = R0 * desc_bin_fctr, Rf1 = R1 * desc_bin_fctr, Rf2 = R2 * desc_bin_fctr;
+    const float Rf3 = R3 * desc_bin_fctr, Rf4 = R4 * desc_bin_fctr, Rf5 = R5 * desc_bin_fctr;
+    const float Rf6 = R6 * desc_bin_fctr, Rf7 = R7 * desc_bin_fctr, Rf8 = R8 * desc_bin_fctr;
+    const float hwf = desc_hw * desc_bin_fctr - 0.5f;
 
     // ---- heavy phase + replay for up to 32 queued voxels (packed = dx | dy<<10 | dz<<20 offsets) ----
     auto heavy = [&](uint32_t packed, bool valid) {
@@ -1336,10 +1345,16 @@ __global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const
             const int xx = xs + (int)(packed & 1023u), yy = y0 + (int)((packed >> 10) & 1023u), zz = z0 + (int)(packed >> 20);
             const float dx = ((float)xx - cx) * u, dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
             const float sq = dx * dx + dy * dy + dz * dz;
-            vb0 = (R0 * dx + R1 * dy + R2 * dz + desc_hw) * desc_bin_fctr;
-            vb1 = (R3 * dx + R4 * dy + R5 * dz + desc_hw) * desc_bin_fctr;
-            vb2 = (R6 * dx + R7 * dy + R8 * dz + desc_hw) * desc_bin_fctr;
-            vb0 -= 0.5f; vb1 -= 0.5f; vb2 -= 0.5f;
+            if constexpr (Q) {  // cell split only (no inclusion decision here): fused form
+                vb0 = __fmaf_rn(Rf0, dx, __fmaf_rn(Rf1, dy, __fmaf_rn(Rf2, dz, hwf)));
+                vb1 = __fmaf_rn(Rf3, dx, __fmaf_rn(Rf4, dy, __fmaf_rn(Rf5, dz, hwf)));
+                vb2 = __fmaf_rn(Rf6, dx, __fmaf_rn(Rf7, dy, __fmaf_rn(Rf8, dz, hwf)));
+            } else {
+                vb0 = (R0 * dx + R1 * dy + R2 * dz + desc_hw) * desc_bin_fctr;
+                vb1 = (R3 * dx + R4 * dy + R5 * dz + desc_hw) * desc_bin_fctr;
+                vb2 = (R6 * dx + R7 * dy + R8 * dz + desc_hw) * desc_bin_fctr;
+                vb0 -= 0.5f; vb1 -= 0.5f; vb2 -= 0.5f;
+            }
             const int mi = (int)(sq * inv_u2);  // sq = u*u*m exactly, see wtab_kernel
             const float weight = wt_s ? S.wt[mi] : wt_g[mi];  // == expf(-0.5f * sq / s2), :1312
             const ll i = (ll)xx + (ll)yy * ys + (ll)zz * zs;
@@ -1472,18 +1487,35 @@ __global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const
         const int len_other = __shfl_xor_sync(0xffffffffu, len, 16);
         const int iters = (max(len, len_other) + 15) >> 4;
         const uint32_t pyz = ((uint32_t)(yy - y0) << 10) | ((uint32_t)(zz - z0) << 20);
+        // row constants of the fused grid coordinates (Q)
+        const float rb0 = __fmaf_rn(Rf1, dy, __fmaf_rn(Rf2, dz, hwf)), rb1 = __fmaf_rn(Rf4, dy, __fmaf_rn(Rf5, dz, hwf)),
+                    rb2 = __fmaf_rn(Rf7, dy, __fmaf_rn(Rf8, dz, hwf));
         for (int it = 0; it < iters; ++it) {
             const int xx = xlo + it * 16 + hl;
             bool pass = false;
             if (xx <= xhi) {
                 const float dx = ((float)xx - cx) * u;
-                const float sq = dx * dx + dy * dy + dz * dz;
-                if (!(sq > r2)) {  // :1270
+                auto exact_pass = [&]() -> bool {
                     float vb0 = (R0 * dx + R1 * dy + R2 * dz + desc_hw) * desc_bin_fctr;
                     float vb1 = (R3 * dx + R4 * dy + R5 * dz + desc_hw) * desc_bin_fctr;
                     float vb2 = (R6 * dx + R7 * dy + R8 * dz + desc_hw) * desc_bin_fctr;
                     vb0 -= 0.5f; vb1 -= 0.5f; vb2 -= 0.5f;
-                    pass = !(vb0 <= -0.5f || vb1 <= -0.5f || vb2 <= -0.5f || vb0 >= 3.5f || vb1 >= 3.5f || vb2 >= 3.5f);  // :1300
+                    return !(vb0 <= -0.5f || vb1 <= -0.5f || vb2 <= -0.5f || vb0 >= 3.5f || vb1 >= 3.5f || vb2 >= 3.5f);  // :1300
+                };
+                if constexpr (Q) {
+                    const float sq = __fmaf_rn(dx, dx, dyz2);  // exact (see above)
+                    if (!(sq > r2)) {  // :1270
+                        const float vb0 = __fmaf_rn(Rf0, dx, rb0), vb1 = __fmaf_rn(Rf3, dx, rb1), vb2 = __fmaf_rn(Rf6, dx, rb2);
+                        // distance of the three coordinates to the interval (-0.5, 3.5): inside by more than the margin /
+                        // outside by more than the margin / too close to call
+                        const float lo3 = fminf(vb0, fminf(vb1, vb2)), hi3 = fmaxf(vb0, fmaxf(vb1, vb2));
+                        const float inside = fminf(lo3 + 0.5f, 3.5f - hi3);
+                        pass = inside > 1e-4f;
+                        if (fabsf(lo3 + 0.5f) <= 1e-4f || fabsf(3.5f - hi3) <= 1e-4f) pass = exact_pass();
+                    }
+                } else {
+                    const float sq = dx * dx + dy * dy + dz * dz;
+                    if (!(sq > r2)) pass = exact_pass();  // :1270
                 }
             }
             const unsigned mp = __ballot_sync(0xffffffffu, pass);
