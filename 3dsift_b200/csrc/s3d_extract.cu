@@ -230,6 +230,11 @@ static int initial_describe_path() {
 }
 static std::atomic<int> g_describe_path{initial_describe_path()};
 
+static bool desc_order_enabled() {
+    static const bool on = !(getenv("S3D_DESC_ORDER") && getenv("S3D_DESC_ORDER")[0] == '0');
+    return on;
+}
+
 static bool supported_fast_hw(int hw) { return hw == 2 || hw == 3 || hw == 4 || hw == 5 || hw == 6 || hw == 8; }
 
 template <int HW>
@@ -253,14 +258,27 @@ static void launch_march(const float* src, float* dst, int nx, int n, ll st_m, i
     const int seg = pick_seg(nx4, n_other, n);
     const int nseg = (n + seg - 1) / seg;
     ll threads = (ll)nx4 * n_other * nseg;
+    // S3D_ZVAR: 0 = register-ring prefetch (blur_march_kernel), 1 = cp.async ring (blur_marchc_kernel, default)
+    static const int zvar = [] { const char* e = getenv("S3D_ZVAR"); return (e && e[0] >= '0' && e[0] <= '1' && !e[1]) ? e[0] - '0' : 1; }();
+    const unsigned blocks = s3d_blocks((size_t)threads, 128);
     if (dog) {
-        auto kfn = blur_march_kernel<HW, true>;
-        S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 128), 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
-                   prev, dog, slot);
+        if (zvar == 0) {
+            auto kfn = blur_march_kernel<HW, true>;
+            S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t, prev, dog, slot);
+        } else {
+            auto kfn = blur_marchc_kernel<HW, true>;
+            S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t, prev, dog, slot);
+        }
     } else {
-        auto kfn = blur_march_kernel<HW, false>;
-        S3D_LAUNCH(kfn, s3d_blocks((size_t)threads, 128), 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
-                   (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr);
+        if (zvar == 0) {
+            auto kfn = blur_march_kernel<HW, false>;
+            S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
+                       (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr);
+        } else {
+            auto kfn = blur_marchc_kernel<HW, false>;
+            S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
+                       (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr);
+        }
     }
 }
 
@@ -355,15 +373,23 @@ static int xy_seg_override() {
     const char* e = getenv("S3D_BLUR_XY_SEG");
     return e ? atoi(e) : 0;
 }
+static int blur_xy_mode() {
+    // S3D_BLUR_XY: 0 = separate X and Y passes, 1 = blur_xy_kernel for hw <= 6 (separate passes at hw 8),
+    // 2 = blur_xy_kernel for hw <= 3 and the compact-code blur_xyc_kernel for hw >= 4 (default),
+    // 3 = blur_xyc_kernel for every hw
+    const char* e = getenv("S3D_BLUR_XY");
+    return (e && e[0] >= '0' && e[0] <= '3' && !e[1]) ? e[0] - '0' : 2;
+}
 static bool blur_xy_pass(const float* src, float* dst, int nx, int ny, int nz, const Taps& t0, cudaStream_t st, Prof* prof) {
-    static const bool enabled = !(getenv("S3D_BLUR_XY") && getenv("S3D_BLUR_XY")[0] == '0');
+    static const int mode = blur_xy_mode();
     static const int seg_env = xy_seg_override();
     const int hw = t0.hw, T = nx >> 2;
-    // measured on B200 (profiles/r01_ncu_blur_xy.txt): the fused kernel beats X + Y for hw <= 6 (octave 0:
-    // 191/241/339/385/542 us against 412/434/460/515/645); at hw = 8 its two CTA barriers per row cost
-    // more than the saved round trip (881 against 767 us), so the widest level keeps the separate passes
-    if (!enabled || hw > 6 || nx % 4 != 0 || T < 1 || T > 128 || 128 % T != 0 || T <= hw + 1 || !supported_fast_hw(hw) ||
-        nx < 2 * hw + 2 || ny < 2 * hw + 2 || (ll)nx * ny * nz < 4096)
+    // measured on B200 (profiles/r01_ncu_blur_xy.txt): blur_xy_kernel beats X + Y for hw <= 6 (octave 0:
+    // 191/241/339/385/542 us against 412/434/460/515/645) but stalls on instruction fetch from hw 4 up (its
+    // unrolled ring replicates the X body); blur_xyc_kernel is the same arithmetic in compact code
+    const bool compact = mode == 3 || (mode == 2 && hw >= 4);
+    if (mode == 0 || (mode == 1 && hw > 6) || nx % 4 != 0 || T < 1 || T > 128 || 128 % T != 0 || T <= hw + 1 ||
+        !supported_fast_hw(hw) || nx < 2 * hw + 2 || ny < 2 * hw + 2 || (ll)nx * ny * nz < 4096)
         return false;
     const Taps tx = with_ext(t0, nx), ty = with_ext(t0, ny);
     const int lpc = 128 / T, zgroups = (nz + lpc - 1) / lpc;
@@ -375,8 +401,14 @@ static bool blur_xy_pass(const float* src, float* dst, int nx, int ny, int nz, c
     const size_t smem = (size_t)lpc * kXYBufs * (nx + 2 * ((hw + 3) / 4 * 4)) * sizeof(float);
     ProfScope ps(prof, K_BLUR_XY, 8.0 * (double)nx * ny * nz);
 #define CALLXY(H) S3D_LAUNCH(blur_xy_kernel<H>, (unsigned)(zgroups * nseg), 128, smem, st, src, dst, nx, ny, nz, seg, tx, ty)
-    S3D_HW_SWITCH(hw, CALLXY)
+#define CALLXYC(H) S3D_LAUNCH(blur_xyc_kernel<H>, (unsigned)(zgroups * nseg), 128, smem, st, src, dst, nx, ny, nz, seg, tx, ty)
+    if (compact) {
+        S3D_HW_SWITCH(hw, CALLXYC)
+    } else {
+        S3D_HW_SWITCH(hw, CALLXY)
+    }
 #undef CALLXY
+#undef CALLXYC
     return true;
 }
 
@@ -848,6 +880,7 @@ static int stage_sparse(s3d_ctx* c) {
     }
     int *d_recheck = nullptr;
     int* d_surv = nullptr;
+    int* d_order = nullptr;
     const size_t nea = std::max(ne, 1);
     S3D_CUDA(cudaMallocAsync((void**)&c->d_extre, sizeof(s3d_keypoint) * nea, st));
     S3D_CUDA(cudaMallocAsync((void**)&c->d_codes, sizeof(int) * nea, st));
@@ -871,6 +904,11 @@ static int stage_sparse(s3d_ctx* c) {
     {
         ProfScope ps(&c->prof, K_SURVIVORS, 8.0 * ne);
         S3D_LAUNCH(survivors_kernel, 1, 1024, 0, st, c->d_codes, ne, d_surv, d_total + 3);
+        // heavy-first launch order of the descriptor CTAs (S3D_DESC_ORDER=0: list order)
+        if (desc_order_enabled() && ne > 0) {
+            S3D_CUDA(cudaMallocAsync((void**)&d_order, sizeof(int) * nea, st));
+            S3D_LAUNCH(desc_order_kernel, 1, 1024, 0, st, c->d_extre, d_surv, d_total + 3, G - 1, d_order);
+        }
     }
     S3D_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
     S3D_CUDA(cudaStreamSynchronize(st));
@@ -904,7 +942,7 @@ static int stage_sparse(s3d_ctx* c) {
             {
                 ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
                 S3D_LAUNCH(describe_kernel<true>, c->n_kps, kDescWarps * 32, sizeof(DescSmemQ), st, c->d_extre, d_surv, c->n_kps, tab,
-                           c->d_mesh, c->d_kps, c->d_desc, (const int*)nullptr, (const int*)nullptr, d_redo + 1, d_redo,
+                           c->d_mesh, c->d_kps, c->d_desc, (const int*)d_order, (const int*)nullptr, d_redo + 1, d_redo,
                            path == 2 ? 0.02f : kQMargin);
             }
             ProfScope ps(&c->prof, K_DESCRIBE_REDO, 0.0);
@@ -919,7 +957,7 @@ static int stage_sparse(s3d_ctx* c) {
 
     // ---- Release_SIFT (:1659-1678) unless the caller asked to keep the pyramids ---------------
     if (!c->prm.keep_levels) free_levels(c);
-    void* tmp[] = {d_blk_cnt, d_blk_off, d_total, d_stage, d_stage_count, d_cand, d_recheck, d_surv, d_wtab, d_redo};
+    void* tmp[] = {d_blk_cnt, d_blk_off, d_total, d_stage, d_stage_count, d_cand, d_recheck, d_surv, d_order, d_wtab, d_redo};
     for (void* q : tmp) if (q) cudaFreeAsync(q, st);
     S3D_CUDA(cudaEventRecord(c->ev[6], st));
     c->queued = true;

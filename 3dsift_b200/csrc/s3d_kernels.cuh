@@ -252,12 +252,15 @@ __global__ void __launch_bounds__(256) blur_x_kernel(const float* __restrict__ s
 // extended-line samples (ext_sample4), so there is no separate boundary path.
 // Requires nx % 4 == 0 and n >= 2*HW+2.  n = length of the marched axis, st = its stride, n_other / st_other =
 // the remaining non-x axis.
-template <int HW, bool DOG>
+// PFX = extra prefetch distance of the marched samples, PP = prefetch distance of the DoG pass's `prev`
+// operand (its loads are issued PP steps before their use; PP = 1 left the Z pass waiting on every one:
+// ncu long_scoreboard = 20 warp-cycles per issue at 63 % of DRAM throughput).
+template <int HW, bool DOG, int PFX = 0, int PP = 1>
 __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
                                                          int n, ll st, int n_other, ll st_other, int seg, Taps t,
                                                          const float* __restrict__ prev, float* __restrict__ dog,
                                                          unsigned* maxslot) {
-    constexpr int PF = HW >= 5 ? 2 : 4;       // loads are issued PF steps ahead of their first use
+    constexpr int PF = (HW >= 5 ? 2 : 4) + PFX;  // loads are issued PF steps ahead of their first use
     constexpr int WR = 2 * HW + 1 + PF;       // ring size == unroll factor (static slot indices)
     const unsigned nx4 = (unsigned)nx >> 2;
     const int nseg = (n + seg - 1) / seg;
@@ -281,8 +284,12 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict
             win[r] = (q <= qmax) ? ext_sample4(col, st, n, q, t) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         win[2 * HW + PF] = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (DOG) pv = *reinterpret_cast<const float4*>(prev + line0 + (ll)p0 * st);
+        float4 pvq[PP];  // prev samples p .. p+PP-1
+#pragma unroll
+        for (int k = 0; k < PP; ++k) {
+            pvq[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (DOG && p0 + k < p1) pvq[k] = *reinterpret_cast<const float4*>(prev + line0 + (ll)(p0 + k) * st);
+        }
         for (int ib = 0; p0 + ib < p1; ib += WR) {
 #pragma unroll
             for (int j = 0; j < WR; ++j) {
@@ -292,7 +299,7 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict
                     const int q = p + HW + PF;
                     if (q <= qmax) win[(j + 2 * HW + PF) % WR] = ext_sample4(col, st, n, q, t);
                     float4 pvn = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (DOG && p + 1 < p1) pvn = *reinterpret_cast<const float4*>(prev + line0 + (ll)(p + 1) * st);
+                    if (DOG && p + PP < p1) pvn = *reinterpret_cast<const float4*>(prev + line0 + (ll)(p + PP) * st);
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int k = 0; k <= 2 * HW; ++k) {
@@ -304,15 +311,126 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict
                     *reinterpret_cast<float4*>(dst + oidx) = acc;
                     if (DOG) {
                         float4 dv;
+                        const float4 pv = pvq[0];
                         dv.x = (acc.x - pv.x) * (-1); dv.y = (acc.y - pv.y) * (-1);
                         dv.z = (acc.z - pv.z) * (-1); dv.w = (acc.w - pv.w) * (-1);
                         *reinterpret_cast<float4*>(dog + oidx) = dv;
                         m = fmaxf(m, fmaxf(fmaxf(fabsf(dv.x), fabsf(dv.y)), fmaxf(fabsf(dv.z), fabsf(dv.w))));
-                        pv = pvn;
+#pragma unroll
+                        for (int k = 0; k + 1 < PP; ++k) pvq[k] = pvq[k + 1];
+                        pvq[PP - 1] = pvn;
                     }
                 }
             }
         }
+    }
+    if (DOG) {
+        m = warp_max(m);
+        if ((threadIdx.x & 31) == 0) atomic_max_abs(maxslot, m);
+    }
+}
+
+constexpr int kXYBufs = 4;  // shared-memory row ring of the fused X+Y pass (cp.async runs kXYBufs-1 rows ahead)
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The same march with the loads issued as cp.async copies into a per-thread ring in shared memory.
+// blur_march_kernel prefetches into registers, and a warp has only six scoreboards to track its
+// outstanding loads: waiting for the oldest one also waits for younger ones that share its scoreboard, so
+// the prefetch distance collapses once occupancy is register-limited (scripts/micro/stream4_bench.cu: a
+// 2-read/2-write march at 4-7 CTAs/SM moves 5.4-5.6 TB/s with a register ring and 6.4-6.5 TB/s with this
+// ring).  cp.async groups are counted, not score-boarded: the copies of step r + D - 1 are issued before
+// step r's are consumed, whatever the occupancy.  Every slot is written and read by the same thread, so no
+// CTA barrier is needed.  One loop covers prologue and body: step r takes extended-line sample
+// q = p0 - HW + r into the register window and, from r = 2*HW on, emits output p = p0 + r - 2*HW.
+// Samples beyond the line's end (q >= n-1, the reference's right-edge blend) are loaded directly.
+template <int HW, bool DOG>
+__global__ void __launch_bounds__(128) blur_marchc_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
+                                                          int n, ll st, int n_other, ll st_other, int seg, Taps t,
+                                                          const float* __restrict__ prev, float* __restrict__ dog,
+                                                          unsigned* maxslot) {
+    constexpr int D = 4;             // copies in flight per thread and stream
+    constexpr int WR = 2 * HW + 1;   // register window == unroll factor (static slot indices)
+    constexpr int NS = DOG ? 2 : 1;
+    __shared__ float4 ring[D][NS][128];
+    const unsigned nx4 = (unsigned)nx >> 2;
+    const int nseg = (n + seg - 1) / seg;
+    const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.0f;
+    if (gid < nx4 * (unsigned)n_other * (unsigned)nseg) {
+        const unsigned tt = gid / nx4;
+        const int x4 = (int)(gid - tt * nx4);
+        const int s = (int)(tt / (unsigned)n_other);
+        const int other = (int)(tt - (unsigned)s * (unsigned)n_other);
+        const int p0 = s * seg;
+        const int p1 = min(n, p0 + seg);
+        const int nsamp = p1 - p0 + 2 * HW;  // samples q = p0-HW .. p1-1+HW
+        const ll line0 = (ll)x4 * 4 + (ll)other * st_other;
+        const float* col = src + line0;
+        const float* pcol = DOG ? prev + line0 : nullptr;
+        const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(&ring[0][0][threadIdx.x]);
+        constexpr uint32_t kSlotBytes = NS * 128 * 16, kPrevOff = 128 * 16;
+        auto issue = [&](int r, uint32_t slot_addr) {
+            if (r < nsamp) {
+                const int q = p0 - HW + r;
+                if (q < n - 1)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot_addr), "l"(col + (ll)(q < 0 ? -q : q) * st) : "memory");
+                if (DOG && r >= 2 * HW)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot_addr + kPrevOff), "l"(pcol + (ll)(q - HW) * st) : "memory");
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int r = 0; r < D - 1; ++r) issue(r, ring0 + r * kSlotBytes);
+        int slot = 0;  // slot of step r; step r + D - 1 goes into the slot before it
+        float4 win[WR];
+#pragma unroll
+        for (int r = 0; r < WR; ++r) win[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ib = 0; ib < nsamp; ib += WR) {
+#pragma unroll
+            for (int j = 0; j < WR; ++j) {
+                const int r = ib + j;
+                if (r < nsamp) {
+                    const int pslot = slot == 0 ? D - 1 : slot - 1;
+                    issue(r + D - 1, ring0 + pslot * kSlotBytes);
+                    cp_async_wait<D - 1>();
+                    const int q = p0 - HW + r;
+                    float4 sv;
+                    if (q < n - 1) {
+                        sv = ring[slot][0][threadIdx.x];
+                    } else {
+                        sv = ext_sample4(col, st, n, q, t);
+                    }
+                    win[j] = sv;
+                    if (r >= 2 * HW) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k <= 2 * HW; ++k) {
+                            const float4 v = win[(j - k + WR) % WR];  // sample q - k = p + HW - k
+                            const float w = t.w[k];
+                            acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+                        }
+                        const ll oidx = line0 + (ll)(q - HW) * st;
+                        *reinterpret_cast<float4*>(dst + oidx) = acc;
+                        if (DOG) {
+                            const float4 pv = ring[slot][NS - 1][threadIdx.x];
+                            float4 dv;
+                            dv.x = (acc.x - pv.x) * (-1); dv.y = (acc.y - pv.y) * (-1);
+                            dv.z = (acc.z - pv.z) * (-1); dv.w = (acc.w - pv.w) * (-1);
+                            *reinterpret_cast<float4*>(dog + oidx) = dv;
+                            m = fmaxf(m, fmaxf(fmaxf(fabsf(dv.x), fabsf(dv.y)), fmaxf(fabsf(dv.z), fabsf(dv.w))));
+                        }
+                    }
+                    slot = slot == D - 1 ? 0 : slot + 1;
+                }
+            }
+        }
+        cp_async_wait<0>();
     }
     if (DOG) {
         m = warp_max(m);
@@ -336,15 +454,6 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict
 //     correlation over the ring.  Rows beyond the ends of the y line are the extended-line samples of
 //     the X-BLURRED rows (ext_il/ext_frac of the y axis), as in the reference's second sweep.
 // Requires nx % 4 == 0, (nx/4) a divisor of 128 and > HW + 1, nx and ny >= 2*HW+2.
-constexpr int kXYBufs = 4;  // shared-memory row ring of the fused X+Y pass (cp.async runs kXYBufs-1 rows ahead)
-
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 template <int HW>
 __global__ void __launch_bounds__(128, 4) blur_xy_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny,
                                                          int nz, int seg, Taps tx, Taps ty) {
@@ -453,6 +562,118 @@ __global__ void __launch_bounds__(128, 4) blur_xy_kernel(const float* __restrict
                 }
                 if (zok) *reinterpret_cast<float4*>(oplane + (size_t)p * nx + 4 * x4) = acc;
             }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+// The same pass with COMPACT CODE for the wide taps.  blur_xy_kernel inlines X() at every slot of its
+// (2*HW+1)-way unrolled ring (three bodies per slot through sample()), which at HW >= 4 is tens of
+// thousands of instructions: ncu shows the warps waiting on instruction fetch (no_instruction is the top
+// stall at HW 4/6/8).  Here the row loop is NOT unrolled: one X body, one Y body, the ring advances by
+// register moves (win[r] = win[r+1]); the wide passes are bound by the FP32 pipe (-fmad=false: an FMUL and
+// an FADD per tap, each two issue cycles per warp), so the moves ride in otherwise idle issue slots.
+// Arithmetic, operand order and the row sequence are those of blur_xy_kernel — results are bit-identical.
+template <int HW>
+__global__ void __launch_bounds__(128, 4) blur_xyc_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx, int ny,
+                                                          int nz, int seg, Taps tx, Taps ty) {
+    constexpr int PAD = (HW + 3) / 4 * 4;
+    constexpr int NV = (2 * PAD + 4) / 4;
+    constexpr int WR = 2 * HW + 1;
+    constexpr int NB = kXYBufs;
+    extern __shared__ __align__(16) float xy_sm[];
+    const int T = nx >> 2, lpc = 128 / T;
+    const int line = threadIdx.x / T, x4 = threadIdx.x - line * T;
+    const int zgroups = (nz + lpc - 1) / lpc;
+    const int s = blockIdx.x / zgroups, zg = blockIdx.x - s * zgroups;
+    const int zraw = zg * lpc + line;
+    const bool zok = zraw < nz;
+    const int z = zok ? zraw : nz - 1;
+    const int p0 = s * seg, p1 = min(ny, p0 + seg);
+    const int rowlen = nx + 2 * PAD;
+    float* const bufs = xy_sm + (size_t)line * NB * rowlen;
+    const float* const plane = src + (size_t)z * nx * ny;
+    float* const oplane = dst + (size_t)z * nx * ny;
+    const int nsamp = (p1 - 1 + HW) - (p0 - HW) + 1;
+    const int nreg = max(0, min(nsamp, (ny - 1) - (p0 - HW)));
+    const int ncalls = nreg + 2 * (nsamp - nreg);
+    auto rowof = [&](int i) -> int {
+        if (i < nreg) {
+            const int q = p0 - HW + i;
+            return q < 0 ? -q : q;
+        }
+        const int j = i - nreg;
+        return ty.ext_il[j >> 1] + (j & 1);
+    };
+    auto issue = [&](int i) {
+        if (i < ncalls) cp_async16(bufs + (i % NB) * rowlen + PAD + 4 * x4, plane + (size_t)rowof(i) * nx + 4 * x4);
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int i = 0; i < NB - 1; ++i) issue(i);
+    // right-edge blend of the x axis: per-thread constants
+    const int xe = T - 1 - x4;
+    const bool xr = xe <= HW;
+    const int xil = xr ? tx.ext_il[xe] : 0;
+    const float xfrac = xr ? tx.ext_frac[xe] : 0.0f;
+
+    float4 win[WR];
+#pragma unroll
+    for (int r = 0; r < WR; ++r) win[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int ci = 0;
+#pragma unroll 1
+    for (int i = 0; i < nsamp; ++i) {
+        const bool blend = i >= nreg;  // CTA-uniform: this sample is a blend of two X-blurred rows
+        float4 lo = make_float4(0.f, 0.f, 0.f, 0.f), xr4 = lo;
+#pragma unroll 1
+        for (int c = 0; c < (blend ? 2 : 1); ++c) {
+            float* b = bufs + (ci % NB) * rowlen;
+            cp_async_wait<NB - 2>();
+            __syncthreads();
+            issue(ci + NB - 1);
+            ++ci;
+            if (x4 >= 1 && x4 <= HW) b[PAD - x4] = b[PAD + x4];
+            if (xr) {
+                const float l = b[PAD + xil], h = b[PAD + xil + 1];
+                b[PAD + nx - 1 + xe] = (1.0f - xfrac) * l + xfrac * h;
+            }
+            __syncthreads();
+            float v[2 * PAD + 4];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const float4 f = *reinterpret_cast<const float4*>(b + 4 * x4 + 4 * q);
+                v[4 * q] = f.x; v[4 * q + 1] = f.y; v[4 * q + 2] = f.z; v[4 * q + 3] = f.w;
+            }
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int k = 0; k <= 2 * HW; ++k) acc += tx.w[k] * v[PAD + j + HW - k];
+                o[j] = acc;
+            }
+            lo = xr4;
+            xr4 = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        if (blend) {  // (lo, xr4) = rows (ext_il, ext_il + 1) of the y axis
+            const float frac = ty.ext_frac[i - nreg];
+            float4 r;
+            r.x = (1.0f - frac) * lo.x + frac * xr4.x; r.y = (1.0f - frac) * lo.y + frac * xr4.y;
+            r.z = (1.0f - frac) * lo.z + frac * xr4.z; r.w = (1.0f - frac) * lo.w + frac * xr4.w;
+            xr4 = r;
+        }
+#pragma unroll
+        for (int r = 0; r < 2 * HW; ++r) win[r] = win[r + 1];
+        win[2 * HW] = xr4;  // win[r] = extended-line sample p - HW + r of output row p = p0 + i - 2*HW
+        if (i >= 2 * HW) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k <= 2 * HW; ++k) {
+                const float4 vv = win[2 * HW - k];  // sample p + HW - k
+                const float w = ty.w[k];
+                acc.x += w * vv.x; acc.y += w * vv.y; acc.z += w * vv.z; acc.w += w * vv.w;
+            }
+            if (zok) *reinterpret_cast<float4*>(oplane + (size_t)(p0 + i - 2 * HW) * nx + 4 * x4) = acc;
         }
     }
     cp_async_wait<0>();
@@ -1067,6 +1288,78 @@ __global__ void __launch_bounds__(1024) survivors_kernel(const int* __restrict__
     for (int i = b; i < e; ++i)
         if (codes[i] == 1) surv[run++] = i;
     if (threadIdx.x == 1023) *total_out = part[1023];
+}
+
+// Launch order of the descriptor CTAs: heaviest keypoints first.  A keypoint's window volume grows with
+// the cube of its level's scale (levels 1..L: about 35k / 68k / 137k contributing voxels), and the
+// survivor list is in (octave, level, z, y, x) order, so a grid launched in list order ends on the
+// slowest CTAs with most SMs idle.  order[] = survivor indices by DESCENDING level, stable within a level
+// (one CTA, one ordered block scan per level).  Results do not depend on the order: every CTA writes its
+// own keypoint's slot.
+__global__ void __launch_bounds__(1024) desc_order_kernel(const s3d_keypoint* __restrict__ extre, const int* __restrict__ surv,
+                                                          const int* __restrict__ n_dev, int max_level, int* __restrict__ order) {
+    constexpr int NL = kMaxG;  // classes: level 1..NL-1, class 0 = anything else (goes last)
+    constexpr int CH = 16;     // levels cached per thread
+    __shared__ int wtot[32][NL];
+    __shared__ int cbase[NL];
+    const int n = *n_dev;
+    const int per = (n + 1023) / 1024;
+    const int b = min(n, (int)threadIdx.x * per), e = min(n, b + per);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    auto cls = [&](int i) -> int {
+        const int l = extre[surv[i]].level;
+        return (l >= 1 && l <= max_level && l < NL) ? l : 0;
+    };
+    unsigned char lv[CH];
+    int cnt[NL];
+#pragma unroll
+    for (int c = 0; c < NL; ++c) cnt[c] = 0;
+    for (int i = b; i < e; ++i) {
+        const int c = cls(i);
+        if (i - b < CH) lv[i - b] = (unsigned char)c;
+#pragma unroll
+        for (int k = 0; k < NL; ++k) cnt[k] += (c == k);
+    }
+    // exclusive block scan of every class count: warp shuffles, then the warp totals
+    int excl[NL];
+#pragma unroll
+    for (int c = 0; c < NL; ++c) {
+        int v = cnt[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        excl[c] = v - cnt[c];
+        if (lane == 31) wtot[wid][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NL) {  // per class: exclusive scan over the 32 warps, and the class base (descending level)
+        const int c = threadIdx.x;
+        int run = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int t = wtot[w][c];
+            wtot[w][c] = run;
+            run += t;
+        }
+        cbase[c] = run;  // total, turned into a base below
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = NL - 1; c >= 1; --c) { const int t = cbase[c]; cbase[c] = run; run += t; }
+        cbase[0] = run;
+    }
+    __syncthreads();
+    int pos[NL];
+#pragma unroll
+    for (int c = 0; c < NL; ++c) pos[c] = cbase[c] + wtot[wid][c] + excl[c];
+    for (int i = b; i < e; ++i) {
+        const int c = (i - b < CH) ? (int)lv[i - b] : cls(i);
+#pragma unroll
+        for (int k = 0; k < NL; ++k)
+            if (c == k) order[pos[k]++] = i;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 900 python -m pytest tests/test_gpu_dense.py tests/test_gpu_slab.py tests/test_gpu_sparse.py -m gpu -q -x > gpurun_out/pytest_ab.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_ab.log
+for v in "S3D_ZVAR=0" "S3D_ZVAR=1"; do
+  env $v timeout 300 python scripts/ab_step.py 512 4 2>&1 | tail -1
+done | tee gpurun_out/ab3.log
