@@ -897,7 +897,7 @@ static int stage_sparse(s3d_ctx* c) {
         }
         ProfScope ps(&c->prof, K_ORIENT_EXACT, 0.0);
         if (c->prm.exact_recheck)
-            S3D_LAUNCH(orient_exact_kernel, (unsigned)std::min<size_t>(s3d_blocks((size_t)ne, kExactWarps), 148 * 16),
+            S3D_LAUNCH(orient_exact_kernel, (unsigned)std::min<size_t>((size_t)ne, 148 * 6),
                        kExactWarps * 32, 0, st, d_cand, tab, c->d_extre, c->d_codes, d_recheck, d_total + 1,
                        c->prm.max_eig_thres, c->prm.corner_thresh, d_total + 2);
     }

@@ -1189,21 +1189,27 @@ __device__ __forceinline__ bool orient_terms(const float* __restrict__ g, ll i, 
 // nine addends of up to 32 consecutive voxels in parallel and park them, rank-compacted, in a
 // per-warp shared-memory tile; lane k < 9 then adds column k IN ORDER — the serial sum of
 // component k, bit for bit, at one LDS + FADD per voxel for all nine components together.
-constexpr int kExactWarps = 2;
+// One CTA per re-checked detection: warps 1..7 PRODUCE the nine addends of consecutive window positions
+// (the reference's z, y, x order, linearised) into a double-buffered shared-memory chunk while warp 0
+// CONSUMES the previous chunk — lane k < 9 adds component k's values one by one, which is the reference's
+// serial FP32 summation (Src/cSIFT3D.cc:957-1010).  Positions outside the sphere contribute +0.0f, which
+// leaves a running sum that started at +0.0f unchanged bit for bit (x + 0 == x; the sum can never be -0).
+// The first version gave a whole window to one warp, which waited a full L2 round trip per row before
+// its 24 dependent adds: 0.40 ms for the slowest detection, whatever the GPU's width.
+constexpr int kExactWarps = 8;
+constexpr int kExactChunk = 512;  // window positions per chunk
 __global__ void __launch_bounds__(kExactWarps * 32) orient_exact_kernel(const Cand* __restrict__ cand, LevelTable tab,
                                                                         s3d_keypoint* __restrict__ out,
                                                                         int* __restrict__ codes,
                                                                         const int* __restrict__ recheck_list,
                                                                         const int* __restrict__ n_recheck, float max_eig,
                                                                         float corner, int* n_flipped) {
-    __shared__ float tile[kExactWarps][9][33];
+    __shared__ float buf[2][9][kExactChunk];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
     const int nre = *n_recheck;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const int row9 = lane < 9 ? lane : 0;
-    float(*tl)[33] = tile[wid];
-    for (int ri = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ri < nre; ri += warps_per_grid) {
+    constexpr int NP = (kExactWarps - 1) * 32;  // producer threads
+    for (int ri = blockIdx.x; ri < nre; ri += gridDim.x) {
         const int ci = recheck_list[ri];
         int o, lvl, x, y, z;
         cand_decode(cand[ci], tab, o, lvl, x, y, z);
@@ -1224,46 +1230,57 @@ __global__ void __launch_bounds__(kExactWarps * 32) orient_exact_kernel(const Ca
         window_bounds(kp.y, win_radius / u, ny, y0, y1);
         window_bounds(kp.z, win_radius / u, nz, z0, z1);
         const ll ys = nx, zs = (ll)nx * ny;
-        float acc = 0.0f;  // lane k < 9 owns component k
-        for (int zz = z0; zz <= z1; ++zz)
-            for (int yy = y0; yy <= y1; ++yy) {
-                const float dy = ((float)yy - kp.y) * u, dz = ((float)zz - kp.z) * u;
-                for (int xb = xs; xb <= xe; xb += 32) {
-                    const int xx = xb + lane;
-                    float tm[9];
-                    bool in = false;
-                    if (xx <= xe)
-                        in = orient_terms(g, (ll)xx + (ll)yy * ys + (ll)zz * zs, ys, zs, ((float)xx - kp.x) * u, dy, dz, iu,
-                                          inv_u2, wt, r2, tm);
-                    const unsigned m = __ballot_sync(0xffffffffu, in);
-                    if (in) {
-                        const int col = __popc(m & lt_mask);
+        const int ncol = max(0, xe - xs + 1), nrow = max(0, y1 - y0 + 1), nsl = max(0, z1 - z0 + 1);
+        const int npos = ncol * nrow * nsl;
+        const int nchunk = (npos + kExactChunk - 1) / kExactChunk;
+        float acc = 0.0f;  // warp 0, lane k < 9: component k
+        for (int c = 0; c <= nchunk; ++c) {
+            if (wid > 0) {
+                if (c < nchunk) {
+                    float(*bw)[kExactChunk] = buf[c & 1];
+                    for (int t = (int)threadIdx.x - 32; t < kExactChunk; t += NP) {
+                        const int idx = c * kExactChunk + t;
+                        float tm[9];
+                        bool in = false;
+                        if (idx < npos) {
+                            const int rowi = idx / ncol;
+                            const int xx = xs + (idx - rowi * ncol);
+                            const int sl = rowi / nrow;
+                            const int yy = y0 + (rowi - sl * nrow), zz = z0 + sl;
+                            in = orient_terms(g, (ll)xx + (ll)yy * ys + (ll)zz * zs, ys, zs, ((float)xx - kp.x) * u,
+                                              ((float)yy - kp.y) * u, ((float)zz - kp.z) * u, iu, inv_u2, wt, r2, tm);
+                        }
 #pragma unroll
-                        for (int k = 0; k < 9; ++k) tl[k][col] = tm[k];
+                        for (int k = 0; k < 9; ++k) bw[k][t] = in ? tm[k] : 0.0f;
                     }
-                    __syncwarp();
-                    const int cnt = __popc(m);
-                    int j = 0;
-                    for (; j + 4 <= cnt; j += 4) {
-                        const float a0 = tl[row9][j], a1 = tl[row9][j + 1], a2 = tl[row9][j + 2], a3 = tl[row9][j + 3];
-                        acc += a0; acc += a1; acc += a2; acc += a3;
-                    }
-                    for (; j < cnt; ++j) acc += tl[row9][j];
-                    __syncwarp();
                 }
+            } else if (c > 0) {
+                const float* br = buf[(c - 1) & 1][row9];
+                const int cnt = min(kExactChunk, npos - (c - 1) * kExactChunk);
+                int j = 0;
+                for (; j + 8 <= cnt; j += 8) {
+                    const float4 a = *reinterpret_cast<const float4*>(br + j), b = *reinterpret_cast<const float4*>(br + j + 4);
+                    acc += a.x; acc += a.y; acc += a.z; acc += a.w;
+                    acc += b.x; acc += b.y; acc += b.z; acc += b.w;
+                }
+                for (; j < cnt; ++j) acc += br[j];
             }
-        OrientSums S;
-        S.t00 = __shfl_sync(0xffffffffu, acc, 0); S.t01 = __shfl_sync(0xffffffffu, acc, 1);
-        S.t02 = __shfl_sync(0xffffffffu, acc, 2); S.t11 = __shfl_sync(0xffffffffu, acc, 3);
-        S.t12 = __shfl_sync(0xffffffffu, acc, 4); S.t22 = __shfl_sync(0xffffffffu, acc, 5);
-        S.wx = __shfl_sync(0xffffffffu, acc, 6); S.wy = __shfl_sync(0xffffffffu, acc, 7);
-        S.wz = __shfl_sync(0xffffffffu, acc, 8);
-        const int code = orient_finish(S, kp, max_eig, corner, nullptr);
-        if (lane == 0) {
-            if (code < 1) kp.x = kp.y = kp.z = -1.0f;
-            if (code != codes[ci]) atomicAdd(n_flipped, 1);
-            out[ci] = kp;
-            codes[ci] = code;
+            __syncthreads();
+        }
+        if (wid == 0) {
+            OrientSums S;
+            S.t00 = __shfl_sync(0xffffffffu, acc, 0); S.t01 = __shfl_sync(0xffffffffu, acc, 1);
+            S.t02 = __shfl_sync(0xffffffffu, acc, 2); S.t11 = __shfl_sync(0xffffffffu, acc, 3);
+            S.t12 = __shfl_sync(0xffffffffu, acc, 4); S.t22 = __shfl_sync(0xffffffffu, acc, 5);
+            S.wx = __shfl_sync(0xffffffffu, acc, 6); S.wy = __shfl_sync(0xffffffffu, acc, 7);
+            S.wz = __shfl_sync(0xffffffffu, acc, 8);
+            const int code = orient_finish(S, kp, max_eig, corner, nullptr);
+            if (lane == 0) {
+                if (code < 1) kp.x = kp.y = kp.z = -1.0f;
+                if (code != codes[ci]) atomicAdd(n_flipped, 1);
+                out[ci] = kp;
+                codes[ci] = code;
+            }
         }
     }
 }
@@ -1482,6 +1499,7 @@ static_assert(kQCopyStride >= kHistStride && kQCopyStride % 32 == 4, "copy strid
 struct DescSmemQ {
     uint32_t hist[kQCopies * kQCopyStride];
     uint32_t queue[kDescWarps][64];
+    uint4 queue2[kDescWarps][64];  // second-stage ring: (packed offsets, rotated gradient) of voxels above the |grad|^2 floor
     MeshConst M;
     s3d_keypoint kp;
     float red[kDescWarps + 1];
@@ -1668,35 +1686,7 @@ __global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const
                 }
             }
         }
-        if constexpr (Q) {
-            if (contrib) {
-                // Trilinear_interpolation_over_desc_debug :1466-1522, contributions in fixed point
-                const float msq = mag * qscale;
-                q_over |= msq > kQCap;
-                const int ib0 = (int)vb0, ib1 = (int)vb1, ib2 = (int)vb2;  // truncation, Q12
-                const float dv0 = vb0 - floorf(vb0), dv1 = vb1 - floorf(vb1), dv2 = vb2 - floorf(vb2);
-                const float wx[2] = {1.0f - dv0, dv0}, wy[2] = {1.0f - dv1, dv1}, wz[2] = {1.0f - dv2, dv2};
-                const bool okx[2] = {ib0 >= 0 && ib0 <= 3, ib0 >= -1 && ib0 <= 2};
-                const bool oky[2] = {ib1 >= 0 && ib1 <= 3, ib1 >= -1 && ib1 <= 2};
-                const bool okz[2] = {ib2 >= 0 && ib2 <= 3, ib2 >= -1 && ib2 <= 2};
-                const int ax[2] = {ib0 * 12, ib0 * 12 + 12}, ay[2] = {ib1 * 48, ib1 * 48 + 48}, az[2] = {ib2 * kHistZ, ib2 * kHistZ + kHistZ};
-                const int i0 = M.idx[face][0], i1 = M.idx[face][1], i2 = M.idx[face][2];
-                const float qb0 = msq * b[0], qb1 = msq * b[1], qb2 = msq * b[2];
-                uint32_t* hq = S.hist + (lane & (kQCopies - 1)) * kQCopyStride;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int ddx = (c >> 2) & 1, ddy = (c >> 1) & 1, ddz = c & 1;
-                    if (okx[ddx] && oky[ddy] && okz[ddz]) {
-                        const float wt = wx[ddx] * wy[ddy] * wz[ddz];
-                        const int base = ax[ddx] + ay[ddy] + az[ddz];
-                        // round-to-nearest via the 2^23 trick (values are < 2^23): full-rate FFMA + IADD instead of F2I
-                        atomicAdd(&hq[base + i0], __float_as_uint(__fmaf_rn(wt, qb0, 8388608.0f)) - 0x4B000000u);
-                        atomicAdd(&hq[base + i1], __float_as_uint(__fmaf_rn(wt, qb1, 8388608.0f)) - 0x4B000000u);
-                        atomicAdd(&hq[base + i2], __float_as_uint(__fmaf_rn(wt, qb2, 8388608.0f)) - 0x4B000000u);
-                    }
-                }
-            }
-        } else {
+        if constexpr (!Q) {
         float* myh = S.hist[wid];
         uint2(*stg)[kStageCols] = S.stage[wid];
         const unsigned mc = __ballot_sync(0xffffffffu, contrib);
@@ -1747,6 +1737,93 @@ __global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const
                 __syncwarp();
             }
         }
+        }
+    };
+
+    // ---- Q: two compaction stages.  Stage A (full warps of voxels that passed the inclusion tests): window
+    // weight, gradient, rotation into the keypoint frame, the reference's |grad|^2 floor (:1544).  On smooth data a
+    // large share of the voxels stops here (ncu on the 512^3 benchmark volume: 18 of 32 lanes were active in
+    // everything downstream), so survivors are queued a second time and stage B — face search, barycentric
+    // split, the 24 fixed-point atomics — again runs on full warps.  Per-voxel arithmetic is unchanged and
+    // integer adds commute, so the descriptors are bit-identical to the single-stage kernel's.
+    int q2head = 0, q2n = 0;  // warp-uniform ring state of the second stage
+    auto stage_b = [&](uint4 ent, bool valid) {
+        if constexpr (Q) {
+            if (!valid) return;
+            const uint32_t packed = ent.x;
+            const float rx = __uint_as_float(ent.y), ry = __uint_as_float(ent.z), rz = __uint_as_float(ent.w);
+            const int xx = xs + (int)(packed & 1023u), yy = y0 + (int)((packed >> 10) & 1023u), zz = z0 + (int)(packed >> 20);
+            const float dx = ((float)xx - cx) * u, dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
+            // cell split only (no inclusion decision here): fused form
+            const float vb0 = __fmaf_rn(Rf0, dx, __fmaf_rn(Rf1, dy, __fmaf_rn(Rf2, dz, hwf)));
+            const float vb1 = __fmaf_rn(Rf3, dx, __fmaf_rn(Rf4, dy, __fmaf_rn(Rf5, dz, hwf)));
+            const float vb2 = __fmaf_rn(Rf6, dx, __fmaf_rn(Rf7, dy, __fmaf_rn(Rf8, dz, hwf)));
+            float b[3] = {0.f, 0.f, 0.f};
+            const int face = find_face(M, rx, ry, rz, bary_eps, b[0], b[1], b[2]);
+            if (face < 0) return;
+            const float n2 = rx * rx + ry * ry + rz * rz;  // the expression stage A tested
+            const float mag = sqrtf(n2);
+            // Trilinear_interpolation_over_desc_debug :1466-1522, contributions in fixed point
+            const float msq = mag * qscale;
+            q_over |= msq > kQCap;
+            const int ib0 = (int)vb0, ib1 = (int)vb1, ib2 = (int)vb2;  // truncation, Q12
+            const float dv0 = vb0 - floorf(vb0), dv1 = vb1 - floorf(vb1), dv2 = vb2 - floorf(vb2);
+            const float wx[2] = {1.0f - dv0, dv0}, wy[2] = {1.0f - dv1, dv1}, wz[2] = {1.0f - dv2, dv2};
+            const bool okx[2] = {ib0 >= 0 && ib0 <= 3, ib0 >= -1 && ib0 <= 2};
+            const bool oky[2] = {ib1 >= 0 && ib1 <= 3, ib1 >= -1 && ib1 <= 2};
+            const bool okz[2] = {ib2 >= 0 && ib2 <= 3, ib2 >= -1 && ib2 <= 2};
+            const int ax[2] = {ib0 * 12, ib0 * 12 + 12}, ay[2] = {ib1 * 48, ib1 * 48 + 48}, az[2] = {ib2 * kHistZ, ib2 * kHistZ + kHistZ};
+            const int i0 = M.idx[face][0], i1 = M.idx[face][1], i2 = M.idx[face][2];
+            const float qb0 = msq * b[0], qb1 = msq * b[1], qb2 = msq * b[2];
+            uint32_t* hq = S.hist + (lane & (kQCopies - 1)) * kQCopyStride;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int ddx = (c >> 2) & 1, ddy = (c >> 1) & 1, ddz = c & 1;
+                if (okx[ddx] && oky[ddy] && okz[ddz]) {
+                    const float wt = wx[ddx] * wy[ddy] * wz[ddz];
+                    const int base = ax[ddx] + ay[ddy] + az[ddz];
+                    // round-to-nearest via the 2^23 trick (values are < 2^23): full-rate FFMA + IADD instead of F2I
+                    atomicAdd(&hq[base + i0], __float_as_uint(__fmaf_rn(wt, qb0, 8388608.0f)) - 0x4B000000u);
+                    atomicAdd(&hq[base + i1], __float_as_uint(__fmaf_rn(wt, qb1, 8388608.0f)) - 0x4B000000u);
+                    atomicAdd(&hq[base + i2], __float_as_uint(__fmaf_rn(wt, qb2, 8388608.0f)) - 0x4B000000u);
+                }
+            }
+        }
+    };
+    auto stage_a = [&](uint32_t packed, bool valid) {
+        if constexpr (Q) {
+            uint4* que2 = S.queue2[wid];
+            bool pass = false;
+            float rx = 0.f, ry = 0.f, rz = 0.f;
+            if (valid) {
+                const int xx = xs + (int)(packed & 1023u), yy = y0 + (int)((packed >> 10) & 1023u), zz = z0 + (int)(packed >> 20);
+                const float dx = ((float)xx - cx) * u, dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
+                const float sq = dx * dx + dy * dy + dz * dz;
+                const int mi = (int)(sq * inv_u2);  // sq = u*u*m exactly, see wtab_kernel
+                const float weight = wt_s ? S.wt[mi] : wt_g[mi];  // == expf(-0.5f * sq / s2), :1312
+                const ll i = (ll)xx + (ll)yy * ys + (ll)zz * zs;
+                float gx = 0.5f * (g[i + 1] - g[i - 1]);  // == (float)(0.5 * (double)(a - b))
+                float gy = 0.5f * (g[i + ys] - g[i - ys]);
+                float gz = 0.5f * (g[i + zs] - g[i - zs]);
+                gx *= iu; gy *= iu; gz *= iu;
+                gx = gx * weight; gy = gy * weight; gz = gz * weight;  // SIFT3D_CVEC_SCALE :1322
+                rx = R0 * gx + R1 * gy + R2 * gz;
+                ry = R3 * gx + R4 * gy + R5 * gz;
+                rz = R6 * gx + R7 * gy + R8 * gz;
+                const float n2 = rx * rx + ry * ry + rz * rz;  // exact form: input of the reference's |grad|^2 floor
+                pass = !(n2 < bary_eps);  // Check_intersect_faces :1544
+            }
+            const unsigned mp = __ballot_sync(0xffffffffu, pass);
+            if (pass)
+                que2[(q2head + q2n + __popc(mp & lt_mask)) & 63] =
+                    make_uint4(packed, __float_as_uint(rx), __float_as_uint(ry), __float_as_uint(rz));
+            q2n += __popc(mp);
+            __syncwarp();
+            if (q2n >= 32) {
+                stage_b(que2[(q2head + lane) & 63], true);
+                q2head = (q2head + 32) & 63;
+                q2n -= 32;
+            }
         }
     };
 
@@ -1816,13 +1893,19 @@ __global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const
             qn += __popc(mp);
             __syncwarp();
             if (qn >= 32) {
-                heavy(que[(qhead + lane) & 63], true);
+                if constexpr (Q) stage_a(que[(qhead + lane) & 63], true);
+                else heavy(que[(qhead + lane) & 63], true);
                 qhead = (qhead + 32) & 63;
                 qn -= 32;
             }
         }
     }
-    if (qn > 0) heavy(que[(qhead + lane) & 63], lane < qn);
+    if constexpr (Q) {
+        if (qn > 0) stage_a(que[(qhead + lane) & 63], lane < qn);
+        if (q2n > 0) stage_b(S.queue2[wid][(q2head + lane) & 63], lane < q2n);
+    } else {
+        if (qn > 0) heavy(que[(qhead + lane) & 63], lane < qn);
+    }
     if constexpr (Q) {
         if (q_over) S.overflow = 1;
     }
