@@ -739,6 +739,28 @@ __global__ void __launch_bounds__(256) detect_kernel(const float* __restrict__ D
         for (int q = 0; q < 4; ++q)
             above |= ((fabsf(f[q].x) > thres ? 1u : 0u) | (fabsf(f[q].y) > thres ? 2u : 0u) | (fabsf(f[q].z) > thres ? 4u : 0u) |
                       (fabsf(f[q].w) > thres ? 8u : 0u)) << (4 * q);
+        // Pre-filter in registers: an extremum is in particular a strict extremum against its two x
+        // neighbours, which sit in the same float4 or in the adjacent lane's (flat index +-1; voxels on a
+        // row end are rejected by the interior test below whatever this says).  Elements whose neighbour
+        // lies outside the warp's 512 voxels stay candidates.  This drops most above-threshold voxels
+        // before the divergent per-voxel loop of phase 2.
+        if (__any_sync(0xffffffffu, above != 0)) {
+            unsigned keep = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float lw = __shfl_up_sync(0xffffffffu, f[q].w, 1), rx = __shfl_down_sync(0xffffffffu, f[q].x, 1);
+                const float pl = __shfl_sync(0xffffffffu, f[q > 0 ? q - 1 : 0].w, 31), nr = __shfl_sync(0xffffffffu, f[q < 3 ? q + 1 : 3].x, 0);
+                const bool hasl = lane > 0 || q > 0, hasr = lane < 31 || q < 3;
+                const float left = lane == 0 ? pl : lw, right = lane == 31 ? nr : rx;
+                auto ext = [](float v, float a, float b) { return (v < a && v < b) || (v > a && v > b); };
+                const unsigned e0 = (!hasl || ext(f[q].x, left, f[q].y)) ? 1u : 0u;
+                const unsigned e1 = ext(f[q].y, f[q].x, f[q].z) ? 2u : 0u;
+                const unsigned e2 = ext(f[q].z, f[q].y, f[q].w) ? 4u : 0u;
+                const unsigned e3 = (!hasr || ext(f[q].w, f[q].z, right)) ? 8u : 0u;
+                keep |= (e0 | e1 | e2 | e3) << (4 * q);
+            }
+            above &= keep;
+        }
     } else {
 #pragma unroll
         for (int b = 0; b < kDetectPer; ++b) {
@@ -828,27 +850,56 @@ __global__ void __launch_bounds__(256) detect_kernel(const float* __restrict__ D
     }
 }
 
-// Exclusive scan of n ints by ONE CTA (1024 threads); total -> *total_out.
+// Exclusive scan of n ints by ONE CTA (1024 threads); total -> *total_out.  Each warp owns a contiguous
+// range and walks it with coalesced loads (lane-contiguous, 4 x 32 entries in flight per step): the first
+// version gave every THREAD a contiguous range, i.e. 32 different cache lines per warp load (111 us for the
+// 112k per-CTA counts of a 512^3 detection).
 __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int* __restrict__ out, int n, int* total_out) {
-    __shared__ int part[1024];
-    const int per = (n + 1023) / 1024;
-    const int b = threadIdx.x * per, e = min(n, b + per);
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int per = (((n + 31) / 32) + 127) / 128 * 128;  // entries per warp, a multiple of 128
+    const int b = min(n, wid * per), e = min(n, b + per);
     int s = 0;
-    for (int i = b; i < e; ++i) s += in[i];
-    part[threadIdx.x] = s;
+    for (int i = b + lane; i < e; i += 128) {
+        const int v0 = in[i], v1 = i + 32 < e ? in[i + 32] : 0, v2 = i + 64 < e ? in[i + 64] : 0, v3 = i + 96 < e ? in[i + 96] : 0;
+        s += (v0 + v1) + (v2 + v3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) wsum[wid] = s;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    int carry = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 32; ++w) {
+        const int t = wsum[w];
+        if (w < wid) carry += t;
+        tot += t;
     }
-    int run = part[threadIdx.x] - s;
-    for (int i = b; i < e; ++i) {
-        out[i] = run;
-        run += in[i];
+    for (int i0 = b; i0 < e; i0 += 128) {
+        int v[4], inc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * 32 + lane;
+            v[q] = i < e ? in[i] : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int x = v[q];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += t;
+            }
+            inc[q] = x;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = i0 + q * 32 + lane;
+            if (i < e) out[i] = carry + inc[q] - v[q];
+            carry += __shfl_sync(0xffffffffu, inc[q], 31);
+        }
     }
-    if (threadIdx.x == 1023 && total_out) *total_out = part[1023];
+    if (threadIdx.x == 0 && total_out) *total_out = tot;
 }
 
 struct Cand {
@@ -1828,38 +1879,62 @@ __global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const
     };
 
     int qhead = 0, qn = 0;  // warp-uniform ring state
-    int py = wid % (wyp > 0 ? wyp : 1), pz = wid / (wyp > 0 ? wyp : 1);  // row-pair cursor (no division in the loop)
-    for (int rp = wid; rp < npairs; rp += kDescWarps) {
-        const int yy = y0 + 2 * py + half, zz = z0 + pz;
-        py += kDescWarps;
-        while (py >= wyp) { py -= wyp; ++pz; }
-        const float dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
-        // fl(fl(dx^2+dy^2)+dz^2) >= fl(dy^2+dz^2) by monotonicity of rounding: safe row reject
-        const float dyz2 = dy * dy + dz * dz;
-        int xlo = 1, xhi = 0;  // empty
-        if (yy <= y1 && !(dyz2 > r2)) {
-            float lo = -(sqrtf(r2 - dyz2) * iu), hi = -lo;  // sphere chord, in voxels about cx
-            bool empty = false;
-            const float c0 = R1 * dy + R2 * dz, c1 = R4 * dy + R5 * dz, c2 = R7 * dy + R8 * dz;
+    // Row pairs rp = wid, wid + kDescWarps, ... belong to this warp; pair t's rows go to the two half-warps.
+    // The per-row set-up (sphere chord, clip against the rotated grid, row constants: ~160 instructions) is
+    // done LANE-PARALLEL for 16 pairs at a time — lane L prepares row (L & 1) of pair t0 + (L >> 1) — and
+    // handed to the half-warps by shuffles; the first version had all 32 lanes repeat it for their 2 rows
+    // (16 % of the kernel's instructions).  Row order, hence queue order, is unchanged.
+    const int nmy = npairs > wid ? (npairs - wid + kDescWarps - 1) / kDescWarps : 0;
+    for (int t0 = 0; t0 < nmy; t0 += 16) {
+        int xlo_l = 1, xhi_l = 0;  // empty
+        uint32_t pyz_l = 0;
+        float dyz2_l = 0.0f, rb0_l = 0.0f, rb1_l = 0.0f, rb2_l = 0.0f;
+        {
+            const int t = t0 + (lane >> 1);
+            if (t < nmy) {
+                const int rp = wid + t * kDescWarps;
+                const int pz = rp / wyp, py = rp - pz * wyp;
+                const int yy = y0 + 2 * py + (lane & 1), zz = z0 + pz;
+                const float dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;
+                // fl(fl(dx^2+dy^2)+dz^2) >= fl(dy^2+dz^2) by monotonicity of rounding: safe row reject
+                const float dyz2 = dy * dy + dz * dz;
+                if (yy <= y1 && !(dyz2 > r2)) {
+                    float lo = -(sqrtf(r2 - dyz2) * iu), hi = -lo;  // sphere chord, in voxels about cx
+                    bool empty = false;
+                    const float c0 = R1 * dy + R2 * dz, c1 = R4 * dy + R5 * dz, c2 = R7 * dy + R8 * dz;
 #define S3D_CLIP(fk, ck, iak)                                                    \
-            if (fk) {                                                            \
-                const float t0 = (-slab - ck) * iak, t1 = (slab - ck) * iak;     \
-                lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));    \
-            } else if (fabsf(ck) > slab) empty = true;
-            S3D_CLIP(f0, c0, ia0) S3D_CLIP(f1, c1, ia1) S3D_CLIP(f2, c2, ia2)
+                    if (fk) {                                                            \
+                        const float t0c = (-slab - ck) * iak, t1c = (slab - ck) * iak;   \
+                        lo = fmaxf(lo, fminf(t0c, t1c)); hi = fminf(hi, fmaxf(t0c, t1c)); \
+                    } else if (fabsf(ck) > slab) empty = true;
+                    S3D_CLIP(f0, c0, ia0) S3D_CLIP(f1, c1, ia1) S3D_CLIP(f2, c2, ia2)
 #undef S3D_CLIP
-            if (!empty && !(lo > hi + 2.0f)) {
-                xlo = max(xs, (int)floorf(cx + lo) - 1);
-                xhi = min(xe, (int)ceilf(cx + hi) + 1);
+                    if (!empty && !(lo > hi + 2.0f)) {
+                        xlo_l = max(xs, (int)floorf(cx + lo) - 1);
+                        xhi_l = min(xe, (int)ceilf(cx + hi) + 1);
+                    }
+                }
+                pyz_l = ((uint32_t)(yy - y0) << 10) | ((uint32_t)(zz - z0) << 20);
+                dyz2_l = dyz2;
+                // row constants of the fused grid coordinates (Q)
+                rb0_l = __fmaf_rn(Rf1, dy, __fmaf_rn(Rf2, dz, hwf));
+                rb1_l = __fmaf_rn(Rf4, dy, __fmaf_rn(Rf5, dz, hwf));
+                rb2_l = __fmaf_rn(Rf7, dy, __fmaf_rn(Rf8, dz, hwf));
             }
         }
+        const int nb = min(16, nmy - t0);
+        for (int j = 0; j < nb; ++j) {
+        const int srcl = 2 * j + half;
+        const int xlo = __shfl_sync(0xffffffffu, xlo_l, srcl), xhi = __shfl_sync(0xffffffffu, xhi_l, srcl);
+        const uint32_t pyz = __shfl_sync(0xffffffffu, pyz_l, srcl);
+        const float dyz2 = __shfl_sync(0xffffffffu, dyz2_l, srcl);
+        const float rb0 = __shfl_sync(0xffffffffu, rb0_l, srcl), rb1 = __shfl_sync(0xffffffffu, rb1_l, srcl),
+                    rb2 = __shfl_sync(0xffffffffu, rb2_l, srcl);
         const int len = xhi - xlo + 1;
         const int len_other = __shfl_xor_sync(0xffffffffu, len, 16);
         const int iters = (max(len, len_other) + 15) >> 4;
-        const uint32_t pyz = ((uint32_t)(yy - y0) << 10) | ((uint32_t)(zz - z0) << 20);
-        // row constants of the fused grid coordinates (Q)
-        const float rb0 = __fmaf_rn(Rf1, dy, __fmaf_rn(Rf2, dz, hwf)), rb1 = __fmaf_rn(Rf4, dy, __fmaf_rn(Rf5, dz, hwf)),
-                    rb2 = __fmaf_rn(Rf7, dy, __fmaf_rn(Rf8, dz, hwf));
+        const int yy = y0 + (int)((pyz >> 10) & 1023u), zz = z0 + (int)(pyz >> 20);
+        const float dy = ((float)yy - cy) * u, dz = ((float)zz - cz) * u;  // exact_pass / FP32 variant
         for (int it = 0; it < iters; ++it) {
             const int xx = xlo + it * 16 + hl;
             bool pass = false;
@@ -1898,6 +1973,7 @@ __global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const
                 qhead = (qhead + 32) & 63;
                 qn -= 32;
             }
+        }
         }
     }
     if constexpr (Q) {
