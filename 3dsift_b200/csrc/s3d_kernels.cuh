@@ -1153,6 +1153,8 @@ __device__ __forceinline__ void kp_init(s3d_keypoint& kp, int o, int lvl, int x,
 //     The FP32 summation order differs from the reference's serial z,y,x order; detections whose
 //     tests land within `recheck_margin` of a threshold are appended to recheck_list for the exact
 //     serial re-evaluation kernel below.
+// (measured: 3 CTAs/SM without spills, with one or two window voxels per lane in flight, is 16-20 % slower
+// than these 4 CTAs/SM with a few spilled words — occupancy hides the L2 latency better)
 __global__ void __launch_bounds__(256, 4) orient_kernel(const Cand* __restrict__ cand, int ncand, LevelTable tab,
                                                      s3d_keypoint* __restrict__ out, int* __restrict__ codes,
                                                      int* __restrict__ xyz5, float max_eig, float corner,
@@ -1235,11 +1237,7 @@ __device__ __forceinline__ bool orient_terms(const float* __restrict__ g, ll i, 
 
 // Exact re-evaluation of the flagged detections in the reference's own summation order
 // (z, y, x serial FP32 accumulation, Src/cSIFT3D.cc:958-998), so near-threshold accept/reject
-// decisions follow the reference's rounding instead of the warp-parallel tree's.  One warp per
-// flagged detection (the list orient_kernel compacted): for each window row the lanes compute the
-// nine addends of up to 32 consecutive voxels in parallel and park them, rank-compacted, in a
-// per-warp shared-memory tile; lane k < 9 then adds column k IN ORDER — the serial sum of
-// component k, bit for bit, at one LDS + FADD per voxel for all nine components together.
+// decisions follow the reference's rounding instead of the warp-parallel tree's.
 // One CTA per re-checked detection: warps 1..7 PRODUCE the nine addends of consecutive window positions
 // (the reference's z, y, x order, linearised) into a double-buffered shared-memory chunk while warp 0
 // CONSUMES the previous chunk — lane k < 9 adds component k's values one by one, which is the reference's

@@ -40,7 +40,7 @@ UNIT = "Mvoxels/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=512, help="cube edge of the synthetic volume")
@@ -141,7 +141,7 @@ def run_reference(a):
     if rank != 0:
         return
     # bounded: the whole --steps/--warmup run must end within a few minutes on the host cores
-    steps, warmup = max(1, min(a.steps, 3)), min(a.warmup, 1)
+    steps, warmup = max(1, min(a.steps, 20)), min(a.warmup, 3)
     val, sec, kind, threads, nk = time_reference(a.cpu_sample, steps, warmup)
     model, ncpu = cpu_info()
     sample = (f"V-blobs {a.cpu_sample}^3 (same generator as the {a.size}^3 workload), CreateCSIFT3D+KpSiftAlgorithm, "
@@ -389,6 +389,12 @@ def main():
                             "volume is slower than one extraction the leg is bound by the host link (h2d_ms)"},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "dominant_by_time": ({"kernel": "describe", "ms_per_step": kernels["describe"]["ms_per_step"],
+                                  "share_of_step": kernels["describe"]["ms_per_step"] / ms_value,
+                                  "bound": "issue rate (not HBM: ncu dram throughput 1.5 %, issue slots 82 % busy; "
+                                           "profiles/r01_ncu_describe_*.txt)",
+                                  "keypoints_per_s": nkp / (kernels["describe"]["ms_per_step"] * 1e-3)}
+                                 if "describe" in kernels and kernels["describe"]["ms_per_step"] > 0 else None),
             "dense_pipeline": {"alg_bytes": b_dense, "ms": dense_ms,
                                "frac_hbm": (b_dense / (dense_ms * 1e-3) / 1e9 / hbm_peak) if dense_ms > 0 else None,
                                "note": "B_dense = 105 bytes/voxel (SURVEY.md §8d) over the summed time of the dense kernels"},
@@ -405,10 +411,10 @@ def main():
                                  "note": "achieved = 2*768*(rows searched forward + reverse) / whole enhancedMatch time (candidate "
                                          "kernel + re-rank + filters); ncu tensor-pipe utilisation of the candidate kernel is in profiles/"}
         if world == 1 and not a.no_cpu_baseline:
-            val, sec, kind, threads, nk = time_reference(a.cpu_sample, 2, 0)
+            val, sec, kind, threads, nk = time_reference(a.cpu_sample, 6, 1)
             model, _ = cpu_info()
             out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "cpu": model,
-                                   "sample": f"V-blobs {a.cpu_sample}^3, 2 volumes, CreateCSIFT3D+KpSiftAlgorithm "
+                                   "sample": f"V-blobs {a.cpu_sample}^3, 6 timed + 1 warm-up volumes, CreateCSIFT3D+KpSiftAlgorithm "
                                              f"({sec:.2f} s each, {nk} keypoints); the 512^3 run would take minutes"}
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -12,20 +12,25 @@ def to_bytes(v, u):
     v = float(v.replace(",", ""))
     return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
 agg = {}
+prev = ""
 for r in rows[2:]:
     name = r[ix["Kernel Name"]]
-    if "blur_march_kernel" in name:
-        cls = "blur_z_dog" if ", 1>" in name or ",1>" in name or "(bool)1" in name else "blur_y"
-    elif "blur_xy_kernel" in name:
+    # a level is blurred as (fused XY | X, Y) then Z: a march that follows blur_x_kernel is the Y pass, any other the Z pass
+    # (bench.py's class blur_z_dog holds every Z pass, with or without the fused DoG)
+    if "blur_march" in name:
+        cls = "blur_y" if prev == "blur_x" else "blur_z_dog"
+    elif "blur_xy" in name:
         cls = "blur_xy"
     elif "blur_x_kernel" in name:
         cls = "blur_x"
     else:
         continue
+    prev = cls
     b = to_bytes(r[ix["dram__bytes_read.sum"]], units[ix["dram__bytes_read.sum"]]) + to_bytes(r[ix["dram__bytes_write.sum"]], units[ix["dram__bytes_write.sum"]])
     a = agg.setdefault(cls, [0, 0.0])
     a[0] += 1; a[1] += b
 out = {k: {"launches": n, "dram_bytes_per_launch": tot / n, "dram_bytes_per_step": tot,
            "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, all launches of one 512^3 extraction ({os.path.basename(rep)})"} for k, (n, tot) in agg.items()}
-json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json"), "w"), indent=1)
+dst = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+json.dump(out, open(dst, "w"), indent=1)
 print(json.dumps(out, indent=1))
