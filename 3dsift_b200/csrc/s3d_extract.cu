@@ -246,7 +246,8 @@ static void launch_x(const float* src, float* dst, int nx, ll nrows, const Taps&
 
 static int pick_seg(int nx4, int n_other, int n) {
     // longest segment that still yields >= ~256k threads, so small octaves keep the GPU busy
-    int seg = 64;
+    static const int seg_env = [] { const char* e = getenv("S3D_MARCH_SEG"); return e ? atoi(e) : 0; }();  // experiments
+    int seg = seg_env > 0 ? seg_env : 64;
     while (seg > 8 && (ll)nx4 * n_other * ((n + seg - 1) / seg) < 262144) seg >>= 1;
     return seg;
 }
