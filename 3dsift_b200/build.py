@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
         if force or _stale(obj, [sp, __file__] + headers):
-            cmd = [nvcc] + ARCH + COMMON + extra + ["-x", "cu" if src.endswith(".cu") else "c++"]
+            cmd = [nvcc] + ARCH + COMMON + extra + os.environ.get("S3D_NVCC_EXTRA", "").split() + ["-x", "cu" if src.endswith(".cu") else "c++"]
             if verbose:
                 cmd += ["-Xptxas", "-v"]
             cmd += ["-c", sp, "-o", obj]

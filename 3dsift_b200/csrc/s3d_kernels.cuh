@@ -1542,9 +1542,15 @@ struct DescSmem {
 // kQCopies interleaved copies (lane & (kQCopies-1) picks one): neighbouring voxels of a row mostly hit
 // the SAME bins, and same-address atomics of one warp instruction are serialised; with the copies
 // kQCopyStride words apart (== 4 mod 32 banks) the lanes of a group also land in different banks.
-constexpr int kQCopies = 8;
-constexpr int kQCopyStride = 836;
-static_assert(kQCopyStride >= kHistStride && kQCopyStride % 32 == 4, "copy stride must cover a histogram and rotate banks");
+// (measured: 16 copies, which fit 3 CTAs/SM instead of 4, halve the same-address serialisation but lose more to the
+// lower occupancy: describe 10.14 ms against 9.52 ms with 8 copies; build with -DS3D_QCOPIES=16 to repeat it)
+#ifndef S3D_QCOPIES
+#define S3D_QCOPIES 8
+#endif
+constexpr int kQCopies = S3D_QCOPIES;
+constexpr int kQCopyStride = kQCopies == 8 ? 836 : 834;  // == 32 / kQCopies mod 32 banks
+constexpr int kQMinCtas = kQCopies == 8 ? 4 : 3;          // CTAs per SM the shared-memory footprint allows
+static_assert(kQCopyStride >= kHistStride && kQCopyStride % 32 == 32 / kQCopies, "copy stride must cover a histogram and rotate banks");
 struct DescSmemQ {
     uint32_t hist[kQCopies * kQCopyStride];
     uint32_t queue[kDescWarps][64];
@@ -1583,7 +1589,7 @@ constexpr float kQMargin = 8.0f;   // qscale = kQCap / (kQMargin * sampled max o
 // above), which takes its keypoints from klist when given.  Inclusion tests, face selection and
 // all per-voxel arithmetic are identical in both variants.
 template <bool Q>
-__global__ void __launch_bounds__(kDescThreads, Q ? 4 : 3) describe_kernel(const s3d_keypoint* __restrict__ extre,
+__global__ void __launch_bounds__(kDescThreads, Q ? kQMinCtas : 3) describe_kernel(const s3d_keypoint* __restrict__ extre,
                                                                    const int* __restrict__ surv, int nkp, LevelTable tab,
                                                                    const MeshConst* __restrict__ meshp,
                                                                    s3d_keypoint* __restrict__ kps_out,
