@@ -16,6 +16,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'blu
 python scripts/ncu_summary.py /tmp/ncu/full_blur.ncu-rep --src 12 > gpurun_out/ncu_blur_summary.txt 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'describe_kernel|orient_kernel|orient_exact_kernel' -c 3 -f -o /tmp/ncu/full_sparse python scripts/profile_step.py 512 1 > gpurun_out/ncu_sparse.log 2>&1; echo "ncu sparse rc=$?"
 python scripts/ncu_summary.py /tmp/ncu/full_sparse.ncu-rep --src 40 > gpurun_out/ncu_sparse_summary.txt 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'detect_kernel|scan_kernel|maxabs_kernel|normalize_kernel|downsample_kernel' -c 6 -f -o /tmp/ncu/full_detect python scripts/profile_step.py 512 1 > gpurun_out/ncu_detect.log 2>&1; echo "ncu detect rc=$?"
-python scripts/ncu_summary.py /tmp/ncu/full_detect.ncu-rep --src 16 > gpurun_out/ncu_detect_summary.txt 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'detect_kernel|scan_kernel' -c 4 -f -o /tmp/ncu/full_detect python scripts/profile_step.py 512 1 > gpurun_out/ncu_detect.log 2>&1; echo "ncu detect rc=$?"
+python scripts/ncu_summary.py /tmp/ncu/full_detect.ncu-rep --src 20 > gpurun_out/ncu_detect_summary.txt 2>&1
+timeout 600 ncu --set full --clock-control none -k regex:'maxabs_kernel|normalize_kernel|downsample_kernel' -c 3 -f -o /tmp/ncu/full_small python scripts/profile_step.py 512 1 > gpurun_out/ncu_small.log 2>&1; echo "ncu small rc=$?"
+python scripts/ncu_summary.py /tmp/ncu/full_small.ncu-rep > gpurun_out/ncu_small_summary.txt 2>&1
 du -sh gpurun_out
