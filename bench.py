@@ -58,13 +58,18 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, indices, enabled=True):
+        # ONE sampler per job (rank 0), covering every GPU of the job: nvidia-smi queries take driver locks, and a
+        # poller per rank measurably slows the other ranks' CUDA calls
+        self.indices, self.rows, self.proc, self.enabled = list(indices), [], None, enabled
 
     def start(self):
+        if not self.enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", ",".join(str(i) for i in self.indices)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -234,7 +239,7 @@ def main():
     for _ in range(a.warmup):
         step_resident(False).close()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(range(world), enabled=(rank == 0))
     sampler.start()
     time.sleep(0.3)
     windows = []
