@@ -1875,7 +1875,9 @@ __global__ void __launch_bounds__(kDescThreads, Q ? kQMinCtas : 3) describe_kern
             q2n += __popc(mp);
             __syncwarp();
             if (q2n >= 32) {
-                stage_b(que2[(q2head + lane) & 63], true);
+                const uint4 ent = que2[(q2head + lane) & 63];
+                __syncwarp();  // every lane holds its entry before any lane may push into the freed slots again
+                stage_b(ent, true);
                 q2head = (q2head + 32) & 63;
                 q2n -= 32;
             }

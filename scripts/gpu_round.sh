@@ -20,4 +20,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'det
 python scripts/ncu_summary.py /tmp/ncu/full_detect.ncu-rep --src 20 > gpurun_out/ncu_detect_summary.txt 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:'maxabs_kernel|normalize_kernel|downsample_kernel' -c 3 -f -o /tmp/ncu/full_small python scripts/profile_step.py 512 1 > gpurun_out/ncu_small.log 2>&1; echo "ncu small rc=$?"
 python scripts/ncu_summary.py /tmp/ncu/full_small.ncu-rep > gpurun_out/ncu_small_summary.txt 2>&1
+bash scripts/gpu_sanitize.sh > /dev/null 2>&1; echo "sanitize rc=$?"; grep -E "^==|SUMMARY" gpurun_out/sanitize.txt
 du -sh gpurun_out
