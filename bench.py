@@ -183,7 +183,10 @@ def main():
     s3d.selftest(local)
 
     n = a.size
-    vol = synth.v_blobs(n, seed=rank)
+    # weak scaling = the SAME per-GPU work on every rank: every rank extracts V-blobs(n, seed 0) from its own pinned host
+    # copy (with seed = rank the keypoint count, hence the descriptor time, differed by ~10 % between ranks and the
+    # max over ranks measured the heaviest volume instead of the scaling)
+    vol = synth.v_blobs(n, seed=0)
     h_vol = torch.from_numpy(vol).pin_memory()
     d_vol = h_vol.cuda(non_blocking=False)
     nvox = vol.size
@@ -336,7 +339,14 @@ def main():
 
     # ---- reductions over ranks ---------------------------------------------------------------------
     t = torch.tensor([ms_value, ms_e2e], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
+        # per-rank view (value ms, e2e ms, summed kernel ms of the last resident step) before the max
+        mine = torch.tensor([ms_value, ms_e2e, stage.get("d_TotalTime", 0.0) * 1e3], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_value": [round(float(x[0]), 3) for x in allr], "ms_e2e": [round(float(x[1]), 3) for x in allr],
+                    "device_ms_last_step": [round(float(x[2]), 3) for x in allr]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_value, ms_e2e = float(t[0]), float(t[1])
     value = world * nvox / (ms_value * 1e-3) / 1e6
@@ -382,7 +392,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"V-blobs {n}^3 float32 volume per GPU (BASELINE.json configs[2] size), full extraction: "
                                    "normalise + Gaussian pyramid + DoG + detection + orientation + 768-d descriptors",
-                       "volumes_per_step": world, "keypoints_per_volume": nkp, "detections_per_volume": n_extre,
+                       "volumes_per_step": world, "per_rank_input": "every rank: V-blobs(n, seed 0), own pinned host copy", "keypoints_per_volume": nkp, "detections_per_volume": n_extre,
                        "l2": f"inputs ({vol.nbytes >> 20} MiB/volume) are larger than L2; no flush needed",
                        "parallelism": f"dp{world} (one volume per GPU, no collective on the data path)"},
             "clocks": sampler.summary(windows[:2]),   # the two extraction legs (value, e2e)
@@ -393,6 +403,7 @@ def main():
                             "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors); when the copy of the next "
                             "volume is slower than one extraction the leg is bound by the host link (h2d_ms)"},
             "gpu_launches": int(launches),
+            "per_rank": per_rank,
             "roofline": roof,
             "dominant_by_time": ({"kernel": "describe", "ms_per_step": kernels["describe"]["ms_per_step"],
                                   "share_of_step": kernels["describe"]["ms_per_step"] / ms_value,
