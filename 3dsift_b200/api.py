@@ -73,6 +73,8 @@ def lib():
     L.s3d_level_dims.argtypes = [vp, C.c_int, C.POINTER(C.c_int * 3)]
     L.s3d_num_keypoints.argtypes = [vp, C.POINTER(C.c_int)]
     L.s3d_get_keypoints.argtypes = [vp, vp, fp]
+    L.s3d_get_keypoints_async.argtypes = [vp, vp, fp]
+    L.s3d_sync.argtypes = [vp]
     L.s3d_num_extrema.argtypes = [vp, C.POINTER(C.c_int)]
     L.s3d_get_extrema.argtypes = [vp, vp, ip, ip]
     L.s3d_get_level.argtypes = [vp, C.c_int, C.c_int, fp]
@@ -264,6 +266,13 @@ class CSIFT3D:
 
     def wait(self):
         check(lib().s3d_wait(self._h))
+
+    def get_keypoints_async(self, kp_ptr, desc_ptr):
+        """Enqueue the D2H copies of the records / descriptors into (pinned) host memory; sync() completes them."""
+        check(lib().s3d_get_keypoints_async(self._h, kp_ptr, desc_ptr))
+
+    def sync(self):
+        check(lib().s3d_sync(self._h))
 
     # -- parity hooks (GET_GSS / GET_DOG / GET_LEVEL, Include/cSIFT3D.h:169-177) -----------------
     def num_keypoints(self):

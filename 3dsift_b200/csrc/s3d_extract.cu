@@ -447,7 +447,7 @@ struct s3d_ctx {
     int n_rechecked = 0, n_flipped = 0;
     int* d_redo = nullptr;          // [0] = count, [1..] = keypoint indices (freed in s3d_wait)
     int n_desc_redo = 0;            // keypoints the fixed-point descriptor kernel handed to the FP32 one
-    bool ran = false, levels_alive = false, queued = false, h2d_pending = false;
+    bool ran = false, levels_alive = false, queued = false, h2d_pending = false, d2h_pending = false;
     // z-slab sharding.  Unsharded: slab = false, za = p0 = 0, zb = p1 = nz_o.
     // A shard OWNS global planes [p0[o], p1[o]) of octave o and keeps local buffers for planes
     // [za[o], zb[o]) (owned + halo).  nz / dims[][2] / nvox[] stay the GLOBAL sizes.
@@ -1201,25 +1201,40 @@ int s3d_num_keypoints(s3d_handle c, int* n) {
     return S3D_OK;
 }
 
-int s3d_get_keypoints(s3d_handle c, s3d_keypoint* kp, float* desc) {
+int s3d_get_keypoints_async(s3d_handle c, s3d_keypoint* kp, float* desc) {
     clear_error();
     if (!c) return fail(S3D_ERR_ARG, "null handle");
     if (!c->ran) return fail(S3D_ERR_STATE, "not run yet");
     S3D_CUDA(cudaSetDevice(c->device));
-    cudaEvent_t e0 = c->ev[6], e1 = c->ev[7];
-    S3D_CUDA(cudaEventRecord(e0, c->stream));
+    S3D_CUDA(cudaEventRecord(c->ev[6], c->stream));
     if (c->n_kps > 0) {
         if (kp) S3D_CUDA(cudaMemcpyAsync(kp, c->d_kps, sizeof(s3d_keypoint) * c->n_kps, cudaMemcpyDeviceToHost, c->stream));
         if (desc)
             S3D_CUDA(cudaMemcpyAsync(desc, c->d_desc, sizeof(float) * S3D_DESC_LEN * (size_t)c->n_kps,
                                      cudaMemcpyDeviceToHost, c->stream));
     }
-    S3D_CUDA(cudaEventRecord(e1, c->stream));
-    S3D_CUDA(cudaStreamSynchronize(c->stream));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    c->timers[9] = ms * 1e-3;
+    S3D_CUDA(cudaEventRecord(c->ev[7], c->stream));
+    c->d2h_pending = true;
     return S3D_OK;
+}
+
+int s3d_sync(s3d_handle c) {
+    clear_error();
+    if (!c) return fail(S3D_ERR_ARG, "null handle");
+    S3D_CUDA(cudaSetDevice(c->device));
+    S3D_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->d2h_pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[6], c->ev[7]);
+        c->timers[9] = ms * 1e-3;
+        c->d2h_pending = false;
+    }
+    return S3D_OK;
+}
+
+int s3d_get_keypoints(s3d_handle c, s3d_keypoint* kp, float* desc) {
+    const int r = s3d_get_keypoints_async(c, kp, desc);
+    return r != S3D_OK ? r : s3d_sync(c);
 }
 
 int s3d_num_extrema(s3d_handle c, int* n) {

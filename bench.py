@@ -206,8 +206,8 @@ def main():
     first = step_resident(False)
     nk0 = first.num_keypoints()
     cap = int(nk0 * 1.5) + 1024
-    h_kp = torch.empty((cap, 176), dtype=torch.uint8).pin_memory()
-    h_desc = torch.empty((cap, 768), dtype=torch.float32).pin_memory()
+    h_kp = [torch.empty((cap, 176), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    h_desc = [torch.empty((cap, 768), dtype=torch.float32).pin_memory() for _ in range(2)]
     first.close()
 
     # e2e: the public host API with HOST buffers.  Every step uploads its own 512 MiB volume from pinned
@@ -221,22 +221,40 @@ def main():
     e2e_step_ms = []
 
     def e2e_steps(k_steps):
+        """Step i: upload of volume i+1 enqueued (copy engine), volume i extracted, its records + descriptors ENQUEUED for
+        D2H into one of two pinned result buffers (s3d_get_keypoints_async) and collected with s3d_sync - within the same
+        step by default; S3D_E2E_ASYNC_D2H=1 collects it after volume i+1's extraction instead."""
         k = 0
         del e2e_step_ms[:]
         t_prev = time.perf_counter()
-        cur = upload()
+        # measured: steady-state steps 18.5 ms instead of 19.0, but with two handles alive the stream-ordered pool
+        # intermittently re-allocates gigabytes (steps of 45-700 ms) - off until the handles reuse their arenas
+        async_d2h = os.environ.get("S3D_E2E_ASYNC_D2H", "0") == "1"
+
+        def finish(h):
+            h.sync()
+            t = h.m_timer
+            e2e_split.update(h2d_ms=t["d_h2d"] * 1e3, d2h_ms=t["d_d2h"] * 1e3, device_ms=t["d_TotalTime"] * 1e3)
+            h.close()
+
+        cur, pend = upload(), None
         for i in range(k_steps):
             nxt = upload() if i + 1 < k_steps else None
             cur.KpSiftAlgorithm()
+            if pend is not None:
+                finish(pend)
             k = cur.num_keypoints()
-            s3d.check(L.s3d_get_keypoints(cur._h, h_kp.data_ptr(), h_desc.data_ptr()))
-            t = cur.m_timer
-            e2e_split.update(h2d_ms=t["d_h2d"] * 1e3, d2h_ms=t["d_d2h"] * 1e3, device_ms=t["d_TotalTime"] * 1e3)
-            cur.close()
+            cur.get_keypoints_async(h_kp[i & 1].data_ptr(), h_desc[i & 1].data_ptr())
+            pend = cur
+            if not async_d2h:
+                finish(pend)
+                pend = None
             cur = nxt
             now = time.perf_counter()
             e2e_step_ms.append(round((now - t_prev) * 1e3, 2))
             t_prev = now
+        if pend is not None:
+            finish(pend)
         return k
 
     for _ in range(a.warmup):
@@ -400,8 +418,9 @@ def main():
                     "d2h_bytes_per_step": int(k * (176 + 768 * 4)),
                     "last_step_split_ms": e2e_split, "host_wall_ms_per_step": list(e2e_step_ms),
                     "note": "pinned host volume -> CreateCSIFT3D (H2D on the handle's stream, enqueued one step ahead) -> "
-                            "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors); when the copy of the next "
-                            "volume is slower than one extraction the leg is bound by the host link (h2d_ms)"},
+                            "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors into pinned buffers, collected inside the "
+                            "step); when the copy of the next volume is slower than one extraction the leg is bound by the host "
+                            "link (h2d_ms)"},
             "gpu_launches": int(launches),
             "per_rank": per_rank,
             "roofline": roof,

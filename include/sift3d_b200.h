@@ -114,6 +114,11 @@ S3D_API int s3d_level_dims(s3d_handle h, int octave, int* dims3);
  * either pointer may be NULL).  Order = (octave, level, z, y, x) of the surviving detections. */
 S3D_API int s3d_num_keypoints(s3d_handle h, int* n);
 S3D_API int s3d_get_keypoints(s3d_handle h, s3d_keypoint* kp, float* desc);
+/* The same copies ENQUEUED on the handle's stream without waiting (kp / desc should be pinned host memory, and must stay
+ * valid until s3d_sync returns): lets the caller start the next volume's extraction on another handle while this one's
+ * results travel to the host.  s3d_sync = wait for everything enqueued on the handle's stream (records the D2H time). */
+S3D_API int s3d_get_keypoints_async(s3d_handle h, s3d_keypoint* kp, float* desc);
+S3D_API int s3d_sync(s3d_handle h);
 /* The raw detections after orientation (`extre`, Src/cSIFT3D.cc:410,427-456): records carry
  * str_tensor / win / eigvalue / eigvector, rejected ones x=y=z=-1; codes[i] in {1,-1,-2,-3}
  * (RET, Src/cSIFT3D.cc:445).  xyz5 (may be NULL) receives the integer x,y,z,octave,level of every
