@@ -7,7 +7,7 @@ headers under include/3dsift/; this package is the Python host mirror used by te
 """
 from .api import (  # noqa: F401
     CSIFT3D, CSIFT3DFactory, DESC_LENGTH, KP_DTYPE, S3DError, DownSample_3D, GaussianSmooth_3D, blur_axis, check,
-    device_count, launch_count, lib, match_stats, muBruteMatcher, readNiiFile, read_matrix_from_disk, selftest, set_describe_path, set_match_path,
+    device_count, launch_count, lib, match_stats, muBruteMatcher, readNiiFile, read_matrix_from_disk, selftest, set_describe_path, set_match_path, trim_cache,
     write_matrix_to_disk,
 )
 from . import synth  # noqa: F401

@@ -75,6 +75,7 @@ def lib():
     L.s3d_get_keypoints.argtypes = [vp, vp, fp]
     L.s3d_get_keypoints_async.argtypes = [vp, vp, fp]
     L.s3d_sync.argtypes = [vp]
+    L.s3d_trim_cache.argtypes = [C.c_int, C.POINTER(C.c_ulonglong)]
     L.s3d_num_extrema.argtypes = [vp, C.POINTER(C.c_int)]
     L.s3d_get_extrema.argtypes = [vp, vp, ip, ip]
     L.s3d_get_level.argtypes = [vp, C.c_int, C.c_int, fp]
@@ -152,6 +153,13 @@ def launch_count():
 
 def selftest(device=-1):
     check(lib().s3d_selftest(device))
+
+
+def trim_cache(device=-1):
+    """Return the library's cached device blocks to the driver; returns the number of bytes that were cached."""
+    n = C.c_ulonglong()
+    check(lib().s3d_trim_cache(device, C.byref(n)))
+    return n.value
 
 
 MATCH_AUTO, MATCH_EXACT, MATCH_TENSOR, MATCH_TENSOR_SINGLE, MATCH_TENSOR_PAIR = 0, 1, 2, 3, 4

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "s3d_common.h"
+#include "s3d_devcache.h"
 #include "s3d_kernels.cuh"
 
 namespace s3d {
@@ -489,9 +490,9 @@ struct s3d_ctx {
 };
 
 static void free_levels(s3d_ctx* c) {
-    for (auto& p : c->gss) if (p) { cudaFreeAsync(p, c->stream); p = nullptr; }
-    for (auto& p : c->dog) if (p) { cudaFreeAsync(p, c->stream); p = nullptr; }
-    for (int i = 0; i < 2; i++) if (c->d_tmp[i]) { cudaFreeAsync(c->d_tmp[i], c->stream); c->d_tmp[i] = nullptr; }
+    for (auto& p : c->gss) if (p) { s3d::dev_free(p, c->stream); p = nullptr; }
+    for (auto& p : c->dog) if (p) { s3d::dev_free(p, c->stream); p = nullptr; }
+    for (int i = 0; i < 2; i++) if (c->d_tmp[i]) { s3d::dev_free(c->d_tmp[i], c->stream); c->d_tmp[i] = nullptr; }
     c->levels_alive = false;
 }
 
@@ -524,8 +525,8 @@ static int ctx_common_init(s3d_ctx* c, int nx, int ny, int nz, const s3d_params*
 
 static int ctx_normalize(s3d_ctx* c, const float* d_raw) {
     // ctor: data_scale (Src/cUtil.cc:536-564)
-    S3D_CUDA(cudaMallocAsync((void**)&c->d_input, c->n0 * sizeof(float), c->stream));
-    S3D_CUDA(cudaMallocAsync((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_input, c->n0 * sizeof(float), c->stream));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
     S3D_CUDA(cudaMemsetAsync(c->d_slots, 0, 256 * sizeof(unsigned), c->stream));
     const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks(c->n0 / 4 + 1, 256), 148 * 16);
     {
@@ -599,7 +600,7 @@ static int create_host(const float* vol, int nx, int ny, int nz, const s3d_param
     if (r != S3D_OK) { s3d_destroy(c); return r; }
     float* d_raw = nullptr;
     cudaEventRecord(c->ev[6], c->stream);
-    if (cudaMallocAsync((void**)&d_raw, c->n0 * sizeof(float), c->stream) != cudaSuccess ||
+    if (s3d::dev_alloc((void**)&d_raw, c->n0 * sizeof(float), c->stream) != cudaSuccess ||
         cudaMemcpyAsync(d_raw, vol, c->n0 * sizeof(float), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) {
         r = fail(S3D_ERR_CUDA, "H2D copy of the volume failed: %s", cudaGetErrorString(cudaGetLastError()));
         s3d_destroy(c);
@@ -607,7 +608,7 @@ static int create_host(const float* vol, int nx, int ny, int nz, const s3d_param
     }
     cudaEventRecord(c->ev[7], c->stream);
     r = ctx_normalize(c, d_raw);
-    cudaFreeAsync(d_raw, c->stream);
+    s3d::dev_free(d_raw, c->stream);
     if (r != S3D_OK) { s3d_destroy(c); return r; }
     c->h2d_pending = true;
     if (sync) {
@@ -653,7 +654,7 @@ void s3d_destroy(s3d_handle c) {
         cudaSetDevice(c->device);
         free_levels(c);
         void* ptrs[] = {c->d_input, c->d_slots, c->d_thres, c->d_mesh, c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc, c->d_redo};
-        for (void* q : ptrs) if (q) cudaFreeAsync(q, c->stream);
+        for (void* q : ptrs) if (q) s3d::dev_free(q, c->stream);
         cudaStreamSynchronize(c->stream);
         c->prof.resolve();
         if (c->ev_ok) for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
@@ -736,10 +737,10 @@ static int stage_init(s3d_ctx* c) {
     for (int o = 0; o < c->noct; o++) {
         const size_t bytes = std::max<size_t>(c->lvox(o), 4) * sizeof(float);
         tmp_elems = std::max(tmp_elems, c->lvox(o));
-        for (int i = 0; i < G; i++) S3D_CUDA(cudaMallocAsync((void**)&c->gss[o * G + i], bytes, st));
-        for (int i = 0; i < D; i++) S3D_CUDA(cudaMallocAsync((void**)&c->dog[o * D + i], bytes, st));
+        for (int i = 0; i < G; i++) S3D_CUDA(s3d::dev_alloc((void**)&c->gss[o * G + i], bytes, st));
+        for (int i = 0; i < D; i++) S3D_CUDA(s3d::dev_alloc((void**)&c->dog[o * D + i], bytes, st));
     }
-    for (int i = 0; i < 2; i++) S3D_CUDA(cudaMallocAsync((void**)&c->d_tmp[i], tmp_elems * sizeof(float), st));
+    for (int i = 0; i < 2; i++) S3D_CUDA(s3d::dev_alloc((void**)&c->d_tmp[i], tmp_elems * sizeof(float), st));
     if (c->slab && getenv("S3D_SLAB_POISON")) {  // tests: a halo plane that was never filled must show up as NaN
         for (int o = 0; o < c->noct; o++) {
             for (int i = 0; i < G; i++) S3D_CUDA(cudaMemsetAsync(c->gss[o * G + i], 0xFF, c->lvox(o) * sizeof(float), st));
@@ -747,11 +748,11 @@ static int stage_init(s3d_ctx* c) {
         }
     }
     c->levels_alive = true;
-    S3D_CUDA(cudaMallocAsync((void**)&c->d_thres, sizeof(float) * c->noct * L, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_thres, sizeof(float) * c->noct * L, st));
     {
         MeshConst hm;
         host_mesh(&hm);
-        S3D_CUDA(cudaMallocAsync((void**)&c->d_mesh, sizeof(MeshConst), st));
+        S3D_CUDA(s3d::dev_alloc((void**)&c->d_mesh, sizeof(MeshConst), st));
         S3D_CUDA(cudaMemcpyAsync(c->d_mesh, &hm, sizeof(MeshConst), cudaMemcpyHostToDevice, st));
         S3D_CUDA(cudaStreamSynchronize(st));  // hm is a stack object
     }
@@ -837,11 +838,11 @@ static int stage_sparse(s3d_ctx* c) {
     StageEntry* d_stage = nullptr;
     unsigned* d_stage_count = nullptr;
     Cand* d_cand = nullptr;
-    S3D_CUDA(cudaMallocAsync((void**)&d_blk_cnt, sizeof(int) * nblk, st));
-    S3D_CUDA(cudaMallocAsync((void**)&d_blk_off, sizeof(int) * nblk, st));
-    S3D_CUDA(cudaMallocAsync((void**)&d_total, sizeof(int) * 4, st));
-    S3D_CUDA(cudaMallocAsync((void**)&d_stage, sizeof(StageEntry) * (size_t)stage_cap, st));
-    S3D_CUDA(cudaMallocAsync((void**)&d_stage_count, sizeof(unsigned), st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_blk_cnt, sizeof(int) * nblk, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_blk_off, sizeof(int) * nblk, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_total, sizeof(int) * 4, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_stage, sizeof(StageEntry) * (size_t)stage_cap, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_stage_count, sizeof(unsigned), st));
     S3D_CUDA(cudaMemsetAsync(d_stage_count, 0, sizeof(unsigned), st));
     S3D_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int) * 4, st));
     S3D_CUDA(cudaMemsetAsync(d_blk_cnt, 0, sizeof(int) * nblk, st));
@@ -871,7 +872,7 @@ static int stage_sparse(s3d_ctx* c) {
     c->n_extre = h_total[0];
     const int ne = c->n_extre;
     if (ne > 0) {
-        S3D_CUDA(cudaMallocAsync((void**)&d_cand, sizeof(Cand) * (size_t)ne, st));
+        S3D_CUDA(s3d::dev_alloc((void**)&d_cand, sizeof(Cand) * (size_t)ne, st));
         ProfScope ps(&c->prof, K_COMPACT, 24.0 * ne);
         S3D_LAUNCH(scatter_kernel, s3d_blocks(ne, 256), 256, 0, st, d_stage, d_stage_count, stage_cap, d_blk_off, d_cand);
     }
@@ -901,7 +902,7 @@ static int stage_sparse(s3d_ctx* c) {
                 tab.ori_off[lv] = off; tab.ori_n[lv] = (int)(ro * ro / (u * u)) + 2; off += tab.ori_n[lv];
                 tab.desc_off[lv] = off; tab.desc_n[lv] = (int)(rd * rd / (u * u)) + 2; off += tab.desc_n[lv];
             }
-        S3D_CUDA(cudaMallocAsync((void**)&d_wtab, sizeof(float) * std::max(off, 1), st));
+        S3D_CUDA(s3d::dev_alloc((void**)&d_wtab, sizeof(float) * std::max(off, 1), st));
         tab.wtab = d_wtab;
         if (ne > 0) S3D_LAUNCH(wtab_kernel, dim3(2, c->noct * G), 256, 0, st, tab, c->noct, d_wtab);
     }
@@ -909,11 +910,11 @@ static int stage_sparse(s3d_ctx* c) {
     int* d_surv = nullptr;
     int* d_order = nullptr;
     const size_t nea = std::max(ne, 1);
-    S3D_CUDA(cudaMallocAsync((void**)&c->d_extre, sizeof(s3d_keypoint) * nea, st));
-    S3D_CUDA(cudaMallocAsync((void**)&c->d_codes, sizeof(int) * nea, st));
-    S3D_CUDA(cudaMallocAsync((void**)&c->d_xyz5, sizeof(int) * 5 * nea, st));
-    S3D_CUDA(cudaMallocAsync((void**)&d_recheck, sizeof(int) * nea, st));
-    S3D_CUDA(cudaMallocAsync((void**)&d_surv, sizeof(int) * nea, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_extre, sizeof(s3d_keypoint) * nea, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_codes, sizeof(int) * nea, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_xyz5, sizeof(int) * 5 * nea, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_recheck, sizeof(int) * nea, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_surv, sizeof(int) * nea, st));
     if (ne > 0) {
         const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks((size_t)ne * 32, 256), 148 * 32);
         {
@@ -933,7 +934,7 @@ static int stage_sparse(s3d_ctx* c) {
         S3D_LAUNCH(survivors_kernel, 1, 1024, 0, st, c->d_codes, ne, d_surv, d_total + 3);
         // heavy-first launch order of the descriptor CTAs (S3D_DESC_ORDER=0: list order)
         if (desc_order_enabled() && ne > 0) {
-            S3D_CUDA(cudaMallocAsync((void**)&d_order, sizeof(int) * nea, st));
+            S3D_CUDA(s3d::dev_alloc((void**)&d_order, sizeof(int) * nea, st));
             S3D_LAUNCH(desc_order_kernel, 1, 1024, 0, st, c->d_extre, d_surv, d_total + 3, G - 1, d_order);
         }
     }
@@ -946,8 +947,8 @@ static int stage_sparse(s3d_ctx* c) {
 
     // ---- Description -----------------------------------------------------------------------------
     const size_t nka = std::max(c->n_kps, 1);
-    S3D_CUDA(cudaMallocAsync((void**)&c->d_kps, sizeof(s3d_keypoint) * nka, st));
-    S3D_CUDA(cudaMallocAsync((void**)&c->d_desc, sizeof(float) * S3D_DESC_LEN * nka, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_kps, sizeof(s3d_keypoint) * nka, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_desc, sizeof(float) * S3D_DESC_LEN * nka, st));
     int* d_redo = nullptr;
     if (c->n_kps > 0) {
         static bool attr_set[64] = {false};
@@ -964,7 +965,7 @@ static int stage_sparse(s3d_ctx* c) {
         } else {
             // fixed-point atomics for all; the (normally empty) list of keypoints whose scale estimate was
             // too low is redone in FP32 — its grid is sized for the worst case and reads the count on the device
-            S3D_CUDA(cudaMallocAsync((void**)&d_redo, sizeof(int) * ((size_t)c->n_kps + 1), st));
+            S3D_CUDA(s3d::dev_alloc((void**)&d_redo, sizeof(int) * ((size_t)c->n_kps + 1), st));
             S3D_CUDA(cudaMemsetAsync(d_redo, 0, sizeof(int), st));
             {
                 ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
@@ -985,7 +986,7 @@ static int stage_sparse(s3d_ctx* c) {
     // ---- Release_SIFT (:1659-1678) unless the caller asked to keep the pyramids ---------------
     if (!c->prm.keep_levels) free_levels(c);
     void* tmp[] = {d_blk_cnt, d_blk_off, d_total, d_stage, d_stage_count, d_cand, d_recheck, d_surv, d_order, d_wtab, d_redo};
-    for (void* q : tmp) if (q) cudaFreeAsync(q, st);
+    for (void* q : tmp) if (q) s3d::dev_free(q, st);
     S3D_CUDA(cudaEventRecord(c->ev[6], st));
     c->queued = true;
     c->stage = 100;
@@ -1016,7 +1017,7 @@ int s3d_wait(s3d_handle c) {
     S3D_CUDA(cudaStreamSynchronize(c->stream));
     if (c->d_redo) {
         S3D_CUDA(cudaMemcpy(&c->n_desc_redo, c->d_redo, sizeof(int), cudaMemcpyDeviceToHost));
-        cudaFreeAsync(c->d_redo, c->stream);
+        s3d::dev_free(c->d_redo, c->stream);
         c->d_redo = nullptr;
     }
     if (!c->ran) {
@@ -1092,8 +1093,8 @@ int s3d_slab_create(const float* vol_ext, int on_device, int nx, int ny, int nz,
     const size_t plane = (size_t)nx * ny, nloc = plane * (size_t)(zb - za);
     auto body = [&]() -> int {
         // d_input first holds the raw local planes; s3d_slab_begin normalises them in place
-        S3D_CUDA(cudaMallocAsync((void**)&c->d_input, nloc * sizeof(float), c->stream));
-        S3D_CUDA(cudaMallocAsync((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
+        S3D_CUDA(s3d::dev_alloc((void**)&c->d_input, nloc * sizeof(float), c->stream));
+        S3D_CUDA(s3d::dev_alloc((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
         S3D_CUDA(cudaMemsetAsync(c->d_slots, 0, 256 * sizeof(unsigned), c->stream));
         S3D_CUDA(cudaMemcpyAsync(c->d_input, vol_ext, nloc * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                                  c->stream));
@@ -1255,6 +1256,18 @@ int s3d_sync(s3d_handle c) {
         c->timers[9] = ms * 1e-3;
         c->d2h_pending = false;
     }
+    return S3D_OK;
+}
+
+int s3d_trim_cache(int device, unsigned long long* cached_bytes) {
+    clear_error();
+    int cur = 0;
+    S3D_CUDA(cudaGetDevice(&cur));
+    const int dev = device < 0 ? cur : device;
+    if (cached_bytes) *cached_bytes = (unsigned long long)s3d::DevCache::get().cached_bytes(dev);
+    if (dev != cur) S3D_CUDA(cudaSetDevice(dev));
+    s3d::DevCache::get().trim(dev);
+    if (dev != cur) S3D_CUDA(cudaSetDevice(cur));
     return S3D_OK;
 }
 

@@ -222,14 +222,16 @@ def main():
 
     def e2e_steps(k_steps):
         """Step i: upload of volume i+1 enqueued (copy engine), volume i extracted, its records + descriptors ENQUEUED for
-        D2H into one of two pinned result buffers (s3d_get_keypoints_async) and collected with s3d_sync - within the same
-        step by default; S3D_E2E_ASYNC_D2H=1 collects it after volume i+1's extraction instead."""
+        D2H into one of two pinned result buffers (s3d_get_keypoints_async); that copy runs under volume i+1's first kernels
+        and is collected (s3d_sync) after them - the last step's before the timer stops.  S3D_E2E_ASYNC_D2H=0: blocking
+        fetch inside every step."""
         k = 0
         del e2e_step_ms[:]
         t_prev = time.perf_counter()
-        # measured: steady-state steps 18.5 ms instead of 19.0, but with two handles alive the stream-ordered pool
-        # intermittently re-allocates gigabytes (steps of 45-700 ms) - off until the handles reuse their arenas
-        async_d2h = os.environ.get("S3D_E2E_ASYNC_D2H", "0") == "1"
+        # measured: steady-state steps 18.7 ms instead of 19.1.  (With cudaMallocAsync this variant intermittently
+        # re-allocated gigabytes - steps of 45-700 ms - because two handles are alive at once; the library's block
+        # cache, s3d_devcache.h, removed that.)
+        async_d2h = os.environ.get("S3D_E2E_ASYNC_D2H", "1") != "0"
 
         def finish(h):
             h.sync()
@@ -418,9 +420,10 @@ def main():
                     "d2h_bytes_per_step": int(k * (176 + 768 * 4)),
                     "last_step_split_ms": e2e_split, "host_wall_ms_per_step": list(e2e_step_ms),
                     "note": "pinned host volume -> CreateCSIFT3D (H2D on the handle's stream, enqueued one step ahead) -> "
-                            "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors into pinned buffers, collected inside the "
-                            "step); when the copy of the next volume is slower than one extraction the leg is bound by the host "
-                            "link (h2d_ms)"},
+                            "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors into one of two pinned buffers, enqueued "
+                            "with s3d_get_keypoints_async and collected with s3d_sync after the next volume's extraction; the last "
+                            "step's copy is collected before the timer stops); when the copy of the next volume is slower than one "
+                            "extraction the leg is bound by the host link (h2d_ms)"},
             "gpu_launches": int(launches),
             "per_rank": per_rank,
             "roofline": roof,

@@ -119,6 +119,10 @@ S3D_API int s3d_get_keypoints(s3d_handle h, s3d_keypoint* kp, float* desc);
  * results travel to the host.  s3d_sync = wait for everything enqueued on the handle's stream (records the D2H time). */
 S3D_API int s3d_get_keypoints_async(s3d_handle h, s3d_keypoint* kp, float* desc);
 S3D_API int s3d_sync(s3d_handle h);
+/* The handles' device buffers are recycled through a size-class cache inside the library (a freed pyramid serves the next
+ * volume, whatever stream it runs on).  s3d_trim_cache returns every cached block of `device` (-1 = current) to the driver;
+ * *cached_bytes (may be NULL) receives the number of bytes that were cached. */
+S3D_API int s3d_trim_cache(int device, unsigned long long* cached_bytes);
 /* The raw detections after orientation (`extre`, Src/cSIFT3D.cc:410,427-456): records carry
  * str_tensor / win / eigvalue / eigvector, rejected ones x=y=z=-1; codes[i] in {1,-1,-2,-3}
  * (RET, Src/cSIFT3D.cc:445).  xyz5 (may be NULL) receives the integer x,y,z,octave,level of every
