@@ -206,8 +206,9 @@ def main():
     first = step_resident(False)
     nk0 = first.num_keypoints()
     cap = int(nk0 * 1.5) + 1024
-    h_kp = [torch.empty((cap, 176), dtype=torch.uint8).pin_memory() for _ in range(2)]
-    h_desc = [torch.empty((cap, 768), dtype=torch.float32).pin_memory() for _ in range(2)]
+    n_res = 2 * max(3, int(os.environ.get("S3D_E2E_THREADS", "3")))   # two result buffers per e2e host thread
+    h_kp = [torch.empty((cap, 176), dtype=torch.uint8).pin_memory() for _ in range(n_res)]
+    h_desc = [torch.empty((cap, 768), dtype=torch.float32).pin_memory() for _ in range(n_res)]
     first.close()
 
     # e2e: the public host API with HOST buffers.  Every step uploads its own 512 MiB volume from pinned
@@ -220,44 +221,74 @@ def main():
     e2e_split = {}
     e2e_step_ms = []
 
+    # host threads of the e2e leg: every thread's first upload is exposed (9.7 ms each, one copy engine direction), so
+    # concurrency only pays off on longer runs - measured at 10 steps: 19.6 ms/step with 1 thread, 18.9 with 3, 20.8 with 4
+    _thr_env = os.environ.get("S3D_E2E_THREADS")
+    E2E_THREADS = max(1, int(_thr_env)) if _thr_env else (1 if a.steps < 16 else 2 if a.steps < 32 else 3)
+
     def e2e_steps(k_steps):
-        """Step i: upload of volume i+1 enqueued (copy engine), volume i extracted, its records + descriptors ENQUEUED for
-        D2H into one of two pinned result buffers (s3d_get_keypoints_async); that copy runs under volume i+1's first kernels
-        and is collected (s3d_sync) after them - the last step's before the timer stops.  S3D_E2E_ASYNC_D2H=0: blocking
-        fetch inside every step."""
-        k = 0
+        """k_steps volumes through the public host API, dealt to E2E_THREADS host threads (the C calls release the GIL).
+        Each thread keeps three volumes in flight on private handles/streams: volume i+1 uploading (copy engine), volume i
+        extracting, volume i-1's records + descriptors on their way into one of the thread's two pinned result buffers
+        (s3d_get_keypoints_async, collected with s3d_sync after the next extraction; the last one before the thread ends).
+        Several extractions in flight let the GPU fill one volume's kernel tails and its issue-bound descriptor stage
+        with another volume's memory-bound pyramid (measured, resident volumes: 18.1 / 17.9 / 17.5 / 16.7 ms per volume with
+        1 / 2 / 3 / 4 threads); the handles' buffers come from the library's block cache, so overlapping lifetimes do not
+        touch the driver's allocator.  S3D_E2E_THREADS=1, S3D_E2E_ASYNC_D2H=0: the serial loop with a blocking fetch."""
         del e2e_step_ms[:]
-        t_prev = time.perf_counter()
-        # measured: steady-state steps 18.7 ms instead of 19.1.  (With cudaMallocAsync this variant intermittently
-        # re-allocated gigabytes - steps of 45-700 ms - because two handles are alive at once; the library's block
-        # cache, s3d_devcache.h, removed that.)
+        t_start = time.perf_counter()
         async_d2h = os.environ.get("S3D_E2E_ASYNC_D2H", "1") != "0"
+        nthreads = min(E2E_THREADS, max(1, k_steps))
+        done_at, kcount, errors = [], [0], []
+        lock = threading.Lock()
 
-        def finish(h):
-            h.sync()
-            t = h.m_timer
-            e2e_split.update(h2d_ms=t["d_h2d"] * 1e3, d2h_ms=t["d_d2h"] * 1e3, device_ms=t["d_TotalTime"] * 1e3)
-            h.close()
+        def worker(tid, n_steps):
+            try:
+                torch.cuda.set_device(local)
+                kp_buf, desc_buf = h_kp[2 * tid:2 * tid + 2], h_desc[2 * tid:2 * tid + 2]
 
-        cur, pend = upload(), None
-        for i in range(k_steps):
-            nxt = upload() if i + 1 < k_steps else None
-            cur.KpSiftAlgorithm()
-            if pend is not None:
-                finish(pend)
-            k = cur.num_keypoints()
-            cur.get_keypoints_async(h_kp[i & 1].data_ptr(), h_desc[i & 1].data_ptr())
-            pend = cur
-            if not async_d2h:
-                finish(pend)
-                pend = None
-            cur = nxt
-            now = time.perf_counter()
-            e2e_step_ms.append(round((now - t_prev) * 1e3, 2))
-            t_prev = now
-        if pend is not None:
-            finish(pend)
-        return k
+                def finish(h):
+                    h.sync()
+                    t = h.m_timer
+                    with lock:
+                        e2e_split.update(h2d_ms=t["d_h2d"] * 1e3, d2h_ms=t["d_d2h"] * 1e3, device_ms=t["d_TotalTime"] * 1e3)
+                        done_at.append(time.perf_counter())
+                    h.close()
+
+                cur, pend = (upload() if n_steps > 0 else None), None
+                for i in range(n_steps):
+                    nxt = upload() if i + 1 < n_steps else None
+                    cur.KpSiftAlgorithm()
+                    if pend is not None:
+                        finish(pend)
+                    kcount[0] = cur.num_keypoints()
+                    cur.get_keypoints_async(kp_buf[i & 1].data_ptr(), desc_buf[i & 1].data_ptr())
+                    pend = cur
+                    if not async_d2h:
+                        finish(pend)
+                        pend = None
+                    cur = nxt
+                if pend is not None:
+                    finish(pend)
+            except Exception as ex:   # surfaced by the caller: a failed step must fail the bench
+                errors.append(ex)
+
+        shares = [k_steps // nthreads + (1 if t < k_steps % nthreads else 0) for t in range(nthreads)]
+        if nthreads == 1:
+            worker(0, shares[0])
+        else:
+            th = [threading.Thread(target=worker, args=(t, shares[t])) for t in range(nthreads)]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        if errors:
+            raise errors[0]
+        prev = t_start
+        for t in sorted(done_at):   # completion-to-completion times of the volumes
+            e2e_step_ms.append(round((t - prev) * 1e3, 2))
+            prev = t
+        return kcount[0]
 
     for _ in range(a.warmup):
         step_resident(False).close()
@@ -292,7 +323,7 @@ def main():
     # ---- e2e: host buffers, H2D + D2H inside --------------------------------------------------------
     # its own W untimed warm-up steps first: the e2e handles run on private streams, and the first
     # volumes after the resident leg re-home the stream-ordered memory pool's blocks
-    e2e_steps(a.warmup)
+    e2e_steps(max(a.warmup, 3 * E2E_THREADS))   # every thread reaches its three-volumes-in-flight state (block cache warm)
     barrier()
     w0 = time.time()
     ev0.record()
@@ -416,14 +447,14 @@ def main():
                        "l2": f"inputs ({vol.nbytes >> 20} MiB/volume) are larger than L2; no flush needed",
                        "parallelism": f"dp{world} (one volume per GPU, no collective on the data path)"},
             "clocks": sampler.summary(windows[:2]),   # the two extraction legs (value, e2e)
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(vol.nbytes),
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "host_threads": E2E_THREADS, "h2d_bytes_per_step": int(vol.nbytes),
                     "d2h_bytes_per_step": int(k * (176 + 768 * 4)),
                     "last_step_split_ms": e2e_split, "host_wall_ms_per_step": list(e2e_step_ms),
-                    "note": "pinned host volume -> CreateCSIFT3D (H2D on the handle's stream, enqueued one step ahead) -> "
-                            "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors into one of two pinned buffers, enqueued "
-                            "with s3d_get_keypoints_async and collected with s3d_sync after the next volume's extraction; the last "
-                            "step's copy is collected before the timer stops); when the copy of the next volume is slower than one "
-                            "extraction the leg is bound by the host link (h2d_ms)"},
+                    "note": "pinned host volume -> CreateCSIFT3D (H2D on the handle's stream, enqueued one volume ahead) -> "
+                            "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors into pinned buffers, enqueued with "
+                            "s3d_get_keypoints_async and collected with s3d_sync after the next extraction); the steps are dealt to "
+                            "host_threads threads, each with its own handles, streams and result buffers; every volume's H2D and "
+                            "D2H complete before the timer stops; host_wall_ms_per_step = completion-to-completion times"},
             "gpu_launches": int(launches),
             "per_rank": per_rank,
             "roofline": roof,
