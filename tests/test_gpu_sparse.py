@@ -36,7 +36,10 @@ def _compare_sparse(s3d, r, sift, desc_cos=0.9999):
     wscale = np.abs(r.extrema["win"]).max(1, keepdims=True) + 1e-7
     assert (np.abs(kp["win"] - r.extrema["win"]) / wscale).max() < 2e-3
     ok = codes != -1            # eigen fields are only written past the weak-gradient test
-    np.testing.assert_allclose(kp["eigvalue"][ok], r.extrema["eigvalue"][ok], rtol=5e-4, atol=1e-10)
+    # eigenvalues of an FP32-summed tensor are conditioned by the tensor's scale (Weyl), not by their own size: the
+    # smallest one of a nearly singular tensor has no relative accuracy
+    escale = np.abs(r.extrema["eigvalue"][ok]).max(1, keepdims=True) + 1e-30
+    assert (np.abs(kp["eigvalue"][ok] - r.extrema["eigvalue"][ok]) / escale).max() < 5e-4
     ev_g = kp["eigvector"][ok].reshape(-1, 3, 3)
     ev_r = r.extrema["eigvector"][ok].reshape(-1, 3, 3)
     sep = np.abs(np.diff(r.extrema["eigvalue"][ok], axis=1)).min(1) / np.abs(r.extrema["eigvalue"][ok]).max(1)
