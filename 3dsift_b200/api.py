@@ -38,6 +38,49 @@ class S3DError(RuntimeError):
     pass
 
 
+def _rebuild_keypoints(raw, desc):
+    kp = np.frombuffer(bytearray(raw), dtype=KP_DTYPE).view(KeypointArray)
+    return _bind_descriptors(kp, desc, rows=None)
+
+
+def _bind_descriptors(kp, desc, rows):
+    """Point kp['desc'] at rows of `desc` (rows None: keep each record's row index relative to the old block)
+    and make `desc` live as long as kp (and every view / copy / slice of it)."""
+    kp = kp.view(KeypointArray)
+    if rows is None:
+        p = kp["desc"].astype(np.int64)
+        rows = (p - (int(p.min()) if len(p) else 0)) // (DESC_LENGTH * 4)
+    kp["desc"] = desc.ctypes.data + np.asarray(rows, dtype=np.uint64) * np.uint64(DESC_LENGTH * 4)
+    kp._desc_owner = desc
+    return kp
+
+
+class KeypointArray(np.ndarray):
+    """KP_DTYPE records whose `desc` pointers BORROW from a descriptor block (Keypoint::desc borrows from
+    CSIFT3D::global_descriptor, Src/cSIFT3D.cc:486,495).  The reference frees that block in ~CSIFT3D; here
+    the array (and every view, slice or copy of it) holds a strong reference to the block, so a helper that
+    returns only GetKeypoints() cannot leave dangling pointers, and pickling (all_gather_object) ships the
+    block along and re-points the records in the receiving process."""
+
+    _desc_owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._desc_owner = getattr(obj, "_desc_owner", None)
+
+    def __reduce__(self):
+        own = self._desc_owner
+        if own is None or self.dtype != KP_DTYPE:
+            return super().__reduce__()
+        flat = np.ascontiguousarray(self).reshape(-1)
+        base, n = own.ctypes.data, len(flat)
+        rows = (flat["desc"].astype(np.int64) - base) // (DESC_LENGTH * 4) if n else np.zeros(0, np.int64)
+        block = np.ascontiguousarray(own.reshape(-1, DESC_LENGTH)[rows]) if n else np.zeros((0, DESC_LENGTH), np.float32)
+        plain = flat.view(np.ndarray).copy()
+        plain["desc"] = np.arange(n, dtype=np.uint64) * np.uint64(DESC_LENGTH * 4)
+        return (_rebuild_keypoints, (plain.tobytes(), block))
+
+
 class s3d_params(C.Structure):
     _fields_ = [("num_kp_levels", C.c_int), ("sigma_default", C.c_float), ("sigma_n_default", C.c_float),
                 ("peak_thresh", C.c_float), ("max_eig_thres", C.c_float), ("corner_thresh", C.c_float),
@@ -111,16 +154,21 @@ def lib():
     L.s3d_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     ip = C.POINTER(C.c_int)
     L.s3d_slab_extent.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.c_int, ip]
-    L.s3d_slab_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
-    L.s3d_slab_local_max.argtypes = [vp, C.POINTER(C.c_float)]
-    L.s3d_slab_begin.argtypes = [vp, C.c_float]
-    L.s3d_slab_info.argtypes = [vp, ip, ip, ip]
-    L.s3d_slab_seed.argtypes = [vp, C.c_int]
-    L.s3d_slab_octave.argtypes = [vp, C.c_int]
+    L.s3d_slab_bounds.argtypes = [C.c_int, C.c_int, C.c_int, ip, ip]
+    L.s3d_slab_first_replicated.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), ip]
+    L.s3d_slab_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int, ip]
+    L.s3d_comm_unique_id.argtypes = [vp]
+    L.s3d_comm_create.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.s3d_comm_destroy.argtypes = [vp]
+    L.s3d_comm_destroy.restype = None
+    L.s3d_comm_info.argtypes = [vp, ip, ip, ip]
+    L.s3d_comm_traffic.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    L.s3d_slab_run.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
+    L.s3d_slab_gather.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.s3d_slab_phases.argtypes = [vp, C.POINTER(C.c_double * 8)]
+    L.s3d_extract_multi.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), ip, C.c_int, C.c_int, C.POINTER(vp)]
+    L.s3d_slab_info.argtypes = [vp, ip, ip, ip, ip]
     L.s3d_slab_level_buffer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), ip]
-    L.s3d_slab_get_maxima.argtypes = [vp, vp, C.c_int]
-    L.s3d_slab_set_maxima.argtypes = [vp, vp, C.c_int]
-    L.s3d_slab_finish.argtypes = [vp]
     _lib = L
     return L
 
@@ -258,7 +306,8 @@ class CSIFT3D:
         if isinstance(kp, np.ndarray):
             kp = kp[:n]
             desc = desc[:n]
-            kp["desc"] = desc.ctypes.data + np.arange(n, dtype=np.uint64) * (DESC_LENGTH * 4)
+            # the returned array keeps `desc` alive (the pointers must not outlive the block)
+            kp = _bind_descriptors(kp, desc, rows=np.arange(n))
         self._kp, self._desc = kp, desc
         return kp
 
@@ -410,6 +459,13 @@ def _desc_matrix(kps):
         if n == 0:
             return out
         p = kps["desc"].astype(np.uint64)
+        own = getattr(kps, "_desc_owner", None)
+        if own is None:
+            raise S3DError("keypoint records carry raw `desc` addresses but no owner of the descriptor block: pass the "
+                           "array returned by GetKeypoints() (or a slice / copy of it), or an n x 768 float32 matrix")
+        lo, hi = own.ctypes.data, own.ctypes.data + own.nbytes
+        if int(p.min()) < lo or int(p.max()) + DESC_LENGTH * 4 > hi:
+            raise S3DError("keypoint `desc` addresses lie outside the descriptor block they were bound to")
         if np.all(np.diff(p.astype(np.int64)) == DESC_LENGTH * 4):  # base + 768*i: one block copy
             C.memmove(out.ctypes.data, int(p[0]), n * DESC_LENGTH * 4)
         else:

@@ -26,6 +26,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=o
 
 UNITS = [
     ("s3d_extract.cu", ["-fmad=false"]),
+    ("s3d_slab.cu", []),
     ("s3d_match.cu", []),
     ("s3d_match_tc.cu", []),
     ("facade.cpp", []),
@@ -72,7 +73,7 @@ def build(force=False, verbose=False):
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
     if force or _stale(LIB, objs):
-        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda", "-lz"]
+        cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda", "-lz", "-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

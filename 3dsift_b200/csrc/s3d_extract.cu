@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "s3d_common.h"
+#include "s3d_ctx.h"
 #include "s3d_devcache.h"
 #include "s3d_kernels.cuh"
 
@@ -202,20 +203,17 @@ static void host_mesh(MeshConst* M) {
 // Extended-line table of a pass along an axis of length n (Src/cSIFT3D.cc:751-760): for tap
 // coordinate c = q = n-1+e the reference samples at c' = 2(n-1) - c - 0.1f, lo = (int)c',
 // frac = c' - lo.  Same FP32 operations as the reference (volatile: no wider evaluation).
-// A z-slab shard passes the GLOBAL line length and the global coordinate of its first local plane:
-// frac is "whatever FP32 gives" for c' (App. A.2), so it depends on the magnitude of n — a shard that
-// holds the top of the volume must blend with the global c' (and address il relative to its buffer).
-static Taps with_ext(const Taps& t0, int n, int n_glob = -1, int off = 0) {
+// frac is "whatever FP32 gives" for c' (App. A.2), so it depends on the magnitude of n: a z-slab shard always
+// passes the GLOBAL line length (its kernels address planes through a virtual origin, see blur_z).
+static Taps with_ext(const Taps& t0, int n) {
     Taps t = t0;
-    const bool top_is_global = n_glob > 0 && off + n == n_glob;
-    const int ng = top_is_global ? n_glob : n;
     for (int e = 0; e <= kMaxHW; e++) {
-        volatile float c = (float)(2 * (ng - 1));
-        c = c - (float)(ng - 1 + e);
+        volatile float c = (float)(2 * (n - 1));
+        c = c - (float)(n - 1 + e);
         c = c - 0.1f;
         int il = (int)c;
         volatile float fr = c - (float)il;
-        t.ext_il[e] = top_is_global ? il - off : il;
+        t.ext_il[e] = il;
         t.ext_frac[e] = fr;
     }
     return t;
@@ -253,12 +251,14 @@ static int pick_seg(int nx4, int n_other, int n) {
     return seg;
 }
 
+// March along an axis of (global) length n over the output positions [zlo, zhi); src/dst/prev/dog address position 0
+// of every line (a z-slab shard passes its local buffers offset to that virtual origin).
 template <int HW>
 static void launch_march(const float* src, float* dst, int nx, int n, ll st_m, int n_other, ll st_other, const Taps& t,
-                         ll total, const float* prev, float* dog, unsigned* slot, cudaStream_t st) {
+                         const float* prev, float* dog, unsigned* slot, cudaStream_t st, int zlo, int zhi) {
     const int nx4 = nx >> 2;
-    const int seg = pick_seg(nx4, n_other, n);
-    const int nseg = (n + seg - 1) / seg;
+    const int seg = pick_seg(nx4, n_other, zhi - zlo);
+    const int nseg = (zhi - zlo + seg - 1) / seg;
     ll threads = (ll)nx4 * n_other * nseg;
     // S3D_ZVAR: 0 = register-ring prefetch (blur_march_kernel), 1 = cp.async ring (blur_marchc_kernel, default)
     static const int zvar = [] { const char* e = getenv("S3D_ZVAR"); return (e && e[0] >= '0' && e[0] <= '1' && !e[1]) ? e[0] - '0' : 1; }();
@@ -266,87 +266,30 @@ static void launch_march(const float* src, float* dst, int nx, int n, ll st_m, i
     if (dog) {
         if (zvar == 0) {
             auto kfn = blur_march_kernel<HW, true>;
-            S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t, prev, dog, slot);
+            S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t, prev, dog, slot, zlo, zhi);
         } else {
             auto kfn = blur_marchc_kernel<HW, true>;
-            S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t, prev, dog, slot);
+            S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t, prev, dog, slot, zlo, zhi);
         }
     } else {
         if (zvar == 0) {
             auto kfn = blur_march_kernel<HW, false>;
             S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
-                       (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr);
+                       (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr, zlo, zhi);
         } else {
             auto kfn = blur_marchc_kernel<HW, false>;
             S3D_LAUNCH(kfn, blocks, 128, 0, st, src, dst, nx, n, st_m, n_other, st_other, seg, t,
-                       (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr);
+                       (const float*)nullptr, (float*)nullptr, (unsigned*)nullptr, zlo, zhi);
         }
     }
 }
 
-// ---- per-kernel-class device timing (params.profile) ---------------------------------------
-enum KCls { K_MAXABS, K_NORMALIZE, K_BLUR_X, K_BLUR_Y, K_BLUR_XY, K_BLUR_Z_DOG, K_BLUR_GENERIC, K_DOWNSAMPLE, K_DETECT, K_COMPACT,
-            K_ORIENT, K_ORIENT_EXACT, K_SURVIVORS, K_DESCRIBE, K_DESCRIBE_REDO, K_NCLS };
+// ---- per-kernel-class device timing (params.profile): s3d_ctx.h -------------------------------
 static const char* kClsName[K_NCLS] = {"maxabs", "normalize", "blur_x", "blur_y", "blur_xy", "blur_z_dog", "blur_generic", "downsample",
-                                       "detect", "compact", "orient", "orient_exact", "survivors", "describe", "describe_redo"};
-// Timing events are recycled through a per-device free list: a 512^3 step brackets ~120 launches, and creating and
-// destroying 240 events per step cost more host time than the small octaves' kernels take.
-struct EventPool {
-    std::mutex mu;
-    std::vector<cudaEvent_t> free_[64];
-    cudaEvent_t get(int dev) {
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            auto& f = free_[dev & 63];
-            if (!f.empty()) { cudaEvent_t e = f.back(); f.pop_back(); return e; }
-        }
-        cudaEvent_t e = nullptr;
-        cudaEventCreate(&e);
-        return e;
-    }
-    void put(int dev, cudaEvent_t e) {
-        std::lock_guard<std::mutex> lk(mu);
-        free_[dev & 63].push_back(e);
-    }
-};
-static EventPool g_event_pool;
-
-struct Prof {
-    bool on = false;
-    int dev = 0;
-    cudaStream_t st = nullptr;
-    struct Rec { int cls; cudaEvent_t a, b; double bytes; };
-    std::vector<Rec> recs;
-    double ms[K_NCLS] = {0};
-    long long cnt[K_NCLS] = {0};
-    double bytes[K_NCLS] = {0};
-    // (measured: letting back-to-back scopes share a boundary event saves 0.2 ms of a 19 ms step but charges the
-    // inter-kernel gaps to the next class - blur_xy +7 % - so every scope keeps its own two events)
-    void begin(int cls, double by) {
-        if (!on) return;
-        Rec r; r.cls = cls; r.bytes = by;
-        r.a = g_event_pool.get(dev); r.b = g_event_pool.get(dev);
-        cudaEventRecord(r.a, st);
-        recs.push_back(r);
-    }
-    void end() {
-        if (!on) return;
-        cudaEventRecord(recs.back().b, st);
-    }
-    void resolve() {  // after the stream has been synchronised
-        for (auto& r : recs) {
-            float t = 0;
-            if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.cls] += t; cnt[r.cls]++; bytes[r.cls] += r.bytes; }
-            g_event_pool.put(dev, r.a); g_event_pool.put(dev, r.b);
-        }
-        recs.clear();
-    }
-};
-struct ProfScope {
-    Prof* p;
-    ProfScope(Prof* p_, int cls, double by) : p(p_) { if (p) p->begin(cls, by); }
-    ~ProfScope() { if (p) p->end(); }
-};
+                                       "detect", "compact", "orient", "orient_exact", "survivors", "describe", "describe_redo", "blur_xyz"};
+EventPool g_event_pool;
+static_assert(sizeof(TapsH) == sizeof(Taps) && kCtxMaxOct == kMaxOct && kCtxMaxG == kMaxG && kCtxMaxHW == kMaxHW, "s3d_ctx.h mirrors");
+static inline const Taps& taps_of(const s3d_ctx* c, int i) { return reinterpret_cast<const Taps&>(c->taps[i]); }
 
 #define S3D_HW_SWITCH(hw, CALL)            \
     switch (hw) {                          \
@@ -359,16 +302,13 @@ struct ProfScope {
         default: break;                    \
     }
 
-// One separable pass.  variant 0 = generic kernel; 1 = fast kernels when eligible.
-// prev/dog/slot non-null fuses the DoG subtraction + max|DoG| (only meaningful on the last pass).
-// nz_glob / z_off (z passes of a z-slab shard): global plane count and global index of local plane 0.
+// One separable pass over a whole buffer of nx x ny x nz voxels.  variant 0 = generic kernel; 1 = fast kernels when
+// eligible.  prev/dog/slot non-null fuses the DoG subtraction + max|DoG| (only meaningful on the last pass).
 static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int axis, const Taps& t0, int variant,
-                      const float* prev, float* dog, unsigned* slot, cudaStream_t st, Prof* prof = nullptr, int nz_glob = -1,
-                      int z_off = 0) {
+                      const float* prev, float* dog, unsigned* slot, cudaStream_t st, Prof* prof = nullptr) {
     const ll total = (ll)nx * ny * nz;
     const int n = axis == 0 ? nx : (axis == 1 ? ny : nz);
-    const bool partial = axis == 2 && nz_glob > 0 && (z_off != 0 || nz != nz_glob);
-    const Taps t = partial ? with_ext(t0, n, nz_glob, z_off) : with_ext(t0, n);
+    const Taps t = with_ext(t0, n);
     const bool fast = variant == 1 && (nx % 4 == 0) && supported_fast_hw(t.hw) && n >= 2 * t.hw + 2 && total >= 4096 &&
                       !(axis == 0 && dog);
     // algorithmic bytes: read src + write dst (+ read prev + write dog on the fused pass)
@@ -376,7 +316,7 @@ static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int 
                  (dog ? 16.0 : 8.0) * (double)total);
     if (!fast) {
         S3D_LAUNCH(blur_generic_kernel, s3d_blocks((size_t)total, 256), 256, 0, st, src, dst, nx, ny, nz, axis, t, prev,
-                   dog, slot, partial ? nz_glob : 0, partial ? z_off : 0);
+                   dog, slot, 0, 0, 0, 0);
         return;
     }
     if (axis == 0) {
@@ -384,13 +324,46 @@ static void blur_pass(const float* src, float* dst, int nx, int ny, int nz, int 
         S3D_HW_SWITCH(t.hw, CALLX)
 #undef CALLX
     } else if (axis == 1) {
-#define CALLY(H) launch_march<H>(src, dst, nx, ny, (ll)nx, nz, (ll)nx * ny, t, total, prev, dog, slot, st)
+#define CALLY(H) launch_march<H>(src, dst, nx, ny, (ll)nx, nz, (ll)nx * ny, t, prev, dog, slot, st, 0, ny)
         S3D_HW_SWITCH(t.hw, CALLY)
 #undef CALLY
     } else {
-#define CALLZ(H) launch_march<H>(src, dst, nx, nz, (ll)nx * ny, ny, (ll)nx, t, total, prev, dog, slot, st)
+#define CALLZ(H) launch_march<H>(src, dst, nx, nz, (ll)nx * ny, ny, (ll)nx, t, prev, dog, slot, st, 0, nz)
         S3D_HW_SWITCH(t.hw, CALLZ)
 #undef CALLZ
+    }
+}
+
+// Z pass of a level whose LOCAL buffers (src = the X/Y-blurred planes, dst, prev, dog) hold global planes
+// [za, za + nzl) of a line of nz_glob planes, for the output planes [zlo, zhi).  The unsharded run has za = 0,
+// nzl = nz_glob, [zlo, zhi) = [0, nz_glob) and takes exactly the launches of blur_pass(axis 2).  A z-slab shard
+// needs src valid on [zlo - hw, zhi + hw) (clipped to the line; the mirror / blend of the reference's boundary rule
+// only reaches planes next to the line's own ends, which the shard at that end holds): the fast kernels address
+// the buffers through a virtual origin (global plane 0), the generic kernel through (gn, goff) with clamped fetches.
+static void blur_z(const float* src, float* dst, const float* prev, float* dog, unsigned* slot, int nx, int ny, int nz_glob,
+                   int za, int nzl, int zlo, int zhi, const Taps& t0, cudaStream_t st, Prof* prof) {
+    if (zhi <= zlo) return;
+    if (za == 0 && nzl == nz_glob && zlo == 0 && zhi == nz_glob) {
+        blur_pass(src, dst, nx, ny, nz_glob, 2, t0, 1, prev, dog, slot, st, prof);
+        return;
+    }
+    const size_t plane = (size_t)nx * ny;
+    const ll total = (ll)plane * (zhi - zlo);
+    const Taps t = with_ext(t0, nz_glob);
+    const bool fast = (nx % 4 == 0) && supported_fast_hw(t.hw) && nz_glob >= 2 * t.hw + 2 && (ll)plane * nz_glob >= 4096;
+    ProfScope ps(prof, fast ? K_BLUR_Z_DOG : K_BLUR_GENERIC, (dog ? 16.0 : 8.0) * (double)total);
+    if (fast) {
+        const ptrdiff_t off = (ptrdiff_t)za * (ptrdiff_t)plane;
+        const float* vs = src - off; float* vd = dst - off;
+        const float* vp = prev ? prev - off : nullptr; float* vg = dog ? dog - off : nullptr;
+#define CALLZ(H) launch_march<H>(vs, vd, nx, nz_glob, (ll)plane, ny, (ll)nx, t, vp, vg, slot, st, zlo, zhi)
+        S3D_HW_SWITCH(t.hw, CALLZ)
+#undef CALLZ
+    } else {
+        const int b0 = std::max(za, zlo - t.hw), b1 = std::min(za + nzl, zhi + t.hw);  // planes the launch touches
+        const size_t o = (size_t)(b0 - za) * plane;
+        S3D_LAUNCH(blur_generic_kernel, s3d_blocks(plane * (size_t)(b1 - b0), 256), 256, 0, st, src + o, dst + o, nx, ny, b1 - b0, 2, t,
+                   prev ? prev + o : nullptr, dog ? dog + o : nullptr, slot, nz_glob, b0, zlo, zhi);
     }
 }
 
@@ -439,64 +412,16 @@ static bool blur_xy_pass(const float* src, float* dst, int nx, int ny, int nz, c
     return true;
 }
 
-}  // namespace s3d
 
-using namespace s3d;
-
-// ---------------------------------------------------------------------------------------------
-struct s3d_ctx {
-    s3d_params prm;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    Prof prof;
-    int nx = 0, ny = 0, nz = 0;
-    size_t n0 = 0;
-    int noct = 0, G = 0, D = 0, L = 0;
-    int dims[kMaxOct][3];
-    size_t nvox[kMaxOct];
-    float sig[kMaxG];
-    Taps taps[kMaxG];
-    float* d_input = nullptr;       // normalised input (Host_Im)
-    std::vector<float*> gss, dog;   // device levels
-    float* d_tmp[2] = {nullptr, nullptr};
-    unsigned* d_slots = nullptr;    // [0] input max|v|, [1 + o*D + i] max|DoG(o,i)|
-    float* d_thres = nullptr;       // noct * L thresholds
-    MeshConst* d_mesh = nullptr;
-    // sparse stage
-    int n_extre = 0, n_kps = 0;
-    s3d_keypoint* d_extre = nullptr;
-    int* d_codes = nullptr;
-    int* d_xyz5 = nullptr;
-    s3d_keypoint* d_kps = nullptr;
-    float* d_desc = nullptr;
-    int n_rechecked = 0, n_flipped = 0;
-    int* d_redo = nullptr;          // [0] = count, [1..] = keypoint indices (freed in s3d_wait)
-    int n_desc_redo = 0;            // keypoints the fixed-point descriptor kernel handed to the FP32 one
-    bool ran = false, levels_alive = false, queued = false, h2d_pending = false, d2h_pending = false;
-    // z-slab sharding.  Unsharded: slab = false, za = p0 = 0, zb = p1 = nz_o.
-    // A shard OWNS global planes [p0[o], p1[o]) of octave o and keeps local buffers for planes
-    // [za[o], zb[o]) (owned + halo).  nz / dims[][2] / nvox[] stay the GLOBAL sizes.
-    bool slab = false;
-    int own0 = 0, own1 = 0, halo = 0;      // owned octave-0 planes, halo depth (planes, every octave)
-    int za[kMaxOct], zb[kMaxOct], p0[kMaxOct], p1[kMaxOct];
-    int stage = 0;                          // 0 created, 1 initialised, 2 + o = octave o done, 100 sparse done
-    int next_octave = 0;
-    size_t lvox(int o) const { return (size_t)dims[o][0] * dims[o][1] * (size_t)(zb[o] - za[o]); }
-    size_t plane(int o) const { return (size_t)dims[o][0] * dims[o][1]; }
-    cudaEvent_t ev[8];
-    bool ev_ok = false;
-    double timers[10] = {0};
-};
-
-static void free_levels(s3d_ctx* c) {
+// ---- context plumbing ---------------------------------------------------------------------------
+void free_levels(s3d_ctx* c) {
     for (auto& p : c->gss) if (p) { s3d::dev_free(p, c->stream); p = nullptr; }
     for (auto& p : c->dog) if (p) { s3d::dev_free(p, c->stream); p = nullptr; }
     for (int i = 0; i < 2; i++) if (c->d_tmp[i]) { s3d::dev_free(c->d_tmp[i], c->stream); c->d_tmp[i] = nullptr; }
     c->levels_alive = false;
 }
 
-static int ctx_common_init(s3d_ctx* c, int nx, int ny, int nz, const s3d_params* p) {
+int ctx_common_init(s3d_ctx* c, int nx, int ny, int nz, const s3d_params* p) {
     s3d_params def;
     s3d_default_params(&def);
     c->prm = p ? *p : def;
@@ -520,26 +445,45 @@ static int ctx_common_init(s3d_ctx* c, int nx, int ny, int nz, const s3d_params*
     c->prof.dev = c->device;
     for (int i = 0; i < 8; i++) S3D_CUDA(cudaEventCreate(&c->ev[i]));
     c->ev_ok = true;
+    host_sigmas(c->L, c->prm.sigma_default, c->prm.sigma_n_default, c->sig);
+    for (int i = 0; i < c->G; i++)
+        if (host_taps(c->sig[i], reinterpret_cast<Taps*>(&c->taps[i])) < 0)
+            return fail(S3D_ERR_ARG, "sigma %g needs more than %d taps per side", c->sig[i], kMaxHW);
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
+    S3D_CUDA(cudaMemsetAsync(c->d_slots, 0, 256 * sizeof(unsigned), c->stream));
+    return S3D_OK;
+}
+
+// data_scale (Src/cUtil.cc:536-564), first sweep: max|v| folded into d_slots[0]
+int stage_input_max(s3d_ctx* c, const float* d, size_t n) {
+    if (n == 0) return S3D_OK;
+    const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks(n / 4 + 1, 256), 148 * 16);
+    ProfScope ps(&c->prof, K_MAXABS, 4.0 * n);
+    S3D_LAUNCH(maxabs_kernel, grid, 256, 0, c->stream, d, n, c->d_slots);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+// second sweep: v / max (IEEE division per voxel)
+int stage_input_normalize(s3d_ctx* c, const float* src, float* dst, size_t n) {
+    if (n == 0) return S3D_OK;
+    const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks(n / 4 + 1, 256), 148 * 16);
+    ProfScope ps(&c->prof, K_NORMALIZE, 8.0 * n);
+    S3D_LAUNCH(normalize_kernel, grid, 256, 0, c->stream, src, dst, n, c->d_slots);
+    S3D_CUDA(cudaGetLastError());
     return S3D_OK;
 }
 
 static int ctx_normalize(s3d_ctx* c, const float* d_raw) {
     // ctor: data_scale (Src/cUtil.cc:536-564)
     S3D_CUDA(s3d::dev_alloc((void**)&c->d_input, c->n0 * sizeof(float), c->stream));
-    S3D_CUDA(s3d::dev_alloc((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
-    S3D_CUDA(cudaMemsetAsync(c->d_slots, 0, 256 * sizeof(unsigned), c->stream));
-    const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks(c->n0 / 4 + 1, 256), 148 * 16);
-    {
-        ProfScope ps(&c->prof, K_MAXABS, 4.0 * c->n0);
-        S3D_LAUNCH(maxabs_kernel, grid, 256, 0, c->stream, d_raw, c->n0, c->d_slots);
-    }
-    {
-        ProfScope ps(&c->prof, K_NORMALIZE, 8.0 * c->n0);
-        S3D_LAUNCH(normalize_kernel, grid, 256, 0, c->stream, d_raw, c->d_input, c->n0, c->d_slots);
-    }
-    S3D_CUDA(cudaGetLastError());
-    return S3D_OK;
+    S3D_TRY(stage_input_max(c, d_raw, c->n0));
+    return stage_input_normalize(c, d_raw, c->d_input, c->n0);
 }
+
+}  // namespace s3d
+
+using namespace s3d;
 
 extern "C" {
 
@@ -653,38 +597,59 @@ void s3d_destroy(s3d_handle c) {
     if (c->stream) {
         cudaSetDevice(c->device);
         free_levels(c);
-        void* ptrs[] = {c->d_input, c->d_slots, c->d_thres, c->d_mesh, c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc, c->d_redo};
+        void* ptrs[] = {c->d_input, c->d_slots, c->d_thres, c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc, c->d_redo};
         for (void* q : ptrs) if (q) s3d::dev_free(q, c->stream);
         cudaStreamSynchronize(c->stream);
         c->prof.resolve();
         if (c->ev_ok) for (int i = 0; i < 8; i++) cudaEventDestroy(c->ev[i]);
+        for (auto& e : c->ph_ev) if (e) cudaEventDestroy(e);
         if (c->own_stream) cudaStreamDestroy(c->stream);
     }
     delete c;
 }
 
-// Initialize (Src/cSIFT3D.cc:237-266) + Build_Gaussian_Scale_Space (:268-319) +
-// Build_DOG_Scale_Space (:346-360; fused into the Z pass) + Detect_KeyPoints (:362-425) +
-// Assign_Orientation (:427-482) + Extract_Description (:484-502).
+}  // extern "C"
+
+namespace s3d {
+
 // ---- the pipeline in stages (shared by the unsharded run and the z-slab shards) ----------------
 //
 // Initialize (Src/cSIFT3D.cc:237-266) -> per octave Build_Gaussian_Scale_Space (:268-319) with
 // Build_DOG_Scale_Space (:346-360) fused into the Z pass -> Detect_KeyPoints (:362-425) ->
 // Assign_Orientation (:427-482) -> Extract_Description (:484-502).
 
-static int halo_for(const s3d_ctx* c) {
-    // planes a shard needs beyond its owned range: the blur chain must leave every DoG level valid
-    // on owned +-1 (detection neighbours), and the descriptor window reaches ceil(r/u)+1 planes
-    // (r = 2*7.0711*scale, Src/cSIFT3D.cc:1155-1156, clamped windows :1182-1198, +1 for the gradient)
-    int cum = 0;
-    for (int i = 0; i < c->G; i++) cum += c->taps[i].hw;
-    const int blur_need = 1 + cum + c->G;  // low side needs 1 + sum(hw); high side one more plane per level
-    const float ratio = host_level_scale(0, c->L, c->L, c->prm.sigma_default);
-    const int desc_need = (int)ceilf(2.0f * 7.071067812f * ratio) + 2;
-    return std::max(blur_need, desc_need);
+// Planes of its own octave that the windows of keypoint level `lvl` reach beyond the keypoint's plane:
+// r = 2*7.0711*scale (Src/cSIFT3D.cc:1155-1156), clamped windows :1182-1198, +1 for the central difference, +1 for ceil
+// (the orientation window, r = 4.5*scale :27-28,:915, is smaller).  scale/unit does not depend on the octave.
+int slab_window_halo(const s3d_ctx* c, int lvl) {
+    const float ratio = host_level_scale(0, lvl, c->L, c->prm.sigma_default);
+    return (int)ceilf(2.0f * 7.071067812f * ratio) + 2;
 }
 
-static int stage_init(s3d_ctx* c) {
+static int halo_for(const s3d_ctx* c) {
+    // local planes a shard keeps beyond its owned range: the source halo of the widest blur (hw + 1: every level is
+    // produced on owned +-1 so that the DoG neighbours of detection are local) and the widest descriptor window
+    int hwmax = 0;
+    for (int i = 0; i < c->G; i++) hwmax = std::max(hwmax, c->taps[i].hw);
+    return std::max(hwmax + 2, slab_window_halo(c, c->L));
+}
+
+int slab_halo_from_params(const s3d_params* p, int* halo) {
+    s3d_ctx tmp;
+    s3d_params def;
+    s3d_default_params(&def);
+    tmp.prm = p ? *p : def;
+    tmp.L = tmp.prm.num_kp_levels;
+    if (tmp.L < 1 || tmp.L + 3 > kMaxG) return fail(S3D_ERR_ARG, "num_kp_levels %d unsupported", tmp.L);
+    tmp.G = tmp.L + 3;
+    host_sigmas(tmp.L, tmp.prm.sigma_default, tmp.prm.sigma_n_default, tmp.sig);
+    for (int i = 0; i < tmp.G; i++)
+        if (host_taps(tmp.sig[i], reinterpret_cast<Taps*>(&tmp.taps[i])) < 0) return fail(S3D_ERR_ARG, "sigma %g too wide", tmp.sig[i]);
+    *halo = halo_for(&tmp);
+    return S3D_OK;
+}
+
+int stage_init(s3d_ctx* c) {
     if (c->stage != 0) return fail(S3D_ERR_STATE, "already initialised (KpSiftAlgorithm is single-shot)");
     cudaStream_t st = c->stream;
     S3D_CUDA(cudaSetDevice(c->device));
@@ -709,12 +674,10 @@ static int stage_init(s3d_ctx* c) {
             nx /= 2; ny /= 2; nz /= 2;  // Src/cUtil.cc:219-221
         }
     }
-    host_sigmas(L, c->prm.sigma_default, c->prm.sigma_n_default, c->sig);
-    for (int i = 0; i < G; i++)
-        if (host_taps(c->sig[i], &c->taps[i]) < 0)
-            return fail(S3D_ERR_ARG, "sigma %g needs more than %d taps per side", c->sig[i], kMaxHW);
+    if (c->slab) c->halo = halo_for(c);
     for (int o = 0; o < c->noct; o++) {
         const int nzo = c->dims[o][2];
+        c->full[o] = false;
         if (!c->slab) {
             c->p0[o] = c->za[o] = 0; c->p1[o] = c->zb[o] = nzo;
         } else {
@@ -722,13 +685,14 @@ static int stage_init(s3d_ctx* c) {
             const int sh = 1 << o;
             c->p0[o] = std::min(nzo, (c->own0 + sh - 1) >> o);
             c->p1[o] = std::min(nzo, (c->own1 + sh - 1) >> o);
-            if (o > 0) {  // nz/2 truncation can drop the last plane of an odd level
-                c->p0[o] = std::min(c->p0[o], nzo);
-                c->p1[o] = std::min(c->p1[o], nzo);
+            if (o >= c->first_full) {  // replicated octave: every shard holds all planes
+                c->full[o] = true;
+                c->za[o] = 0; c->zb[o] = nzo;
+            } else {
+                c->za[o] = std::max(0, c->p0[o] - c->halo);
+                c->zb[o] = std::min(nzo, c->p1[o] + c->halo);
+                if (c->p1[o] <= c->p0[o]) { c->za[o] = c->zb[o] = c->p0[o]; }  // owns nothing here
             }
-            c->za[o] = std::max(0, c->p0[o] - c->halo);
-            c->zb[o] = std::min(nzo, c->p1[o] + c->halo);
-            if (c->p1[o] <= c->p0[o]) { c->za[o] = c->zb[o] = c->p0[o]; }  // owns nothing here
         }
     }
     c->gss.assign((size_t)c->noct * G, nullptr);
@@ -746,32 +710,41 @@ static int stage_init(s3d_ctx* c) {
             for (int i = 0; i < G; i++) S3D_CUDA(cudaMemsetAsync(c->gss[o * G + i], 0xFF, c->lvox(o) * sizeof(float), st));
             for (int i = 0; i < D; i++) S3D_CUDA(cudaMemsetAsync(c->dog[o * D + i], 0xFF, c->lvox(o) * sizeof(float), st));
         }
+        for (int i = 0; i < 2; i++) S3D_CUDA(cudaMemsetAsync(c->d_tmp[i], 0xFF, tmp_elems * sizeof(float), st));
     }
     c->levels_alive = true;
     S3D_CUDA(s3d::dev_alloc((void**)&c->d_thres, sizeof(float) * c->noct * L, st));
     {
-        MeshConst hm;
-        host_mesh(&hm);
-        S3D_CUDA(s3d::dev_alloc((void**)&c->d_mesh, sizeof(MeshConst), st));
-        S3D_CUDA(cudaMemcpyAsync(c->d_mesh, &hm, sizeof(MeshConst), cudaMemcpyHostToDevice, st));
-        S3D_CUDA(cudaStreamSynchronize(st));  // hm is a stack object
+        // the icosahedron table is the same for every handle: built and uploaded once per device, from a buffer that
+        // outlives the copy (no stream synchronisation on the extraction path)
+        static std::mutex mu;
+        static MeshConst* dev_mesh[64] = {nullptr};
+        static MeshConst host_copy;
+        static bool host_ready = false;
+        std::lock_guard<std::mutex> lk(mu);
+        if (!host_ready) { host_mesh(&host_copy); host_ready = true; }
+        MeshConst*& dm = dev_mesh[c->device & 63];
+        if (!dm) {
+            S3D_CUDA(cudaMalloc((void**)&dm, sizeof(MeshConst)));
+            S3D_CUDA(cudaMemcpy(dm, &host_copy, sizeof(MeshConst), cudaMemcpyHostToDevice));
+        }
+        c->d_mesh = dm;  // shared, never freed
     }
     S3D_CUDA(cudaEventRecord(c->ev[1], st));
     c->stage = 1;
-    c->next_octave = 0;
     return S3D_OK;
 }
 
-// Octave seed = even-index decimation of level L of the previous octave (:311), owned planes only
-// (a shard's halo planes of the seed come from their owners, s3d_slab_level_buffer + exchange).
-static int stage_seed(s3d_ctx* c, int o) {
+// Octave seed = even-index decimation of level L of the previous octave (:311) for planes [k0, k1) of octave o
+// (a shard: its owned planes; halo planes of the seed come from their owners, s3d_slab.cu).
+int stage_seed(s3d_ctx* c, int o, int k0, int k1) {
     cudaStream_t st = c->stream;
     const int L = c->L, G = c->G;
-    const int nown = c->p1[o] - c->p0[o];
+    const int nown = k1 - k0;
     if (o < 1 || nown <= 0) return S3D_OK;
     const int nx = c->dims[o][0], ny = c->dims[o][1];
-    const float* src = c->gss[(o - 1) * G + L] + (size_t)(2 * c->p0[o] - c->za[o - 1]) * c->plane(o - 1);
-    float* dst = c->gss[o * G] + (size_t)(c->p0[o] - c->za[o]) * c->plane(o);
+    const float* src = c->gss[(o - 1) * G + L] + (size_t)(2 * k0 - c->za[o - 1]) * c->plane(o - 1);
+    float* dst = c->gss[o * G] + (size_t)(k0 - c->za[o]) * c->plane(o);
     const size_t nout = (size_t)nown * c->plane(o);
     ProfScope ps(&c->prof, K_DOWNSAMPLE, 8.0 * nout);
     S3D_LAUNCH(downsample_kernel, s3d_blocks(nout, 256), 256, 0, st, src, c->dims[o - 1][0], c->dims[o - 1][1], dst, nx, ny, nown);
@@ -779,44 +752,34 @@ static int stage_seed(s3d_ctx* c, int o) {
     return S3D_OK;
 }
 
-// Levels of one octave over the local planes [za, zb): X -> Y -> Z (:609-617); the Z pass of level
-// i >= 1 also emits DoG[i-1] = G[i-1] - G[i] and (unsharded) folds max|DoG| into its slot.  A shard
-// takes the maxima over its OWNED planes only (halo planes hold partial results) with maxabs_kernel.
-static int stage_octave(s3d_ctx* c, int o) {
+// Level i of octave o on the output planes [zlo, zhi): X -> Y -> Z (:609-617); the Z pass of level i >= 1 also emits
+// DoG[i-1] = G[i-1] - G[i] on those planes and folds max|DoG| over them into its slot.  The X/Y passes are plane-local
+// and run on the planes the Z pass reads, [zlo - hw, zhi + hw) clipped to the level; the source must be valid there.
+int stage_level(s3d_ctx* c, int o, int i, int zlo, int zhi) {
     cudaStream_t st = c->stream;
-    const int L = c->L, G = c->G, D = c->D;
-    (void)L;
-    const int nx = c->dims[o][0], ny = c->dims[o][1], nz = c->zb[o] - c->za[o];
-    if (nz <= 0) return S3D_OK;
-    unsigned* scratch_slot = c->d_slots + 255;  // sink for the fused max of a shard's Z passes
-    for (int i = 0; i < G; i++) {
-        if (i == 0 && o > 0) continue;  // seed already in place
-        float* dst = c->gss[o * G + i];
-        const float* src = (o == 0 && i == 0) ? c->d_input : c->gss[o * G + i - 1];
-        const Taps& t = c->taps[i];
-        if (!blur_xy_pass(src, c->d_tmp[1], nx, ny, nz, t, st, &c->prof)) {
-            blur_pass(src, c->d_tmp[0], nx, ny, nz, 0, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
-            blur_pass(c->d_tmp[0], c->d_tmp[1], nx, ny, nz, 1, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
-        }
-        if (i >= 1) {
-            unsigned* slot = c->d_slots + 1 + o * D + i - 1;
-            blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, src, c->dog[o * D + i - 1], c->slab ? scratch_slot : slot, st,
-                      &c->prof, c->dims[o][2], c->za[o]);
-            if (c->slab && c->p1[o] > c->p0[o]) {
-                const size_t n = (size_t)(c->p1[o] - c->p0[o]) * c->plane(o);
-                const float* own = c->dog[o * D + i - 1] + (size_t)(c->p0[o] - c->za[o]) * c->plane(o);
-                ProfScope ps(&c->prof, K_MAXABS, 4.0 * n);
-                S3D_LAUNCH(maxabs_kernel, (unsigned)std::min<size_t>(s3d_blocks(n / 4 + 1, 256), 148 * 16), 256, 0, st, own, n, slot);
-            }
-        } else {
-            blur_pass(c->d_tmp[1], dst, nx, ny, nz, 2, t, 1, nullptr, nullptr, nullptr, st, &c->prof, c->dims[o][2], c->za[o]);
-        }
+    const int G = c->G, D = c->D;
+    const int nx = c->dims[o][0], ny = c->dims[o][1], nzg = c->dims[o][2];
+    const int za = c->za[o], nzl = c->zb[o] - c->za[o];
+    if (zhi <= zlo || nzl <= 0) return S3D_OK;
+    if (i == 0 && o > 0) return S3D_OK;  // the seed is produced by stage_seed
+    const Taps& t = taps_of(c, i);
+    float* dst = c->gss[o * G + i];
+    const float* src = (o == 0 && i == 0) ? c->d_input : c->gss[o * G + i - 1];
+    const int x0 = std::max(std::max(0, za), zlo - t.hw), x1 = std::min(std::min(nzg, za + nzl), zhi + t.hw);
+    const size_t off = (size_t)(x0 - za) * c->plane(o);
+    if (!blur_xy_pass(src + off, c->d_tmp[1] + off, nx, ny, x1 - x0, t, st, &c->prof)) {
+        blur_pass(src + off, c->d_tmp[0] + off, nx, ny, x1 - x0, 0, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
+        blur_pass(c->d_tmp[0] + off, c->d_tmp[1] + off, nx, ny, x1 - x0, 1, t, 1, nullptr, nullptr, nullptr, st, &c->prof);
     }
+    if (i >= 1)
+        blur_z(c->d_tmp[1], dst, src, c->dog[o * D + i - 1], c->d_slots + 1 + o * D + i - 1, nx, ny, nzg, za, nzl, zlo, zhi, t, st, &c->prof);
+    else
+        blur_z(c->d_tmp[1], dst, nullptr, nullptr, nullptr, nx, ny, nzg, za, nzl, zlo, zhi, t, st, &c->prof);
     S3D_CUDA(cudaGetLastError());
     return S3D_OK;
 }
 
-static int stage_sparse(s3d_ctx* c) {
+int stage_sparse(s3d_ctx* c) {
     cudaStream_t st = c->stream;
     const int L = c->L, G = c->G, D = c->D;
     S3D_CUDA(cudaEventRecord(c->ev[2], st));
@@ -961,7 +924,7 @@ static int stage_sparse(s3d_ctx* c) {
         if (path == 1) {  // FP32 staged/ordered accumulation for every keypoint
             ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
             S3D_LAUNCH(describe_kernel<false>, c->n_kps, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, c->n_kps, tab,
-                       c->d_mesh, c->d_kps, c->d_desc, (const int*)nullptr, (const int*)nullptr, (int*)nullptr, (int*)nullptr, 0.0f);
+                       (const MeshConst*)c->d_mesh, c->d_kps, c->d_desc, (const int*)nullptr, (const int*)nullptr, (int*)nullptr, (int*)nullptr, 0.0f);
         } else {
             // fixed-point atomics for all; the (normally empty) list of keypoints whose scale estimate was
             // too low is redone in FP32 — its grid is sized for the worst case and reads the count on the device
@@ -970,12 +933,12 @@ static int stage_sparse(s3d_ctx* c) {
             {
                 ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
                 S3D_LAUNCH(describe_kernel<true>, c->n_kps, kDescWarps * 32, sizeof(DescSmemQ), st, c->d_extre, d_surv, c->n_kps, tab,
-                           c->d_mesh, c->d_kps, c->d_desc, (const int*)d_order, (const int*)nullptr, d_redo + 1, d_redo,
+                           (const MeshConst*)c->d_mesh, c->d_kps, c->d_desc, (const int*)d_order, (const int*)nullptr, d_redo + 1, d_redo,
                            path == 2 ? 0.02f : kQMargin);
             }
             ProfScope ps(&c->prof, K_DESCRIBE_REDO, 0.0);
             S3D_LAUNCH(describe_kernel<false>, c->n_kps, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, c->n_kps, tab,
-                       c->d_mesh, c->d_kps, c->d_desc, (const int*)(d_redo + 1), (const int*)d_redo, (int*)nullptr, (int*)nullptr, 0.0f);
+                       (const MeshConst*)c->d_mesh, c->d_kps, c->d_desc, (const int*)(d_redo + 1), (const int*)d_redo, (int*)nullptr, (int*)nullptr, 0.0f);
             c->d_redo = d_redo;  // the count is read in s3d_wait
             d_redo = nullptr;
         }
@@ -993,13 +956,17 @@ static int stage_sparse(s3d_ctx* c) {
     return S3D_OK;
 }
 
+}  // namespace s3d
+
+extern "C" {
+
 static int run_impl(s3d_ctx* c) {
     if (c->ran || c->stage != 0) return fail(S3D_ERR_STATE, "s3d_run called twice on one handle (KpSiftAlgorithm is single-shot)");
-    if (c->slab) return fail(S3D_ERR_STATE, "a z-slab shard is driven stage by stage (s3d_slab_*), not by s3d_run");
+    if (c->slab) return fail(S3D_ERR_STATE, "a z-slab shard is driven by s3d_slab_run / s3d_extract_multi, not by s3d_run");
     S3D_TRY(stage_init(c));
     for (int o = 0; o < c->noct; o++) {
-        S3D_TRY(stage_seed(c, o));
-        S3D_TRY(stage_octave(c, o));
+        S3D_TRY(stage_seed(c, o, 0, c->dims[o][2]));
+        for (int i = 0; i < c->G; i++) S3D_TRY(stage_level(c, o, i, 0, c->dims[o][2]));
     }
     return stage_sparse(c);
 }
@@ -1014,6 +981,7 @@ int s3d_wait(s3d_handle c) {
     clear_error();
     if (!c) return fail(S3D_ERR_ARG, "null handle");
     if (!c->queued) return fail(S3D_ERR_STATE, "s3d_wait before s3d_run_async");
+    S3D_CUDA(cudaSetDevice(c->device));
     S3D_CUDA(cudaStreamSynchronize(c->stream));
     if (c->d_redo) {
         S3D_CUDA(cudaMemcpy(&c->n_desc_redo, c->d_redo, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1043,26 +1011,7 @@ int s3d_run(s3d_handle c) {
     return s3d_wait(c);
 }
 
-// ---- z-slab shards ---------------------------------------------------------
-// One handle per shard (one process per GPU, or several logical shards on one device).  The caller
-// drives the stages in lockstep over all shards and moves planes between the shards' level buffers
-// (s3d_slab_level_buffer) and scalars (maxima) between the stages: NCCL send/recv + all-reduce in
-// 3dsift_b200/dist.py.  Every stage only enqueues work on the handle's stream unless noted.
-
-static int slab_halo_from_params(const s3d_params* p, int* halo) {
-    s3d_ctx tmp;
-    s3d_params def;
-    s3d_default_params(&def);
-    tmp.prm = p ? *p : def;
-    tmp.L = tmp.prm.num_kp_levels;
-    if (tmp.L < 1 || tmp.L + 3 > kMaxG) return fail(S3D_ERR_ARG, "num_kp_levels %d unsupported", tmp.L);
-    tmp.G = tmp.L + 3;
-    host_sigmas(tmp.L, tmp.prm.sigma_default, tmp.prm.sigma_n_default, tmp.sig);
-    for (int i = 0; i < tmp.G; i++)
-        if (host_taps(tmp.sig[i], &tmp.taps[i]) < 0) return fail(S3D_ERR_ARG, "sigma %g too wide", tmp.sig[i]);
-    *halo = halo_for(&tmp);
-    return S3D_OK;
-}
+// ---- z-slab shards: plane bookkeeping; the orchestration is in s3d_slab.cu ------------------
 
 int s3d_slab_extent(int nz, int own0, int own1, const s3d_params* p, int octave, int* out4) {
     clear_error();
@@ -1079,93 +1028,18 @@ int s3d_slab_extent(int nz, int own0, int own1, const s3d_params* p, int octave,
     return S3D_OK;
 }
 
-int s3d_slab_create(const float* vol_ext, int on_device, int nx, int ny, int nz, int own0, int own1, const s3d_params* p,
-                    s3d_handle* out) {
-    clear_error();
-    if (!vol_ext || !out || own0 < 0 || own1 <= own0 || own1 > nz) return fail(S3D_ERR_ARG, "bad slab arguments");
-    s3d_ctx* c = new s3d_ctx();
-    int r = ctx_common_init(c, nx, ny, nz, p);
-    if (r == S3D_OK) r = slab_halo_from_params(&c->prm, &c->halo);
-    if (r != S3D_OK) { s3d_destroy(c); return r; }
-    c->slab = true;
-    c->own0 = own0; c->own1 = own1;
-    const int za = std::max(0, own0 - c->halo), zb = std::min(nz, own1 + c->halo);
-    const size_t plane = (size_t)nx * ny, nloc = plane * (size_t)(zb - za);
-    auto body = [&]() -> int {
-        // d_input first holds the raw local planes; s3d_slab_begin normalises them in place
-        S3D_CUDA(s3d::dev_alloc((void**)&c->d_input, nloc * sizeof(float), c->stream));
-        S3D_CUDA(s3d::dev_alloc((void**)&c->d_slots, 256 * sizeof(unsigned), c->stream));
-        S3D_CUDA(cudaMemsetAsync(c->d_slots, 0, 256 * sizeof(unsigned), c->stream));
-        S3D_CUDA(cudaMemcpyAsync(c->d_input, vol_ext, nloc * sizeof(float), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                 c->stream));
-        const size_t nown = plane * (size_t)(own1 - own0);
-        ProfScope ps(&c->prof, K_MAXABS, 4.0 * nown);
-        S3D_LAUNCH(maxabs_kernel, (unsigned)std::min<size_t>(s3d_blocks(nown / 4 + 1, 256), 148 * 16), 256, 0, c->stream,
-                   c->d_input + plane * (size_t)(own0 - za), nown, c->d_slots);
-        S3D_CUDA(cudaGetLastError());
-        S3D_CUDA(cudaStreamSynchronize(c->stream));  // `vol_ext` may be released by the caller
-        return S3D_OK;
-    };
-    r = body();
-    if (r != S3D_OK) { s3d_destroy(c); return r; }
-    *out = c;
-    return S3D_OK;
-}
-
-int s3d_slab_local_max(s3d_handle c, float* mx) {
-    clear_error();
-    if (!c || !mx || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
-    S3D_CUDA(cudaSetDevice(c->device));
-    S3D_CUDA(cudaMemcpyAsync(mx, c->d_slots, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    S3D_CUDA(cudaStreamSynchronize(c->stream));
-    return S3D_OK;
-}
-
-int s3d_slab_begin(s3d_handle c, float global_max) {
-    clear_error();
+int s3d_slab_info(s3d_handle c, int* noct, int* halo, int* levels_per_octave, int* first_replicated_octave) {
     if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
-    if (c->stage != 0) return fail(S3D_ERR_STATE, "s3d_slab_begin called twice");
-    S3D_CUDA(cudaSetDevice(c->device));
-    S3D_CUDA(cudaMemcpyAsync(c->d_slots, &global_max, sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    S3D_CUDA(cudaStreamSynchronize(c->stream));  // global_max is a stack value
-    const int za = std::max(0, c->own0 - c->halo), zb = std::min(c->nz, c->own1 + c->halo);
-    const size_t nloc = (size_t)c->nx * c->ny * (size_t)(zb - za);
-    {
-        ProfScope ps(&c->prof, K_NORMALIZE, 8.0 * nloc);
-        S3D_LAUNCH(normalize_kernel, (unsigned)std::min<size_t>(s3d_blocks(nloc / 4 + 1, 256), 148 * 16), 256, 0, c->stream,
-                   c->d_input, c->d_input, nloc, c->d_slots);
-    }
-    S3D_TRY(stage_init(c));
-    return stage_octave(c, 0);
-}
-
-int s3d_slab_info(s3d_handle c, int* noct, int* halo, int* levels_per_octave) {
-    if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
-    if (c->stage < 1) return fail(S3D_ERR_STATE, "s3d_slab_begin first");
+    if (c->stage < 1) return fail(S3D_ERR_STATE, "the shard has not been initialised");
     if (noct) *noct = c->noct;
     if (halo) *halo = c->halo;
     if (levels_per_octave) *levels_per_octave = c->G;
+    if (first_replicated_octave) *first_replicated_octave = std::min(c->first_full, c->noct);
     return S3D_OK;
 }
 
-int s3d_slab_seed(s3d_handle c, int octave) {
-    clear_error();
-    if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
-    if (c->stage < 1 || octave < 1 || octave >= c->noct) return fail(S3D_ERR_STATE, "bad octave / order");
-    S3D_CUDA(cudaSetDevice(c->device));
-    return stage_seed(c, octave);
-}
-
-int s3d_slab_octave(s3d_handle c, int octave) {
-    clear_error();
-    if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
-    if (c->stage < 1 || octave < 1 || octave >= c->noct) return fail(S3D_ERR_STATE, "bad octave / order");
-    S3D_CUDA(cudaSetDevice(c->device));
-    return stage_octave(c, octave);
-}
-
 int s3d_slab_level_buffer(s3d_handle c, int which, int idx, float** d_ptr, int* ext4) {
-    if (!c || !c->slab || !d_ptr || !ext4) return fail(S3D_ERR_ARG, "bad argument");
+    if (!c || !d_ptr || !ext4) return fail(S3D_ERR_ARG, "bad argument");
     if (c->stage < 1 || !c->levels_alive) return fail(S3D_ERR_STATE, "levels not allocated");
     const int per = which == 0 ? c->G : c->D;
     if (which < 0 || which > 1 || idx < 0 || idx >= c->noct * per) return fail(S3D_ERR_ARG, "level index out of range");
@@ -1173,37 +1047,6 @@ int s3d_slab_level_buffer(s3d_handle c, int which, int idx, float** d_ptr, int* 
     *d_ptr = which == 0 ? c->gss[idx] : c->dog[idx];
     ext4[0] = c->za[o]; ext4[1] = c->zb[o]; ext4[2] = c->p0[o]; ext4[3] = c->p1[o];
     return S3D_OK;
-}
-
-int s3d_slab_get_maxima(s3d_handle c, float* out, int n) {
-    clear_error();
-    if (!c || !c->slab || !out) return fail(S3D_ERR_ARG, "bad argument");
-    if (c->stage < 1) return fail(S3D_ERR_STATE, "s3d_slab_begin first");
-    n = std::min(n, c->noct * c->D);
-    S3D_CUDA(cudaSetDevice(c->device));
-    S3D_CUDA(cudaMemcpyAsync(out, c->d_slots + 1, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
-    S3D_CUDA(cudaStreamSynchronize(c->stream));
-    return S3D_OK;
-}
-
-int s3d_slab_set_maxima(s3d_handle c, const float* in, int n) {
-    clear_error();
-    if (!c || !c->slab || !in) return fail(S3D_ERR_ARG, "bad argument");
-    if (c->stage < 1) return fail(S3D_ERR_STATE, "s3d_slab_begin first");
-    n = std::min(n, c->noct * c->D);
-    S3D_CUDA(cudaSetDevice(c->device));
-    S3D_CUDA(cudaMemcpyAsync(c->d_slots + 1, in, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
-    S3D_CUDA(cudaStreamSynchronize(c->stream));
-    return S3D_OK;
-}
-
-int s3d_slab_finish(s3d_handle c) {
-    clear_error();
-    if (!c || !c->slab) return fail(S3D_ERR_ARG, "not a slab handle");
-    if (c->stage != 1) return fail(S3D_ERR_STATE, "s3d_slab_finish out of order");
-    S3D_CUDA(cudaSetDevice(c->device));
-    S3D_TRY(stage_sparse(c));
-    return s3d_wait(c);
 }
 
 int s3d_num_octaves(s3d_handle c, int* n) {

@@ -158,16 +158,18 @@ __global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) blur_generic_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
                                                            int ny, int nz, int axis, Taps t,
                                                            const float* __restrict__ prev, float* __restrict__ dog,
-                                                           unsigned* maxslot, int gn, int goff) {
+                                                           unsigned* maxslot, int gn, int goff, int olo, int ohi) {
     // gn > 0: the buffer holds planes [goff, goff+nz) of a z line of gn planes (a z-slab shard whose
     // local extent is not the whole line).  The boundary rule is then evaluated in GLOBAL coordinates
     // (its FP32 blend fraction depends on the magnitude of the coordinate) and samples are fetched
-    // from the local planes, clamped — clamped samples only feed planes inside the shard's halo margin.
+    // from the local planes (clamped: outputs whose taps would leave the buffer are not requested).
+    // Only the outputs on global planes [olo, ohi) are produced.
     const ll total = (ll)nx * ny * nz;
     const ll idx = (ll)blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.0f;
-    if (idx < total) {
-        const int x = (int)(idx % nx), y = (int)((idx / nx) % ny), z = (int)(idx / ((ll)nx * ny));
+    const int zq = (int)(idx / ((ll)nx * ny));
+    if (idx < total && !(gn > 0 && axis == 2 && (zq + goff < olo || zq + goff >= ohi))) {
+        const int x = (int)(idx % nx), y = (int)((idx / nx) % ny), z = zq;
         const int p = axis == 0 ? x : (axis == 1 ? y : z);
         const int n = axis == 0 ? nx : (axis == 1 ? ny : nz);
         const ll st = axis == 0 ? 1 : (axis == 1 ? (ll)nx : (ll)nx * ny);
@@ -259,11 +261,14 @@ template <int HW, bool DOG, int PFX = 0, int PP = 1>
 __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
                                                          int n, ll st, int n_other, ll st_other, int seg, Taps t,
                                                          const float* __restrict__ prev, float* __restrict__ dog,
-                                                         unsigned* maxslot) {
+                                                         unsigned* maxslot, int zlo, int zhi) {
+    // [zlo, zhi): the output positions along the marched axis (the whole line: 0, n).  A z-slab shard passes pointers
+    // offset to the line's virtual origin, the GLOBAL line length n and its own sub-range, so the boundary rule is
+    // evaluated in global coordinates and interior taps read the shard's halo planes.
     constexpr int PF = (HW >= 5 ? 2 : 4) + PFX;  // loads are issued PF steps ahead of their first use
     constexpr int WR = 2 * HW + 1 + PF;       // ring size == unroll factor (static slot indices)
     const unsigned nx4 = (unsigned)nx >> 2;
-    const int nseg = (n + seg - 1) / seg;
+    const int nseg = (zhi - zlo + seg - 1) / seg;
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.0f;
     if (gid < nx4 * (unsigned)n_other * (unsigned)nseg) {
@@ -271,8 +276,8 @@ __global__ void __launch_bounds__(128) blur_march_kernel(const float* __restrict
         const int x4 = (int)(gid - tt * nx4);
         const int s = (int)(tt / (unsigned)n_other);
         const int other = (int)(tt - (unsigned)s * (unsigned)n_other);
-        const int p0 = s * seg;
-        const int p1 = min(n, p0 + seg);
+        const int p0 = zlo + s * seg;
+        const int p1 = min(zhi, p0 + seg);
         const int qmax = p1 - 1 + HW;  // last extended-line sample this segment needs (<= n-1+HW)
         const ll line0 = (ll)x4 * 4 + (ll)other * st_other;  // flat index of coordinate 0 on this line
         const float* col = src + line0;
@@ -353,13 +358,13 @@ template <int HW, bool DOG>
 __global__ void __launch_bounds__(128) blur_marchc_kernel(const float* __restrict__ src, float* __restrict__ dst, int nx,
                                                           int n, ll st, int n_other, ll st_other, int seg, Taps t,
                                                           const float* __restrict__ prev, float* __restrict__ dog,
-                                                          unsigned* maxslot) {
+                                                          unsigned* maxslot, int zlo, int zhi) {
     constexpr int D = 4;             // copies in flight per thread and stream
     constexpr int WR = 2 * HW + 1;   // register window == unroll factor (static slot indices)
     constexpr int NS = DOG ? 2 : 1;
     __shared__ float4 ring[D][NS][128];
     const unsigned nx4 = (unsigned)nx >> 2;
-    const int nseg = (n + seg - 1) / seg;
+    const int nseg = (zhi - zlo + seg - 1) / seg;  // [zlo, zhi): output positions, see blur_march_kernel
     const unsigned gid = blockIdx.x * blockDim.x + threadIdx.x;
     float m = 0.0f;
     if (gid < nx4 * (unsigned)n_other * (unsigned)nseg) {
@@ -367,8 +372,8 @@ __global__ void __launch_bounds__(128) blur_marchc_kernel(const float* __restric
         const int x4 = (int)(gid - tt * nx4);
         const int s = (int)(tt / (unsigned)n_other);
         const int other = (int)(tt - (unsigned)s * (unsigned)n_other);
-        const int p0 = s * seg;
-        const int p1 = min(n, p0 + seg);
+        const int p0 = zlo + s * seg;
+        const int p1 = min(zhi, p0 + seg);
         const int nsamp = p1 - p0 + 2 * HW;  // samples q = p0-HW .. p1-1+HW
         const ll line0 = (ll)x4 * 4 + (ll)other * st_other;
         const float* col = src + line0;

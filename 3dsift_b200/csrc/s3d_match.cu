@@ -239,7 +239,7 @@ static int initial_match_path() {
     return (e && e[0] >= '0' && e[0] <= '4' && !e[1]) ? e[0] - '0' : 0;
 }
 static std::atomic<int> g_match_path{initial_match_path()};
-static std::atomic<unsigned long long> g_tc_rows{0}, g_fb_rows{0};
+static std::atomic<unsigned long long> g_tc_rows{0}, g_fb_rows{0}, g_refused_searches{0};
 
 // Exact CUDA-core search of the listed queries; results go to out[orig].
 static int exact_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, Top2* d_out,
@@ -283,13 +283,21 @@ static int search_device(const float* d_q, int nq, const float* d_db, int nd, in
     const bool use_tc = nd > 0 && n_act > 0 && (path >= 2 || (path == 0 && (double)n_act * nd >= 4.0e6 && nd >= 512));
     if (use_tc) {
         S3D_CUDA(cudaMallocAsync((void**)&d_fb, sizeof(int) * (size_t)n_act, st));
-        S3D_TRY(tc_search(d_q, d_list, n_act, d_db, nd, db_offset, d_top, d_fb, d_cnt + 1, st, path == 3 ? 1 : (path == 4 ? 2 : 0)));
-        int n_fb = 0;
-        S3D_CUDA(cudaMemcpyAsync(&n_fb, d_cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-        S3D_CUDA(cudaStreamSynchronize(st));
-        g_tc_rows += (unsigned long long)n_act;
-        g_fb_rows += (unsigned long long)n_fb;
-        if (n_fb > 0) S3D_TRY(exact_search(d_q, d_fb, n_fb, d_db, nd, db_offset, d_top, st));
+        const int rc = tc_search(d_q, d_list, n_act, d_db, nd, db_offset, d_top, d_fb, d_cnt + 1, st, path == 3 ? 1 : (path == 4 ? 2 : 0));
+        if (rc == kTcRefused) {
+            // descriptors outside the tensor-core guard's precondition (negative / > 1 / non-finite entries):
+            // the exact kernel is right for any input
+            g_refused_searches++;
+            S3D_TRY(exact_search(d_q, d_list, n_act, d_db, nd, db_offset, d_top, st));
+        } else {
+            S3D_TRY(rc);
+            int n_fb = 0;
+            S3D_CUDA(cudaMemcpyAsync(&n_fb, d_cnt + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+            S3D_CUDA(cudaStreamSynchronize(st));
+            g_tc_rows += (unsigned long long)n_act;
+            g_fb_rows += (unsigned long long)n_fb;
+            if (n_fb > 0) S3D_TRY(exact_search(d_q, d_fb, n_fb, d_db, nd, db_offset, d_top, st));
+        }
     } else if (nd > 0) {
         S3D_TRY(exact_search(d_q, d_list, n_act, d_db, nd, db_offset, d_top, st));
     }

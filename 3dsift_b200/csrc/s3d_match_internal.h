@@ -45,7 +45,10 @@ __device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
     if (b.i2 >= 0) top2_push(a, b.d2, b.i2);
 }
 
-// s3d_match_tc.cu
+// s3d_match_tc.cu.  Returns S3D_OK, an error code, or kTcRefused when the sets violate the precondition of the
+// tensor-core guard (an entry that is negative, above 1 or not finite): nothing was written to d_out / d_fb_list and the
+// caller must run the exact kernel for these rows.
+constexpr int kTcRefused = -1000;
 int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, Top2* d_out,
               int* d_fb_list, int* d_fb_count, cudaStream_t st, int variant);
 

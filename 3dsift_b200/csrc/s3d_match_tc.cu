@@ -218,21 +218,33 @@ __device__ __forceinline__ void topk_scan_tile(uint32_t taddr, int j0, int nd, f
     }
 }
 
-__global__ void cvt_f16_kernel(const float* __restrict__ src, const int* __restrict__ rows, int nrows, __half* __restrict__ dst) {
+// FP32 -> FP16 (x64) copy for the candidate pass.  The guard of the exact re-rank (rerank_kernel) bounds the error of
+// the FP16 dot product RELATIVE to the dot product itself, which only holds when no term can cancel another and no
+// entry leaves the range the scaling was chosen for: descriptors as the reference produces them are non-negative with
+// entries <= 1 (normalise / clamp / normalise, Src/cSIFT3D.cc:1350-1358).  s3d_match accepts arbitrary floats, so the
+// conversion also CHECKS the precondition: any entry that is negative, above 1 or not finite raises *bad, and the
+// caller sends the whole search to the exact kernel instead (tc_search returns kTcRefused).
+__global__ void cvt_f16_kernel(const float* __restrict__ src, const int* __restrict__ rows, int nrows, __half* __restrict__ dst,
+                               int* __restrict__ bad) {
     // one warp per row (768 floats = 6 float4 per lane)
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= nrows) return;
     const float4* s = reinterpret_cast<const float4*>(src + (size_t)(rows ? rows[w] : w) * KD);
     uint2* d = reinterpret_cast<uint2*>(dst + (size_t)w * KD);
+    bool out_of_range = false;
 #pragma unroll
     for (int i = 0; i < KD / 4 / 32; ++i) {
         const float4 v = s[lane + 32 * i];
+        // !(0 <= x <= 1) is true for negative, > 1, NaN and +-inf entries (-0.0f passes: it is zero)
+        out_of_range |= !(v.x >= 0.0f && v.x <= 1.0f) || !(v.y >= 0.0f && v.y <= 1.0f) || !(v.z >= 0.0f && v.z <= 1.0f) ||
+                        !(v.w >= 0.0f && v.w <= 1.0f);
         const __half2 a = __floats2half2_rn(v.x * SCALE, v.y * SCALE), b = __floats2half2_rn(v.z * SCALE, v.w * SCALE);
         uint2 o;
         o.x = *reinterpret_cast<const unsigned*>(&a);
         o.y = *reinterpret_cast<const unsigned*>(&b);
         d[lane + 32 * i] = o;
     }
+    if (__any_sync(0xffffffffu, out_of_range) && lane == 0) *bad = 1;
 }
 
 // Work item = (query tile qt, database part p): the CTA sweeps db tiles [p*tiles_per_part, ...) for
@@ -719,6 +731,7 @@ int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, 
     __half *q16 = nullptr, *db16 = nullptr;
     float* cand_val = nullptr;
     int* cand_idx = nullptr;
+    int* d_bad = nullptr;
     const int n_dbtiles = (nd + BN - 1) / BN;
     const int n_units = pair ? (nql + 2 * pr::BMC - 1) / (2 * pr::BMC) : (nql + BM - 1) / BM;
     const int workers = pair ? std::max(1, sms / 2) : sms;
@@ -726,33 +739,65 @@ int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, 
     const int tiles_per_part = (n_dbtiles + parts - 1) / parts;
     parts = (n_dbtiles + tiles_per_part - 1) / tiles_per_part;
     const int ncand = parts * TOPK;
-    S3D_CUDA(cudaMallocAsync((void**)&q16, sizeof(__half) * KD * (size_t)nql, st));
-    S3D_CUDA(cudaMallocAsync((void**)&db16, sizeof(__half) * KD * (size_t)nd, st));
-    S3D_CUDA(cudaMallocAsync((void**)&cand_val, sizeof(float) * (size_t)nql * ncand, st));
-    S3D_CUDA(cudaMallocAsync((void**)&cand_idx, sizeof(int) * (size_t)nql * ncand, st));
-    S3D_LAUNCH(cvt_f16_kernel, s3d_blocks((size_t)nql * 32, 256), 256, 0, st, d_q, d_qlist, nql, q16);
-    S3D_LAUNCH(cvt_f16_kernel, s3d_blocks((size_t)nd * 32, 256), 256, 0, st, d_db, (const int*)nullptr, nd, db16);
-    CUtensorMap mq, mdb;
-    S3D_TRY(make_map(&mq, q16, nql, BM));
-    S3D_TRY(make_map(&mdb, db16, nd, pair ? pr::BROWS : BN));
-    if (pair) {
-        const int grid = 2 * std::min(workers, n_units * parts);
-        // chunk = the slice of the database all clusters sweep together; parts are swept concurrently, so
-        // together they should stay well inside L2 (126 MB, shared with the streaming query tiles)
-        const int chunk_tiles = std::max(8, pr::kChunkTiles / parts);
-        S3D_LAUNCH(tc_pair_topk_kernel, grid, kThreads, pr::SMEM_BYTES, st, mq, mdb, nql, nd, n_units, parts, tiles_per_part,
-                   n_dbtiles, chunk_tiles, cand_val, cand_idx);
-    } else {
-        const int grid = std::min(sms, n_units * parts);
-        S3D_LAUNCH(tc_topk_kernel, grid, kThreads, SMEM_BYTES, st, mq, mdb, nql, nd, n_units, parts, tiles_per_part, n_dbtiles,
-                   cand_val, cand_idx);
+    // capacity: the FP16 copies and candidate lists are temporaries on top of the caller's FP32 sets (1 M x 1 M:
+    // 2 x 1.5 GB + 64 MB * parts); refuse up front rather than fail half-way through a stream-ordered allocation
+    {
+        size_t free_b = 0, total_b = 0;
+        const size_t need = sizeof(__half) * KD * ((size_t)nql + (size_t)nd) + (sizeof(float) + sizeof(int)) * (size_t)nql * ncand;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+            uint64_t pooled = 0;  // bytes the stream-ordered pool already holds and can hand out again
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t reserved = 0, used = 0;
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+                cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+                pooled = reserved > used ? reserved - used : 0;
+            }
+            if (need > free_b + pooled)
+                return fail(S3D_ERR_CAPACITY, "tensor-core search of %d x %d rows needs %.2f GB of temporaries, %.2f GB available",
+                            nql, nd, need / 1e9, (free_b + pooled) / 1e9);
+        }
     }
-    S3D_LAUNCH(rerank_kernel, s3d_blocks((size_t)nql, 4 * kRrWarps), kRrWarps * 32, 0, st, d_q, d_qlist, nql, d_db, nd, db_offset, ncand,
-               cand_val, cand_idx, d_out, d_fb_list, d_fb_count);
-    S3D_CUDA(cudaGetLastError());
-    void* tmp[] = {q16, db16, cand_val, cand_idx};
-    for (void* p : tmp) S3D_CUDA(cudaFreeAsync(p, st));
-    return S3D_OK;
+    // every exit below goes through `done`, which returns the temporaries to the pool (early returns leaked)
+    auto done = [&](int rc) -> int {
+        void* tmp[] = {q16, db16, cand_val, cand_idx, d_bad};
+        for (void* p : tmp) if (p) cudaFreeAsync(p, st);
+        return rc;
+    };
+    auto body = [&]() -> int {
+        S3D_CUDA(cudaMallocAsync((void**)&q16, sizeof(__half) * KD * (size_t)nql, st));
+        S3D_CUDA(cudaMallocAsync((void**)&db16, sizeof(__half) * KD * (size_t)nd, st));
+        S3D_CUDA(cudaMallocAsync((void**)&d_bad, sizeof(int), st));
+        S3D_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+        S3D_LAUNCH(cvt_f16_kernel, s3d_blocks((size_t)nql * 32, 256), 256, 0, st, d_q, d_qlist, nql, q16, d_bad);
+        S3D_LAUNCH(cvt_f16_kernel, s3d_blocks((size_t)nd * 32, 256), 256, 0, st, d_db, (const int*)nullptr, nd, db16, d_bad);
+        int h_bad = 0;
+        S3D_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        S3D_CUDA(cudaStreamSynchronize(st));
+        if (h_bad) return kTcRefused;  // outside the guard's precondition: the caller runs the exact kernel
+        S3D_CUDA(cudaMallocAsync((void**)&cand_val, sizeof(float) * (size_t)nql * ncand, st));
+        S3D_CUDA(cudaMallocAsync((void**)&cand_idx, sizeof(int) * (size_t)nql * ncand, st));
+        CUtensorMap mq, mdb;
+        S3D_TRY(make_map(&mq, q16, nql, BM));
+        S3D_TRY(make_map(&mdb, db16, nd, pair ? pr::BROWS : BN));
+        if (pair) {
+            const int grid = 2 * std::min(workers, n_units * parts);
+            // chunk = the slice of the database all clusters sweep together; parts are swept concurrently, so
+            // together they should stay well inside L2 (126 MB, shared with the streaming query tiles)
+            const int chunk_tiles = std::max(8, pr::kChunkTiles / parts);
+            S3D_LAUNCH(tc_pair_topk_kernel, grid, kThreads, pr::SMEM_BYTES, st, mq, mdb, nql, nd, n_units, parts, tiles_per_part,
+                       n_dbtiles, chunk_tiles, cand_val, cand_idx);
+        } else {
+            const int grid = std::min(sms, n_units * parts);
+            S3D_LAUNCH(tc_topk_kernel, grid, kThreads, SMEM_BYTES, st, mq, mdb, nql, nd, n_units, parts, tiles_per_part, n_dbtiles,
+                       cand_val, cand_idx);
+        }
+        S3D_LAUNCH(rerank_kernel, s3d_blocks((size_t)nql, 4 * kRrWarps), kRrWarps * 32, 0, st, d_q, d_qlist, nql, d_db, nd, db_offset, ncand,
+                   cand_val, cand_idx, d_out, d_fb_list, d_fb_count);
+        S3D_CUDA(cudaGetLastError());
+        return S3D_OK;
+    };
+    return done(body());
 }
 
 }  // namespace s3d

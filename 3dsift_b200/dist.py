@@ -181,80 +181,37 @@ def needed_from(ext_src, ext_dst):
     return out
 
 
-class _DevMem:
-    """Zero-copy view of raw device memory for torch (``torch.as_tensor(_DevMem(...), device='cuda')``)."""
-
-    def __init__(self, ptr, nelem, typestr="<f4"):
-        self.__cuda_array_interface__ = {"shape": (int(nelem),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
 class SlabShard:
-    """One shard of a z-slab extraction: an s3d slab handle plus its plane bookkeeping."""
+    """One shard's handle of a z-slab extraction (s3d_slab_run / s3d_extract_multi): the shard's own results (the merged
+    results on the gather root), its local level buffers when the run kept them, its plane bookkeeping."""
 
-    def __init__(self, gid, vol_ext, dims, own, params=None, device=-1, stream=None):
-        L = api.lib()
+    def __init__(self, handle, dims, gid=0):
+        self._h = handle if isinstance(handle, C.c_void_p) else C.c_void_p(handle)
         self.gid = gid
         self.nx, self.ny, self.nz = dims
-        self.own = own
-        p = api.s3d_params()
-        L.s3d_default_params(C.byref(p))
-        for k, v in (params or {}).items():
-            setattr(p, k, v)
-        p.device = device
-        p.stream = C.c_void_p(int(stream)) if stream else None
-        self._p = p
-        self._h = C.c_void_p()
-        on_dev = hasattr(vol_ext, "is_cuda") and vol_ext.is_cuda
-        api.check(L.s3d_slab_create(api._ptr(vol_ext), int(on_dev), self.nx, self.ny, self.nz, own[0], own[1], C.byref(p),
-                                    C.byref(self._h)))
+        n, h, g, f = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        api.check(api.lib().s3d_slab_info(self._h, C.byref(n), C.byref(h), C.byref(g), C.byref(f)))
+        self.noct, self.halo, self.G, self.first_replicated = n.value, h.value, g.value, f.value
 
-    def local_max(self):
-        v = C.c_float()
-        api.check(api.lib().s3d_slab_local_max(self._h, C.byref(v)))
-        return float(v.value)
-
-    def begin(self, gmax):
-        api.check(api.lib().s3d_slab_begin(self._h, C.c_float(gmax)))
-        n, h, g = C.c_int(), C.c_int(), C.c_int()
-        api.check(api.lib().s3d_slab_info(self._h, C.byref(n), C.byref(h), C.byref(g)))
-        self.noct, self.halo, self.G = n.value, h.value, g.value
-
-    def seed(self, o):
-        api.check(api.lib().s3d_slab_seed(self._h, o))
-
-    def octave(self, o):
-        api.check(api.lib().s3d_slab_octave(self._h, o))
-
-    def level(self, which, idx):
-        """(torch tensor [local planes, ny_o*nx_o] aliasing the level buffer, (za, zb, p0, p1))."""
-        import torch
+    def extent(self, which, idx):
         ptr = C.c_void_p()
         ext = (C.c_int * 4)()
         api.check(api.lib().s3d_slab_level_buffer(self._h, which, idx, C.byref(ptr), ext))
-        za, zb, p0, p1 = (int(v) for v in ext)
+        return tuple(int(v) for v in ext)
+
+    def get_level_host(self, which, idx):
+        """(local planes [za, zb) of the level as a [zb-za, ny_o*nx_o] array or None, (za, zb, p0, p1))."""
+        za, zb, p0, p1 = self.extent(which, idx)
         per = self.G if which == 0 else self.G - 1
         o = idx // per
         plane = (self.nx >> o) * (self.ny >> o)
-        n = (zb - za) * plane
-        if n == 0:
+        if zb <= za:
             return None, (za, zb, p0, p1)
-        t = torch.as_tensor(_DevMem(ptr.value, n), device="cuda").view(zb - za, plane)
-        return t, (za, zb, p0, p1)
+        out = np.empty(((zb - za), plane), np.float32)
+        api.check(api.lib().s3d_get_level(self._h, which, idx, api._ptr(out)))
+        return out, (za, zb, p0, p1)
 
-    def maxima(self):
-        n = self.noct * (self.G - 1)
-        out = np.zeros(n, np.float32)
-        api.check(api.lib().s3d_slab_get_maxima(self._h, api._ptr(out), n))
-        return out
-
-    def set_maxima(self, m):
-        m = np.ascontiguousarray(m, np.float32)
-        api.check(api.lib().s3d_slab_set_maxima(self._h, api._ptr(m), len(m)))
-
-    def finish(self):
-        api.check(api.lib().s3d_slab_finish(self._h))
-
-    def results(self):
+    def results(self, with_extrema=True):
         L = api.lib()
         n = C.c_int()
         api.check(L.s3d_num_keypoints(self._h, C.byref(n)))
@@ -262,35 +219,33 @@ class SlabShard:
         kp = np.zeros(max(k, 1), api.KP_DTYPE)
         desc = np.zeros((max(k, 1), api.DESC_LENGTH), np.float32)
         api.check(L.s3d_get_keypoints(self._h, api._ptr(kp), api._ptr(desc)))
-        api.check(L.s3d_num_extrema(self._h, C.byref(n)))
-        e = n.value
-        ex = np.zeros(max(e, 1), api.KP_DTYPE)
-        codes = np.zeros(max(e, 1), np.int32)
-        xyz5 = np.zeros((max(e, 1), 5), np.int32)
-        api.check(L.s3d_get_extrema(self._h, api._ptr(ex), api._ptr(codes), api._ptr(xyz5)))
-        return dict(kp=kp[:k], desc=desc[:k], extrema=ex[:e], codes=codes[:e], xyz5=xyz5[:e])
-
-    def device_results(self):
-        """The shard's result arrays as torch tensors aliasing device memory (valid until close()):
-        dict(kp uint8 [k,176], desc float32 [k,768], extrema uint8 [e,176], codes int32 [e,1], xyz5 int32 [e,5])."""
-        import torch
-        ptrs = (C.c_void_p * 5)()
-        k, e = C.c_int(), C.c_int()
-        api.check(api.lib().s3d_device_results(self._h, ptrs, C.byref(k), C.byref(e)))
-        k, e = k.value, e.value
-        spec = (("kp", k, 176, "|u1", torch.uint8), ("desc", k, api.DESC_LENGTH, "<f4", torch.float32),
-                ("extrema", e, 176, "|u1", torch.uint8), ("codes", e, 1, "<i4", torch.int32), ("xyz5", e, 5, "<i4", torch.int32))
-        out = {}
-        for (name, n, w, ts, dt), p in zip(spec, ptrs):
-            if n > 0 and p:
-                out[name] = torch.as_tensor(_DevMem(p, n * w, ts), device="cuda").view(n, w)
-            else:
-                out[name] = torch.empty((0, w), dtype=dt, device="cuda")
+        out = dict(kp=kp[:k], desc=desc[:k])
+        if with_extrema:
+            api.check(L.s3d_num_extrema(self._h, C.byref(n)))
+            e = n.value
+            ex = np.zeros(max(e, 1), api.KP_DTYPE)
+            codes = np.zeros(max(e, 1), np.int32)
+            xyz5 = np.zeros((max(e, 1), 5), np.int32)
+            api.check(L.s3d_get_extrema(self._h, api._ptr(ex), api._ptr(codes), api._ptr(xyz5)))
+            out.update(extrema=ex[:e], codes=codes[:e], xyz5=xyz5[:e])
         return out
 
-    def get_level_host(self, which, idx):
-        t, ext = self.level(which, idx)
-        return (None if t is None else t.cpu().numpy()), ext
+    def num_keypoints(self):
+        n = C.c_int()
+        api.check(api.lib().s3d_num_keypoints(self._h, C.byref(n)))
+        return n.value
+
+    def phases(self):
+        """Device time per phase of this shard's run, ms: upload+normalise, pyramid (incl. halo exchanges), window halos,
+        all-reduce + sparse stages, gather."""
+        ms = (C.c_double * 8)()
+        api.check(api.lib().s3d_slab_phases(self._h, ms))
+        return dict(zip(("upload", "pyramid", "halo", "sparse", "gather"), (float(v) for v in ms[:5])))
+
+    def timers(self):
+        t = (C.c_double * 10)()
+        api.check(api.lib().s3d_get_timers(self._h, C.byref(t)))
+        return list(t)
 
     def close(self):
         if self._h is not None and self._h.value:
@@ -302,6 +257,57 @@ class SlabShard:
             self.close()
         except Exception:
             pass
+
+
+class NcclComm:
+    """s3d_comm over NCCL for one process per GPU: rank 0 draws the unique id inside the library, torch.distributed
+    carries its 128 bytes to the other ranks (any group backend), ncclCommInitRank happens inside the library."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        L = api.lib()
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = (C.c_ubyte * 128)()
+        box = [None]
+        if self.rank == 0:
+            api.check(L.s3d_comm_unique_id(uid))
+            box[0] = bytes(uid)
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        uid = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        self._c = C.c_void_p()
+        dev = torch.cuda.current_device() if device is None else device
+        api.check(L.s3d_comm_create(uid, self.world, self.rank, dev, C.byref(self._c)))
+
+    def traffic(self):
+        a, b = C.c_ulonglong(), C.c_ulonglong()
+        api.check(api.lib().s3d_comm_traffic(self._c, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def close(self):
+        if self._c is not None and self._c.value:
+            api.lib().s3d_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+
+_COMMS = {}
+
+
+def nccl_comm(group=None):
+    """The process's s3d communicator for `group` (created on first use, kept for the life of the process)."""
+    key = id(group)
+    if key not in _COMMS:
+        _COMMS[key] = NcclComm(group)
+    return _COMMS[key]
+
+
+def plan_from_library(nz, world, rank, octave, depth):
+    """s3d_slab_plan: [(peer, 'recv' | 'send', k0, k1)] — the transfers of one halo fill as `rank` sees them."""
+    cap = 4 * world + 8
+    q = (C.c_int * (4 * cap))()
+    n = C.c_int()
+    api.check(api.lib().s3d_slab_plan(nz, world, rank, octave, depth, q, cap, C.byref(n)))
+    return [(int(q[4 * i]), "send" if q[4 * i + 1] else "recv", int(q[4 * i + 2]), int(q[4 * i + 3])) for i in range(n.value)]
 
 
 def exchange_plan(exts, owner_rank, my_rank):
@@ -365,190 +371,67 @@ def merge_shard_results(parts, num_kp_levels=3):
     return out
 
 
-_PINNED = {}
-
-
-def _to_host(t):
-    """Device tensor -> fresh numpy array through a cached pinned staging buffer (a pageable .cpu() of the
-    30 MB descriptor block runs at a few GB/s; pinned D2H + one host memcpy is several times faster)."""
-    import torch
-    n = t.numel() * t.element_size()
-    if n == 0:
-        return t.cpu().numpy()
-    buf = _PINNED.get("buf")
-    if buf is None or buf.numel() < n:
-        buf = torch.empty(max(n, 1 << 22), dtype=torch.uint8).pin_memory()
-        _PINNED["buf"] = buf
-    view = buf[:n].view(t.dtype).view(t.shape)
-    view.copy_(t.contiguous(), non_blocking=False)
-    return view.numpy().copy()
-
-
-def _gather_merge_device(shard_results, world, group, num_kp_levels, with_extrema=True):
-    """All ranks' shard results merged in the reference's order (octave, level, z, y, x), on the GPU:
-    padded all-gathers of the device result arrays over NCCL, a stable sort of the per-row unit key
-    (rows arrive shard-major and in raster order inside a shard, so a STABLE sort by unit is the whole
-    merge, App. B Q16), one gather, one device->host copy per array.
-    shard_results: list of device_results() dicts of the shards held by this process, in shard order."""
-    import torch
-    import torch.distributed as dist
-    cat = {n: torch.cat([r[n] for r in shard_results]) if shard_results else None for n in ("kp", "desc", "extrema", "codes", "xyz5")}
-    k = int(cat["kp"].shape[0]) if shard_results else 0
-    e = int(cat["extrema"].shape[0]) if shard_results else 0
-    if world > 1:
-        cnt = torch.tensor([k, e], dtype=torch.int64, device="cuda")
-        cnts = torch.empty((world, 2), dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(cnts.view(-1), cnt, group=group)
-        cnts = cnts.cpu()
-        kmax, emax = int(cnts[:, 0].max()), int(cnts[:, 1].max())
-    widths = dict(kp=(176, torch.uint8), desc=(api.DESC_LENGTH, torch.float32), extrema=(176, torch.uint8), codes=(1, torch.int32),
-                  xyz5=(5, torch.int32))
-    out = {}
-    names = ("kp", "desc", "extrema", "codes", "xyz5") if with_extrema else ("kp", "desc")
-    flat = {}
-    for name in names:
-        w, dt = widths[name]
-        mine = cat[name] if shard_results else torch.empty((0, w), dtype=dt, device="cuda")
-        if world == 1:
-            flat[name] = mine
-            continue
-        is_k = name in ("kp", "desc")
-        rows, n = (kmax, k) if is_k else (emax, e)
-        buf = torch.zeros((max(rows, 1), w), dtype=dt, device="cuda")
-        buf[:n] = mine
-        allb = torch.empty((world,) + tuple(buf.shape), dtype=dt, device="cuda")
-        dist.all_gather_into_tensor(allb.view(-1), buf.view(-1), group=group)
-        valid = (torch.arange(max(rows, 1), device="cuda")[None, :] < cnts[:, 0 if is_k else 1].cuda()[:, None]).view(-1)
-        flat[name] = allb.view(-1, w)[valid]
-    # unit keys: octave and level sit at int32 words 4 and 5 of a keypoint record; xyz5 carries them as columns 3, 4
-    kw = flat["kp"].contiguous().view(torch.int32).view(-1, 44)
-    ko = torch.sort(kw[:, 4].long() * (num_kp_levels + 1) + kw[:, 5].long(), stable=True).indices
-    out["kp"] = _to_host(flat["kp"][ko]).view(api.KP_DTYPE).reshape(-1)
-    out["desc"] = _to_host(flat["desc"][ko])
-    if with_extrema:
-        x5 = flat["xyz5"]
-        eo = torch.sort(x5[:, 3].long() * (num_kp_levels + 1) + x5[:, 4].long(), stable=True).indices
-        out["extrema"] = _to_host(flat["extrema"][eo]).view(api.KP_DTYPE).reshape(-1)
-        out["codes"] = _to_host(flat["codes"][eo]).reshape(-1)
-        out["xyz5"] = _to_host(x5[eo])
-    return out
-
-
-def extract_slabs(volume, shards=None, group=None, params=None, keep=False, timing=None, with_extrema=True):
-    """Full extraction of ONE volume split into z-slabs.
-
-    * distributed (torch.distributed initialised, ``shards`` None): one shard per rank of ``group``;
-      every rank passes the same host ``volume`` ([nz, ny, nx] float32; only its own planes + halo
-      are uploaded) and receives the merged result.
-    * single process (``shards`` = G): G logical shards on the current device, same code path with
-      device copies instead of send/recv — the CI check that sharded == unsharded.
-
-    ``with_extrema`` = False skips gathering the per-detection debug records (extrema, codes, xyz5).
-    ``timing`` (a dict) receives device-synchronised wall seconds per phase: upload, pyramid (blur
-    chain + seed halo exchanges + scalar all-reduces), halo (descriptor-window planes), sparse, gather.
-
-    Returns dict(kp, desc, extrema, codes, xyz5[, shards]) in the reference's order."""
-    import time
-
-    import torch
-    import torch.distributed as dist
-
-    def tick(name, _t=[None]):
-        if timing is None:
-            return
-        torch.cuda.synchronize()
-        now = time.perf_counter()
-        if name is not None and _t[0] is not None:
-            timing[name] = timing.get(name, 0.0) + now - _t[0]
-        _t[0] = now
-
-    tick(None)
-    distributed = shards is None and dist.is_initialized() and dist.get_world_size(group) > 1
-    if distributed:
-        world, me = dist.get_world_size(group), dist.get_rank(group)
-        G = world
-        owner = list(range(G))
-    else:
-        G = int(shards or 1)
-        world, me = 1, 0
-        owner = [0] * G
-    nz, ny, nx = (int(v) for v in volume.shape)
-    bounds = slab_bounds(nz, G)
-    held = [g for g in range(G) if owner[g] == me and bounds[g + 1] > bounds[g]]
-    L = api.lib()
+def _params(params):
     p = api.s3d_params()
-    L.s3d_default_params(C.byref(p))
+    api.lib().s3d_default_params(C.byref(p))
     for k, v in (params or {}).items():
         setattr(p, k, v)
-    nlev = p.num_kp_levels
+    return p
 
-    def ext_of(g, o):
-        e = (C.c_int * 4)()
-        if bounds[g + 1] <= bounds[g]:
-            return (0, 0, 0, 0)
-        api.check(L.s3d_slab_extent(nz, bounds[g], bounds[g + 1], C.byref(p), o, e))
-        return tuple(int(v) for v in e)
 
-    # the shards run on torch's current stream so that the plane copies / NCCL calls below are
-    # ordered with the kernels (0 = the legacy default stream: pass its explicit handle, 0x1)
-    stream = torch.cuda.current_stream().cuda_stream or 1
-    sh = {}
-    for g in held:
-        za, zb, _, _ = ext_of(g, 0)
-        sh[g] = SlabShard(g, np.ascontiguousarray(volume[za:zb], dtype=np.float32), (nx, ny, nz), (bounds[g], bounds[g + 1]),
-                          params, device=torch.cuda.current_device(), stream=stream)
-    tick("upload")
-    # global max|v| (data_scale, Src/cUtil.cc:538-550)
-    m = max([sh[g].local_max() for g in held] or [0.0])
+def extract_slabs(volume, shards=None, group=None, params=None, keep=False, timing=None, with_extrema=True, devices=None,
+                  on_device=False):
+    """Full extraction of ONE volume split into z-slabs, orchestrated inside the library.
+
+    * distributed (torch.distributed initialised, ``shards`` None): one shard per rank of ``group`` over the library's
+      NCCL communicator; every rank passes the same ``volume`` ([nz, ny, nx] float32, host — pinned for an asynchronous
+      upload — or, with on_device, a CUDA tensor); only the rank's own planes are read.  Rank 0 of the group
+      receives the merged result, the other ranks their own part (``out["merged"]`` tells which).
+    * single process (``shards`` = G): G shards driven by G host threads of this process, shard g on
+      ``devices[g]`` (default: all on the current device — logical shards, the CI check that sharded == unsharded).
+
+    ``timing`` (a dict) receives the device milliseconds per phase of this rank's shard (see SlabShard.phases).
+    Returns dict(kp, desc[, extrema, codes, xyz5], merged[, shards, bounds]) in the reference's order."""
+    import torch.distributed as dist
+    L = api.lib()
+    distributed = shards is None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    nz, ny, nx = (int(v) for v in volume.shape)
+    p = _params(params)
     if distributed:
-        t = torch.tensor([m], dtype=torch.float32, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        m = float(t.item())
-    for g in held:
-        sh[g].begin(m)
-    any_s = sh[held[0]] if held else None
-    noct = any_s.noct if any_s else 0
-    Gl = any_s.G if any_s else nlev + 3
-    if distributed:  # ranks that hold nothing still take part in the collectives
-        t = torch.tensor([noct, Gl], dtype=torch.int64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        noct, Gl = int(t[0]), int(t[1])
-    for o in range(1, noct):
-        for g in held:
-            sh[g].seed(o)
-        exts = [ext_of(g, o) for g in range(G)]
-        lv = {g: sh[g].level(0, o * Gl)[0] for g in held}
-        exchange_halos(lv, exts, owner, me, group)
-        for g in held:
-            sh[g].octave(o)
-    # global max|DoG| per level (Detect_KeyPoints threshold, Src/cSIFT3D.cc:384-385)
-    mx = np.zeros(noct * (Gl - 1), np.float32)
-    for g in held:
-        mx = np.maximum(mx, sh[g].maxima())
-    if distributed:
-        t = torch.from_numpy(mx).cuda()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
-        mx = t.cpu().numpy()
-    for g in held:
-        sh[g].set_maxima(mx)
-    tick("pyramid")
-    # descriptor windows reach into the neighbours' planes: fill the halos of levels 1..L of every octave
-    for o in range(noct):
-        exts = [ext_of(g, o) for g in range(G)]
-        for i in range(1, nlev + 1):
-            lv = {g: sh[g].level(0, o * Gl + i)[0] for g in held}
-            exchange_halos(lv, exts, owner, me, group)
-    tick("halo")
-    for g in held:
-        sh[g].finish()
-    tick("sparse")
-    # results stay on the device until they are merged: all-gather + stable sort + one D2H per array
-    out = _gather_merge_device([sh[g].device_results() for g in held], world if distributed else 1, group, nlev, with_extrema)
-    tick("gather")
+        comm = nccl_comm(group)
+        o0, o1 = C.c_int(), C.c_int()
+        api.check(L.s3d_slab_bounds(nz, comm.world, comm.rank, C.byref(o0), C.byref(o1)))
+        own = volume[o0.value:o1.value]
+        if isinstance(own, np.ndarray):
+            own = np.ascontiguousarray(own, dtype=np.float32)
+        h = C.c_void_p()
+        api.check(L.s3d_slab_run(comm._c, api._ptr(own), int(bool(on_device)), nx, ny, nz, C.byref(p), C.byref(h)))
+        sh = SlabShard(h, (nx, ny, nz), comm.rank)
+        api.check(L.s3d_slab_gather(comm._c, h, 0, int(with_extrema)))
+        out = sh.results(with_extrema)
+        out["merged"] = comm.rank == 0
+        if timing is not None:
+            timing.update(sh.phases())
+        if keep:
+            out["shards"] = {comm.rank: sh}
+        else:
+            sh.close()
+        return out
+    G = int(shards or 1)
+    vol = np.ascontiguousarray(volume, dtype=np.float32) if isinstance(volume, np.ndarray) else volume
+    hs = (C.c_void_p * G)()
+    devs = (C.c_int * G)(*devices) if devices is not None else None
+    api.check(L.s3d_extract_multi(api._ptr(vol), nx, ny, nz, C.byref(p), devs, G, int(with_extrema), hs))
+    sh = {g: SlabShard(C.c_void_p(hs[g]), (nx, ny, nz), g) for g in range(G)}
+    out = sh[0].results(with_extrema)
+    out["merged"] = True
+    if timing is not None:
+        timing.update(sh[0].phases())
+        timing["per_shard"] = [sh[g].phases() for g in range(G)]
     if keep:
         out["shards"] = sh
-        out["bounds"] = bounds
+        out["bounds"] = slab_bounds(nz, G)
     else:
-        for g in held:
+        for g in range(G):
             sh[g].close()
     return out

@@ -170,44 +170,69 @@ S3D_API int s3d_get_kernel_stats(s3d_handle h, int cap, int* n_classes, double* 
 S3D_API const char* s3d_kernel_class_name(int cls);
 
 /* ---- one large volume in z-slabs over several GPUs (BASELINE.json configs[2]) ----
- * The reference processes one volume in one address space (Src/cSIFT3D.cc:165-235).  Here shard r
- * OWNS octave-0 planes [own0, own1) (plane k of octave o belongs to the owner of plane k*2^o) and
- * keeps local level buffers for owned planes +- `halo`.  The caller steps all shards through the
- * stages below in lockstep and moves data between them (3dsift_b200/dist.py: NCCL send/recv of
- * planes, all-reduce(max) of scalars).  Results (levels on owned planes, detections, keypoints,
- * descriptors) are identical to the unsharded run; concatenating the shards' lists per
- * (octave, level) in shard order gives the reference's order.
+ * The reference processes one volume in one address space (Src/cSIFT3D.cc:165-235); its z pass
+ * (Src/cSIFT3D.cc:615-617) is the axis this path shards.  Shard r OWNS octave-0 planes [own0, own1) (plane k of
+ * octave o belongs to the owner of plane k*2^o) and keeps local level buffers for owned planes +- `halo`.
+ * Every Gaussian level is produced on owned +- 1 planes (so the DoG neighbours of detection are local); before
+ * level i the shards exchange the hw_i + 1 source planes next to their borders, and once an octave is complete the
+ * planes of levels 1..L that the orientation / descriptor windows of the neighbours' keypoints reach.  Octaves too
+ * thin to shard are gathered once (their seed level) and computed by every shard ("replicated"); detection,
+ * orientation and description always run on the owned planes only.  Input max|v| and the per-level max|DoG| are
+ * all-reduced(max).  Results (levels on owned planes, detections, keypoints, descriptors) are bit-identical to the
+ * unsharded run; the per-(octave, level) concatenation of the shards' lists in shard order is the reference's order.
+ * All of it is enqueued on the shards' streams from C: the only host waits are the two count read-backs of the
+ * sparse stage and the result gather.
  *
- *   s3d_slab_extent      local/owned plane ranges {za, zb, p0, p1} of an octave (no handle needed)
- *   s3d_slab_create      vol_ext = raw planes [za, zb) of octave 0 (host or device); computes max|v|
- *                        over the OWNED planes; blocks until the copy is done
- *   s3d_slab_local_max   that maximum                      -> caller: all-reduce(max)
- *   s3d_slab_begin       divide by the global maximum (data_scale, Src/cUtil.cc:552-561), allocate
- *                        the pyramids, run octave 0
- *   s3d_slab_seed(o)     decimate the owned planes of octave o from level L of octave o-1
- *                        (DownSample_3D :506-533)          -> caller: fill the halo planes of
- *                        Gaussian level o*G+0 from their owners (s3d_slab_level_buffer)
- *   s3d_slab_octave(o)   levels 1.. of octave o + DoG, maxima over owned planes
- *   s3d_slab_get_maxima / s3d_slab_set_maxima   max|DoG| per level (noct*D floats)
- *                                                          -> caller: all-reduce(max)
- *                        -> caller: fill the halo planes of Gaussian levels 1..L of every octave
- *                           (descriptor windows reach up to `halo` planes beyond the owned range)
- *   s3d_slab_finish      detection on the owned planes, orientation, description; blocks.  Then
- *                        s3d_num_keypoints / s3d_get_keypoints / s3d_get_extrema as usual.
+ * Transports.  s3d_comm wraps NCCL for one process per GPU (the caller distributes the 128-byte unique id, e.g.
+ * with torch.distributed / MPI / a file) — collective calls: every rank calls the same function with the same
+ * volume geometry.  s3d_extract_multi is the single-process form: one host thread per shard, device-to-device /
+ * peer copies between the shards' buffers (shards may share a device: "logical shards", the CI check).
  */
+typedef struct s3d_comm* s3d_comm_t;
+/* Owned octave-0 planes of shard `rank` of `world`: contiguous, balanced, even starts. */
+S3D_API int s3d_slab_bounds(int nz, int world, int rank, int* own0, int* own1);
+/* local/owned plane ranges {za, zb, p0, p1} of a SHARDED octave (no handle needed) */
 S3D_API int s3d_slab_extent(int nz, int own0, int own1, const s3d_params* p, int octave, int* out4);
-S3D_API int s3d_slab_create(const float* vol_ext, int on_device, int nx, int ny, int nz, int own0, int own1,
-                            const s3d_params* p, s3d_handle* out);
-S3D_API int s3d_slab_local_max(s3d_handle h, float* mx);
-S3D_API int s3d_slab_begin(s3d_handle h, float global_max);
-S3D_API int s3d_slab_info(s3d_handle h, int* noct, int* halo, int* levels_per_octave);
-S3D_API int s3d_slab_seed(s3d_handle h, int octave);
-S3D_API int s3d_slab_octave(s3d_handle h, int octave);
+/* First octave that is replicated rather than sharded for this geometry (== octave count: none). */
+S3D_API int s3d_slab_first_replicated(int nx, int ny, int nz, int world, const s3d_params* p, int* octave);
+/* The transfers of one halo fill as shard `rank` sees them (host logic, no GPU): planes [k0, k1) of a level of
+ * `octave` that `rank` receives from (kind 0) or sends to (kind 1) shard `peer`, for a halo of `depth` planes
+ * beyond the owned range (depth < 0: every plane the shard does not own — the gather of a replicated octave).
+ * Writes up to cap (peer, kind, k0, k1) quadruples, returns the count in *n. */
+S3D_API int s3d_slab_plan(int nz, int world, int rank, int octave, int depth, int* quads, int cap, int* n);
+
+S3D_API int s3d_comm_unique_id(void* id128);
+S3D_API int s3d_comm_create(const void* id128, int world, int rank, int device, s3d_comm_t* out);
+S3D_API void s3d_comm_destroy(s3d_comm_t comm);
+S3D_API int s3d_comm_info(s3d_comm_t comm, int* world, int* rank, int* device);
+/* Bytes this rank has sent / received through the communicator since its creation. */
+S3D_API int s3d_comm_traffic(s3d_comm_t comm, unsigned long long* sent, unsigned long long* received);
+
+/* CreateCSIFT3D + KpSiftAlgorithm of ONE volume over the ranks of `comm` (collective).  vol_own = this rank's
+ * OWNED raw planes [own0, own1) of s3d_slab_bounds (host memory, pinned for an asynchronous upload, or device
+ * memory with on_device != 0).  Blocks until this rank's part is done; *out holds the rank's own keypoints
+ * (reference order within the shard) until s3d_slab_gather. */
+S3D_API int s3d_slab_run(s3d_comm_t comm, const float* vol_own, int on_device, int nx, int ny, int nz,
+                         const s3d_params* p, s3d_handle* out);
+/* Collective: merge every rank's results in the reference's order into rank `root`'s handle (its
+ * s3d_num_keypoints / s3d_get_keypoints / s3d_device_descriptors / s3d_get_extrema then answer for the whole
+ * volume); with_extrema = 0 skips the per-detection debug records.  The other ranks keep their own part. */
+S3D_API int s3d_slab_gather(s3d_comm_t comm, s3d_handle h, int root, int with_extrema);
+/* Per-phase device time of this rank's last s3d_slab_run (ms): [0] upload + max + normalise, [1] pyramid incl.
+ * halo exchanges, [2] window-halo exchange, [3] all-reduce + sparse stages, [4] gather (filled by
+ * s3d_slab_gather), [5..7] reserved. */
+S3D_API int s3d_slab_phases(s3d_handle h, double* ms8);
+
+/* The same in ONE process: `nshards` shards, shard g on device devices[g] (repeats allowed; NULL = all on the
+ * current device), `vol` = the whole volume in host memory.  handles[0] receives the merged results, handles[g]
+ * shard g's own part (all must be destroyed by the caller; keep_levels keeps every shard's local levels alive
+ * for s3d_slab_level_buffer / s3d_get_level).  This is what CSIFT3DFactory::CreateCSIFT3D + KpSiftAlgorithm do
+ * when SIFT3D_B200_DEVICES names more than one device. */
+S3D_API int s3d_extract_multi(const float* vol, int nx, int ny, int nz, const s3d_params* p, const int* devices,
+                              int nshards, int with_extrema, s3d_handle* handles);
+S3D_API int s3d_slab_info(s3d_handle h, int* noct, int* halo, int* levels_per_octave, int* first_replicated_octave);
 /* Device address of the local planes of a level (which: 0 Gaussian, 1 DoG) and {za, zb, p0, p1}. */
 S3D_API int s3d_slab_level_buffer(s3d_handle h, int which, int idx, float** d_ptr, int* ext4);
-S3D_API int s3d_slab_get_maxima(s3d_handle h, float* out, int n);
-S3D_API int s3d_slab_set_maxima(s3d_handle h, const float* in, int n);
-S3D_API int s3d_slab_finish(s3d_handle h);
 
 /* ---- free kernels (parity hooks ≙ Include/cSIFT3D.h:208-239) ------------------------------- */
 /* GaussianSmooth_3D  Src/cSIFT3D.cc:535-622 (host buffers in/out). */

@@ -86,8 +86,8 @@ big = torch.from_numpy(synth.v_blobs(a.big, seed=0)).pin_memory().numpy()   # nu
 res, sec = timed(lambda: D.extract_slabs(big, with_extrema=False), reps=3)
 phases = {}
 D.extract_slabs(big, timing=phases, with_extrema=False)
-out["slab_timing"] = {"size": a.big, "seconds": sec, "phases_s": {k: round(v, 4) for k, v in phases.items()}, "mvoxels_per_s": big.size / sec / 1e6, "keypoints": int(len(res["kp"])),
-                      "note": "pinned host volume in, merged keypoints + descriptors out on the host of every rank (includes the per-shard upload and the NCCL result gather)"}
+out["slab_timing"] = {"size": a.big, "seconds": sec, "phases_ms": {k: round(v, 3) for k, v in phases.items() if not isinstance(v, list)}, "mvoxels_per_s": big.size / sec / 1e6, "keypoints": int(len(res["kp"])),
+                      "note": "pinned host volume in, merged keypoints + descriptors out on the host of rank 0 (includes the per-shard upload and the NCCL result gather)"}
 del res
 dr, dt_, _ = synth.d_synth_pair_device(a.match_big, seed=9)   # same seed on every rank: replicated, HBM-resident sets
 res, sec = timed(lambda: D.match_sharded(3, dr, dt_, 0.85))

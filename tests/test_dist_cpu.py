@@ -239,3 +239,72 @@ def test_merge_shard_results_restores_reference_order(s3d):
     got = [(int(r["octave"]), int(r["level"]), int(r["z"])) for r in m["kp"]]
     assert got == [(0, 1, 3), (0, 1, 5), (0, 1, 40), (0, 2, 1), (0, 3, 33), (1, 1, 2), (1, 1, 20), (1, 1, 21)]
     assert [tuple(r[2:]) for r in m["xyz5"]] == [(z, o, l) for o, l, z in got]
+
+
+# ---- the library's own plane bookkeeping (s3d_slab.cu; host logic, no GPU) ---------------------------------------
+
+def test_library_bounds_equal_python_bounds(s3d):
+    import ctypes as C
+    d = importlib.import_module("3dsift_b200.dist")
+    L = s3d.lib()
+    for nz, G in ((512, 8), (512, 2), (96, 3), (70, 2), (64, 4), (20, 8), (9, 1)):
+        b = d.slab_bounds(nz, G)
+        for r in range(G):
+            o0, o1 = C.c_int(), C.c_int()
+            assert L.s3d_slab_bounds(nz, G, r, C.byref(o0), C.byref(o1)) == 0
+            assert (o0.value, o1.value) == (b[r], b[r + 1])
+
+
+def test_library_halo_plan_pairs_up_and_covers_the_halo(s3d):
+    """Every receive of rank b from rank a has the matching send of a to b at the same position of the (a, b) sequence
+    (the pairing contract of Comm::p2p), receives cover exactly the halo planes other shards own, and sends only name
+    owned planes."""
+    d = importlib.import_module("3dsift_b200.dist")
+    for nz, G, o, depth in ((512, 8, 0, 9), (512, 8, 1, 38), (512, 8, 2, 38), (512, 4, 2, -1), (96, 3, 0, 5), (200, 8, 0, 30),
+                            (72, 3, 1, 38), (64, 4, 0, -1)):
+        nzo = nz >> o
+        b = d.slab_bounds(nz, G)
+        own = [(min(nzo, (b[r] + (1 << o) - 1) >> o), min(nzo, (b[r + 1] + (1 << o) - 1) >> o)) for r in range(G)]
+        plans = [d.plan_from_library(nz, G, r, o, depth) for r in range(G)]
+        for r in range(G):
+            p0, p1 = own[r]
+            if depth < 0:
+                need = set(range(0, p0)) | set(range(p1, nzo))
+            elif p1 > p0:
+                need = set(range(max(0, p0 - depth), p0)) | set(range(p1, min(nzo, p1 + depth)))
+            else:
+                need = set()
+            got = [k for peer, kind, k0, k1 in plans[r] if kind == "recv" for k in range(k0, k1)]
+            assert sorted(got) == sorted(need), (nz, G, o, depth, r)
+            for peer, kind, k0, k1 in plans[r]:
+                if kind == "send":
+                    assert own[r][0] <= k0 < k1 <= own[r][1]
+                else:
+                    assert own[peer][0] <= k0 < k1 <= own[peer][1]
+        for a in range(G):
+            for bb in range(G):
+                if a == bb:
+                    continue
+                sends = [(k0, k1) for peer, kind, k0, k1 in plans[a] if kind == "send" and peer == bb]
+                recvs = [(k0, k1) for peer, kind, k0, k1 in plans[bb] if kind == "recv" and peer == a]
+                assert sends == recvs, (nz, G, o, depth, a, bb)
+
+
+def test_library_first_replicated_octave(s3d, monkeypatch):
+    import ctypes as C
+    L = s3d.lib()
+
+    def first(n, world):
+        o = C.c_int()
+        assert L.s3d_slab_first_replicated(n, n, n, world, None, C.byref(o)) == 0
+        return o.value
+    monkeypatch.delenv("S3D_SLAB_MIN_NZ", raising=False)
+    assert first(512, 1) == 7                       # one shard: nothing is replicated
+    assert first(512, 2) == 3                       # 64^3 and below are computed by every shard
+    assert first(512, 8) == 3
+    assert first(256, 8) == 2
+    assert first(64, 2) == 0                        # below the sharding threshold: the input itself is gathered
+    monkeypatch.setenv("S3D_SLAB_MIN_NZ", "0")
+    assert first(512, 8) == 3                       # 64 planes / 8 shards = 8 < 10 planes per shard
+    assert first(512, 2) == 5                       # 16 planes / 2 = 8
+    assert first(64, 2) == 2
