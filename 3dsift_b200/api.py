@@ -141,6 +141,8 @@ def lib():
     L.s3d_pairs_device.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     L.s3d_match_ex.argtypes = [C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_double] + [vp] * 12
     L.s3d_set_match_path.argtypes = [C.c_int]
+    L.s3d_match_sharded.argtypes = [vp, C.c_int, fp, C.c_int, fp, C.c_int, C.c_double] + [vp] * 12
+    L.s3d_match_multi.argtypes = [C.c_int, fp, C.c_int, fp, C.c_int, C.c_double, C.POINTER(C.c_int), C.c_int] + [vp] * 12
     L.s3d_read_nii.restype = C.POINTER(C.c_float)
     L.s3d_read_nii.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.s3d_free_host.restype = None
@@ -164,6 +166,8 @@ def lib():
     L.s3d_comm_info.argtypes = [vp, ip, ip, ip]
     L.s3d_comm_traffic.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     L.s3d_slab_run.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
+    L.s3d_slab_create.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
+    L.s3d_slab_execute.argtypes = [vp, vp]
     L.s3d_slab_gather.argtypes = [vp, vp, C.c_int, C.c_int]
     L.s3d_slab_phases.argtypes = [vp, C.POINTER(C.c_double * 8)]
     L.s3d_extract_multi.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), ip, C.c_int, C.c_int, C.POINTER(vp)]

@@ -35,6 +35,15 @@ struct Comm {
     virtual int finish(cudaStream_t st) = 0;
 };
 
+// In-process transport (s3d_slab.cu): one LocalGroup per collective job, one LocalComm per shard / host thread.
+struct LocalGroup;
+LocalGroup* local_group_create(int world);
+void local_group_destroy(LocalGroup* g);
+void local_group_fail(LocalGroup* g);                          // wake every shard blocked in a barrier
+Comm* local_comm_create(LocalGroup* g, int rank, int device);  // nullptr on failure (s3d_last_error)
+// shard bounds shared by both sharded paths: contiguous, balanced index ranges, rank r owns [b[r], b[r+1])
+inline int shard_lo(long long n, int world, int r) { return (int)(n / world * r + (n % world < r ? n % world : r)); }
+
 }  // namespace s3d
 
 struct s3d_comm {

@@ -137,7 +137,7 @@ struct s3d_ctx {
     bool ev_ok = false;
     double timers[10] = {0};
     // phase boundaries of a sharded run (s3d_slab.cu) and their device times in ms (s3d_slab_phases)
-    cudaEvent_t ph_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ph_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double ph_ms[8] = {0};
 };
 

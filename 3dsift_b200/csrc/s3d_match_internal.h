@@ -49,6 +49,23 @@ __device__ __forceinline__ void top2_merge(Top2& a, const Top2& b) {
 // tensor-core guard (an entry that is negative, above 1 or not finite): nothing was written to d_out / d_fb_list and the
 // caller must run the exact kernel for these rows.
 constexpr int kTcRefused = -1000;
+// Working set of one tensor-core search (device temporaries from the stream-ordered pool; release with tc_free).
+struct TcWork {
+    void* q16 = nullptr;      // __half [nql][768], x64
+    void* db16 = nullptr;     // __half [nd][768], x64
+    float* cand_val = nullptr;
+    int* cand_idx = nullptr;  // [nql][parts * 8]
+    int* d_bad = nullptr;     // device flag: an entry outside [0, 1] or not finite was seen
+    int nql = 0, nd = 0, parts = 0, ncand = 0, tiles_per_part = 0, n_dbtiles = 0, n_units = 0, sms = 148;
+    bool pair = false;
+};
+int tc_convert(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, cudaStream_t st, int variant, TcWork& w);
+int tc_topk(cudaStream_t st, TcWork& w);
+int tc_merge8(cudaStream_t st, const TcWork& w, int idx_offset, float* out_val, int* out_idx);
+int tc_rerank(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, const float* cand_val,
+              const int* cand_idx, int nlists, size_t stride_q, size_t stride_p, Top2* d_out, int* d_fb_list, int* d_fb_count,
+              cudaStream_t st);
+void tc_free(TcWork& w, cudaStream_t st);
 int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, Top2* d_out,
               int* d_fb_list, int* d_fb_count, cudaStream_t st, int variant);
 

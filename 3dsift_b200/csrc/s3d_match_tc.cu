@@ -567,13 +567,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 //             second-best exceeds that bound the eight provably contain the true top-2, otherwise the
 //             row goes to the exact CUDA-core kernel.
 // q rows are addressed through qlist (original row index); results are written to out[orig].
+// The candidate lists of query qi are `parts` (<= 8) top-8 lists at cand[qi * stride_q + p * stride_p + 0..7]: the parts
+// of one tensor-core pass ([query][part][8]: stride_q = parts * 8, stride_p = 8) or, in the database-sharded search, one
+// merged list per rank as they arrive from the ranks ([rank][query][8]: stride_q = 8, stride_p = rows * 8).
+// MERGE_ONLY: stop after step 1 and write the merged list (value, index + idx_offset) to mrg_val / mrg_idx [query][8]
+// (what a rank sends to the rank that re-ranks the query).
 constexpr int kRrWarps = 8;
+template <bool MERGE_ONLY>
 __global__ void __launch_bounds__(kRrWarps * 32) rerank_kernel(const float* __restrict__ q, const int* __restrict__ qlist, int nql,
-                                                               const float* __restrict__ db, int nd, int db_offset, int ncand,
+                                                               const float* __restrict__ db, int nd, int db_offset, int parts,
+                                                               size_t stride_q, size_t stride_p,
                                                                const float* __restrict__ cand_val,
                                                                const int* __restrict__ cand_idx, Top2* __restrict__ out,
-                                                               int* __restrict__ fb_list, int* fb_count) {
-    __shared__ float tile[kRrWarps][32][33];
+                                                               int* __restrict__ fb_list, int* fb_count,
+                                                               float* __restrict__ mrg_val, int* __restrict__ mrg_idx, int idx_offset) {
+    __shared__ float tile[MERGE_ONLY ? 1 : kRrWarps][32][33];
     __shared__ int pair_j[kRrWarps][32];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, c = lane & 7;
     const int gw = blockIdx.x * kRrWarps + wid;
@@ -581,17 +589,17 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_kernel(const float* __re
     const int qi = gw * 4 + g;
     const bool qvalid = qi < nql;
     const int orig = qvalid ? (qlist ? qlist[qi] : qi) : 0;
-    const int parts = ncand / TOPK;  // <= 8
     // ---- 1. merge ----
     float ev[8];
     int ej[8];
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
         const bool ok = qvalid && p < parts;
-        ej[p] = ok ? cand_idx[(size_t)qi * ncand + p * TOPK + c] : -1;
-        ev[p] = ok ? cand_val[(size_t)qi * ncand + p * TOPK + c] : -1.0f;
+        ej[p] = ok ? cand_idx[(size_t)qi * stride_q + p * stride_p + c] : -1;
+        ev[p] = ok ? cand_val[(size_t)qi * stride_q + p * stride_p + c] : -1.0f;
     }
     int myj = -1;
+    float myv = -1.0f;
     float a8 = -1.0f;
 #pragma unroll 1
     for (int r = 0; r < TOPK; ++r) {
@@ -613,13 +621,20 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_kernel(const float* __re
         for (int p = 0; p < 8; ++p)
             if (p == lp) lj = ej[p];
         const int selj = __shfl_sync(0xffffffffu, lj, (lane & ~7) | gl);
-        if (c == r) myj = selj;
+        if (c == r) { myj = selj; myv = gv; }
         if (c == gl && lp >= 0) {
 #pragma unroll
             for (int p = 0; p < 8; ++p)
                 if (p == lp) ej[p] = -1;
         }
         if (r == TOPK - 1) a8 = selj >= 0 ? gv : -1.0f;
+    }
+    if constexpr (MERGE_ONLY) {
+        if (qvalid) {
+            mrg_val[(size_t)qi * TOPK + c] = myj >= 0 ? myv : -1.0f;
+            mrg_idx[(size_t)qi * TOPK + c] = myj >= 0 ? myj + idx_offset : -1;
+        }
+        return;
     }
     // ---- 2. exact dots, coalesced ----
     pair_j[wid][lane] = myj;
@@ -706,15 +721,17 @@ static int choose_parts(int units, int n_dbtiles, int workers) {
     return best;
 }
 
-// Tensor-core search of `nql` query rows (qlist maps to original rows, may be null) against db.
-// out[orig] receives the exact top-2; rows whose candidate set could not be proven complete are
-// appended to fb_list / *fb_count (device) for the exact kernel.
-// variant: 0 = choose by size, 1 = one CTA per tile (tc_topk_kernel), 2 = CTA pairs with the query
-// tile resident in shared memory (tc_pair_topk_kernel).
-int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, Top2* d_out,
-              int* d_fb_list, int* d_fb_count, cudaStream_t st, int variant) {
+// ---- host side of the tensor-core search, in reusable steps (the single-GPU search runs them back to back; the
+// database-sharded search interleaves them with the exchange of candidate lists, s3d_match.cu) ------------------------
+void tc_free(TcWork& w, cudaStream_t st) {
+    void* tmp[] = {w.q16, w.db16, w.cand_val, w.cand_idx, w.d_bad};
+    for (void* p : tmp) if (p) cudaFreeAsync(p, st);
+    w = TcWork();
+}
+
+// FP16 copies of the listed query rows and of the database rows, and the precondition flag *w.d_bad (device).
+int tc_convert(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, cudaStream_t st, int variant, TcWork& w) {
     using namespace tc;
-    if (nql <= 0 || nd <= 0) return S3D_OK;
     int dev = 0, sms = 148;
     S3D_CUDA(cudaGetDevice(&dev));
     S3D_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -727,23 +744,21 @@ int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, 
     // Measured on B200 (profiles/): the one-CTA-per-tile kernel keeps the tensor pipe 90 % busy; the pair
     // kernel moves a third of the L2->SM bytes (and holds higher clocks under the power cap) but its
     // 4 x 8 KB ring leaves the pipe 79 % busy, so it is selected only on request.
-    const bool pair = variant == 2;
-    __half *q16 = nullptr, *db16 = nullptr;
-    float* cand_val = nullptr;
-    int* cand_idx = nullptr;
-    int* d_bad = nullptr;
-    const int n_dbtiles = (nd + BN - 1) / BN;
-    const int n_units = pair ? (nql + 2 * pr::BMC - 1) / (2 * pr::BMC) : (nql + BM - 1) / BM;
-    const int workers = pair ? std::max(1, sms / 2) : sms;
-    int parts = choose_parts(n_units, n_dbtiles, workers);
-    const int tiles_per_part = (n_dbtiles + parts - 1) / parts;
-    parts = (n_dbtiles + tiles_per_part - 1) / tiles_per_part;
-    const int ncand = parts * TOPK;
+    w.pair = variant == 2;
+    w.sms = sms;
+    w.nql = nql; w.nd = nd;
+    w.n_dbtiles = (nd + BN - 1) / BN;
+    w.n_units = w.pair ? (nql + 2 * pr::BMC - 1) / (2 * pr::BMC) : (nql + BM - 1) / BM;
+    const int workers = w.pair ? std::max(1, sms / 2) : sms;
+    int parts = choose_parts(w.n_units, std::max(w.n_dbtiles, 1), workers);
+    w.tiles_per_part = std::max(1, (w.n_dbtiles + parts - 1) / parts);
+    w.parts = std::max(1, (w.n_dbtiles + w.tiles_per_part - 1) / w.tiles_per_part);
+    w.ncand = w.parts * TOPK;
     // capacity: the FP16 copies and candidate lists are temporaries on top of the caller's FP32 sets (1 M x 1 M:
     // 2 x 1.5 GB + 64 MB * parts); refuse up front rather than fail half-way through a stream-ordered allocation
     {
         size_t free_b = 0, total_b = 0;
-        const size_t need = sizeof(__half) * KD * ((size_t)nql + (size_t)nd) + (sizeof(float) + sizeof(int)) * (size_t)nql * ncand;
+        const size_t need = sizeof(__half) * KD * ((size_t)nql + (size_t)nd) + (sizeof(float) + sizeof(int)) * (size_t)nql * w.ncand;
         if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
             uint64_t pooled = 0;  // bytes the stream-ordered pool already holds and can hand out again
             cudaMemPool_t pool;
@@ -758,46 +773,95 @@ int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, 
                             nql, nd, need / 1e9, (free_b + pooled) / 1e9);
         }
     }
-    // every exit below goes through `done`, which returns the temporaries to the pool (early returns leaked)
-    auto done = [&](int rc) -> int {
-        void* tmp[] = {q16, db16, cand_val, cand_idx, d_bad};
-        for (void* p : tmp) if (p) cudaFreeAsync(p, st);
-        return rc;
-    };
+    S3D_CUDA(cudaMallocAsync((void**)&w.q16, sizeof(__half) * KD * (size_t)std::max(nql, 1), st));
+    S3D_CUDA(cudaMallocAsync((void**)&w.db16, sizeof(__half) * KD * (size_t)std::max(nd, 1), st));
+    S3D_CUDA(cudaMallocAsync((void**)&w.d_bad, sizeof(int), st));
+    S3D_CUDA(cudaMemsetAsync(w.d_bad, 0, sizeof(int), st));
+    if (nql > 0) S3D_LAUNCH(cvt_f16_kernel, s3d_blocks((size_t)nql * 32, 256), 256, 0, st, d_q, d_qlist, nql, (__half*)w.q16, w.d_bad);
+    if (nd > 0) S3D_LAUNCH(cvt_f16_kernel, s3d_blocks((size_t)nd * 32, 256), 256, 0, st, d_db, (const int*)nullptr, nd, (__half*)w.db16, w.d_bad);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+// The candidate pass: w.cand_val / w.cand_idx [nql][parts * 8] (index -1 = empty slot; indices local to the database).
+int tc_topk(cudaStream_t st, TcWork& w) {
+    using namespace tc;
+    const int nql = w.nql, nd = w.nd;
+    S3D_CUDA(cudaMallocAsync((void**)&w.cand_val, sizeof(float) * (size_t)std::max(nql, 1) * w.ncand, st));
+    S3D_CUDA(cudaMallocAsync((void**)&w.cand_idx, sizeof(int) * (size_t)std::max(nql, 1) * w.ncand, st));
+    if (nql <= 0) return S3D_OK;
+    if (nd <= 0) {  // an empty database shard: every slot empty
+        S3D_CUDA(cudaMemsetAsync(w.cand_idx, 0xFF, sizeof(int) * (size_t)nql * w.ncand, st));
+        S3D_CUDA(cudaMemsetAsync(w.cand_val, 0, sizeof(float) * (size_t)nql * w.ncand, st));
+        return S3D_OK;
+    }
+    CUtensorMap mq, mdb;
+    S3D_TRY(make_map(&mq, (const __half*)w.q16, nql, BM));
+    S3D_TRY(make_map(&mdb, (const __half*)w.db16, nd, w.pair ? pr::BROWS : BN));
+    const int workers = w.pair ? std::max(1, w.sms / 2) : w.sms;
+    if (w.pair) {
+        const int grid = 2 * std::min(workers, w.n_units * w.parts);
+        // chunk = the slice of the database all clusters sweep together; parts are swept concurrently, so
+        // together they should stay well inside L2 (126 MB, shared with the streaming query tiles)
+        const int chunk_tiles = std::max(8, pr::kChunkTiles / w.parts);
+        S3D_LAUNCH(tc_pair_topk_kernel, grid, kThreads, pr::SMEM_BYTES, st, mq, mdb, nql, nd, w.n_units, w.parts, w.tiles_per_part,
+                   w.n_dbtiles, chunk_tiles, w.cand_val, w.cand_idx);
+    } else {
+        const int grid = std::min(w.sms, w.n_units * w.parts);
+        S3D_LAUNCH(tc_topk_kernel, grid, kThreads, SMEM_BYTES, st, mq, mdb, nql, nd, w.n_units, w.parts, w.tiles_per_part, w.n_dbtiles,
+                   w.cand_val, w.cand_idx);
+    }
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+// Merge the parts' lists to one top-8 per query: out_val / out_idx [nql][8], indices + idx_offset.
+int tc_merge8(cudaStream_t st, const TcWork& w, int idx_offset, float* out_val, int* out_idx) {
+    using namespace tc;
+    if (w.nql <= 0) return S3D_OK;
+    S3D_LAUNCH(rerank_kernel<true>, s3d_blocks((size_t)w.nql, 4 * kRrWarps), kRrWarps * 32, 0, st, (const float*)nullptr, (const int*)nullptr,
+               w.nql, (const float*)nullptr, 0, 0, w.parts, (size_t)w.ncand, (size_t)TOPK, w.cand_val, w.cand_idx, (Top2*)nullptr,
+               (int*)nullptr, (int*)nullptr, out_val, out_idx, idx_offset);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+// Exact re-rank of `nql` listed queries against db from `nlists` (<= 8) top-8 lists per query (see rerank_kernel).
+int tc_rerank(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, const float* cand_val,
+              const int* cand_idx, int nlists, size_t stride_q, size_t stride_p, Top2* d_out, int* d_fb_list, int* d_fb_count,
+              cudaStream_t st) {
+    using namespace tc;
+    if (nql <= 0) return S3D_OK;
+    if (nlists > 8) return fail(S3D_ERR_ARG, "re-rank merges at most 8 candidate lists per query (%d given)", nlists);
+    S3D_LAUNCH(rerank_kernel<false>, s3d_blocks((size_t)nql, 4 * kRrWarps), kRrWarps * 32, 0, st, d_q, d_qlist, nql, d_db, nd, db_offset,
+               nlists, stride_q, stride_p, cand_val, cand_idx, d_out, d_fb_list, d_fb_count, (float*)nullptr, (int*)nullptr, 0);
+    S3D_CUDA(cudaGetLastError());
+    return S3D_OK;
+}
+
+// Tensor-core search of `nql` query rows (qlist maps to original rows, may be null) against db.
+// out[orig] receives the exact top-2; rows whose candidate set could not be proven complete are
+// appended to fb_list / *fb_count (device) for the exact kernel.
+// variant: 0 = choose by size, 1 = one CTA per tile (tc_topk_kernel), 2 = CTA pairs with the query
+// tile resident in shared memory (tc_pair_topk_kernel).
+int tc_search(const float* d_q, const int* d_qlist, int nql, const float* d_db, int nd, int db_offset, Top2* d_out,
+              int* d_fb_list, int* d_fb_count, cudaStream_t st, int variant) {
+    if (nql <= 0 || nd <= 0) return S3D_OK;
+    TcWork w;
+    // every exit goes through tc_free, which returns the temporaries to the pool (early returns leaked)
     auto body = [&]() -> int {
-        S3D_CUDA(cudaMallocAsync((void**)&q16, sizeof(__half) * KD * (size_t)nql, st));
-        S3D_CUDA(cudaMallocAsync((void**)&db16, sizeof(__half) * KD * (size_t)nd, st));
-        S3D_CUDA(cudaMallocAsync((void**)&d_bad, sizeof(int), st));
-        S3D_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
-        S3D_LAUNCH(cvt_f16_kernel, s3d_blocks((size_t)nql * 32, 256), 256, 0, st, d_q, d_qlist, nql, q16, d_bad);
-        S3D_LAUNCH(cvt_f16_kernel, s3d_blocks((size_t)nd * 32, 256), 256, 0, st, d_db, (const int*)nullptr, nd, db16, d_bad);
+        S3D_TRY(tc_convert(d_q, d_qlist, nql, d_db, nd, st, variant, w));
         int h_bad = 0;
-        S3D_CUDA(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        S3D_CUDA(cudaMemcpyAsync(&h_bad, w.d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
         S3D_CUDA(cudaStreamSynchronize(st));
         if (h_bad) return kTcRefused;  // outside the guard's precondition: the caller runs the exact kernel
-        S3D_CUDA(cudaMallocAsync((void**)&cand_val, sizeof(float) * (size_t)nql * ncand, st));
-        S3D_CUDA(cudaMallocAsync((void**)&cand_idx, sizeof(int) * (size_t)nql * ncand, st));
-        CUtensorMap mq, mdb;
-        S3D_TRY(make_map(&mq, q16, nql, BM));
-        S3D_TRY(make_map(&mdb, db16, nd, pair ? pr::BROWS : BN));
-        if (pair) {
-            const int grid = 2 * std::min(workers, n_units * parts);
-            // chunk = the slice of the database all clusters sweep together; parts are swept concurrently, so
-            // together they should stay well inside L2 (126 MB, shared with the streaming query tiles)
-            const int chunk_tiles = std::max(8, pr::kChunkTiles / parts);
-            S3D_LAUNCH(tc_pair_topk_kernel, grid, kThreads, pr::SMEM_BYTES, st, mq, mdb, nql, nd, n_units, parts, tiles_per_part,
-                       n_dbtiles, chunk_tiles, cand_val, cand_idx);
-        } else {
-            const int grid = std::min(sms, n_units * parts);
-            S3D_LAUNCH(tc_topk_kernel, grid, kThreads, SMEM_BYTES, st, mq, mdb, nql, nd, n_units, parts, tiles_per_part, n_dbtiles,
-                       cand_val, cand_idx);
-        }
-        S3D_LAUNCH(rerank_kernel, s3d_blocks((size_t)nql, 4 * kRrWarps), kRrWarps * 32, 0, st, d_q, d_qlist, nql, d_db, nd, db_offset, ncand,
-                   cand_val, cand_idx, d_out, d_fb_list, d_fb_count);
-        S3D_CUDA(cudaGetLastError());
-        return S3D_OK;
+        S3D_TRY(tc_topk(st, w));
+        return tc_rerank(d_q, d_qlist, nql, d_db, nd, db_offset, w.cand_val, w.cand_idx, w.parts, (size_t)w.ncand, (size_t)tc::TOPK, d_out,
+                         d_fb_list, d_fb_count, st);
     };
-    return done(body());
+    const int rc = body();
+    tc_free(w, st);
+    return rc;
 }
 
 }  // namespace s3d

@@ -247,6 +247,16 @@ struct LocalComm : Comm {
     }
 };
 
+LocalGroup* local_group_create(int world) { return new LocalGroup(world); }
+void local_group_destroy(LocalGroup* g) { delete g; }
+void local_group_fail(LocalGroup* g) { g->failed = true; }
+Comm* local_comm_create(LocalGroup* g, int rank, int device) {
+    LocalComm* cm = new LocalComm();
+    cm->world = g->world; cm->rank = rank; cm->device = device; cm->g = g;
+    if (cm->init() != S3D_OK) { delete cm; return nullptr; }
+    return cm;
+}
+
 // =================================================================================================
 // Plane bookkeeping (host logic; identical on every rank)
 // =================================================================================================
@@ -351,21 +361,24 @@ static int exchange(s3d_ctx* c, Comm& cm, float* buf, int o, int depth) {
 // =================================================================================================
 // The sharded run
 // =================================================================================================
-static int slab_run_impl(Comm& cm, const float* vol_own, int on_device, int nx, int ny, int nz, const s3d_params* p, s3d_ctx** out) {
+// CreateCSIFT3D for one shard: allocate, copy the owned planes, first sweep of data_scale (max|v| over them).  Only
+// ENQUEUES work on the shard's own stream and involves no other rank, so the upload of the next volume can run under
+// the extraction of the current one.
+static int slab_create_impl(int world, int rank, int device, const float* vol_own, int on_device, int nx, int ny, int nz,
+                            const s3d_params* p, s3d_ctx** out) {
     s3d_ctx* c = new s3d_ctx();
     *out = c;  // the caller destroys it, also on failure
     s3d_params prm;
     if (p) prm = *p; else s3d_default_params(&prm);
-    prm.device = cm.device;
+    prm.device = device;
     S3D_TRY(ctx_common_init(c, nx, ny, nz, &prm));
     c->slab = true;
-    slab_bounds_of(nz, cm.world, cm.rank, &c->own0, &c->own1);
-    c->first_full = first_replicated(nx, ny, nz, cm.world);
+    slab_bounds_of(nz, world, rank, &c->own0, &c->own1);
+    c->first_full = first_replicated(nx, ny, nz, world);
     cudaStream_t st = c->stream;
     for (auto& e : c->ph_ev) S3D_CUDA(cudaEventCreate(&e));
-    S3D_CUDA(cudaEventRecord(c->ph_ev[0], st));
+    S3D_CUDA(cudaEventRecord(c->ph_ev[6], st));
     S3D_TRY(stage_init(c));
-    const int G = c->G, D = c->D, L = c->L;
     const size_t plane0 = c->plane(0);
     // ---- CreateCSIFT3D: copy + data_scale (Src/cSIFT3D.cc:146-163, Src/cUtil.cc:536-564) ------------------
     S3D_CUDA(s3d::dev_alloc((void**)&c->d_input, std::max<size_t>(c->lvox(0), 4) * sizeof(float), st));
@@ -377,6 +390,20 @@ static int slab_run_impl(Comm& cm, const float* vol_own, int on_device, int nx, 
         S3D_CUDA(cudaMemcpyAsync(own_ptr, vol_own, nown * sizeof(float), on_device ? cudaMemcpyDefault : cudaMemcpyHostToDevice, st));
     }
     S3D_TRY(stage_input_max(c, own_ptr, nown));
+    S3D_CUDA(cudaEventRecord(c->ph_ev[5], st));  // end of the upload phase proper
+    return S3D_OK;
+}
+
+// KpSiftAlgorithm over the shards (collective): second sweep of data_scale with the global maximum, pyramid with halo
+// exchanges, thresholds, sparse stages on the owned planes.  Blocks until this shard's results are ready.
+static int slab_run_impl(Comm& cm, s3d_ctx* c) {
+    if (!c->slab || c->stage != 1 || c->ran) return fail(S3D_ERR_STATE, "not a freshly created slab handle");
+    cudaStream_t st = c->stream;
+    const int G = c->G, D = c->D, L = c->L;
+    const size_t plane0 = c->plane(0);
+    const size_t nown = plane0 * (size_t)(c->own1 - c->own0);
+    float* own_ptr = c->d_input + plane0 * (size_t)(c->own0 - c->za[0]);
+    S3D_CUDA(cudaEventRecord(c->ph_ev[0], st));
     S3D_TRY(cm.allreduce_max_u32(c->d_slots, 1, st));
     S3D_TRY(stage_input_normalize(c, own_ptr, own_ptr, nown));
     S3D_CUDA(cudaEventRecord(c->ph_ev[1], st));
@@ -421,6 +448,11 @@ static int slab_run_impl(Comm& cm, const float* vol_own, int on_device, int nx, 
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ph_ev[k], c->ph_ev[k + 1]);
         c->ph_ms[k] = ms;
+    }
+    {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ph_ev[6], c->ph_ev[5]);
+        c->ph_ms[5] = ms;
     }
     return S3D_OK;
 }
@@ -662,15 +694,30 @@ int s3d_comm_traffic(s3d_comm_t comm, unsigned long long* sent, unsigned long lo
     return S3D_OK;
 }
 
-int s3d_slab_run(s3d_comm_t comm, const float* vol_own, int on_device, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
+int s3d_slab_create(s3d_comm_t comm, const float* vol_own, int on_device, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
     clear_error();
     if (!comm || !comm->impl || !out) return fail(S3D_ERR_ARG, "null argument");
     S3D_CUDA(cudaSetDevice(comm->impl->device));
     s3d_ctx* c = nullptr;
-    const int r = slab_run_impl(*comm->impl, vol_own, on_device, nx, ny, nz, p, &c);
+    const int r = slab_create_impl(comm->impl->world, comm->impl->rank, comm->impl->device, vol_own, on_device, nx, ny, nz, p, &c);
     if (r != S3D_OK) { if (c) s3d_destroy(c); *out = nullptr; return r; }
     *out = c;
     return S3D_OK;
+}
+
+int s3d_slab_execute(s3d_comm_t comm, s3d_handle h) {
+    clear_error();
+    if (!comm || !comm->impl || !h) return fail(S3D_ERR_ARG, "null argument");
+    S3D_CUDA(cudaSetDevice(comm->impl->device));
+    return slab_run_impl(*comm->impl, h);
+}
+
+int s3d_slab_run(s3d_comm_t comm, const float* vol_own, int on_device, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
+    int r = s3d_slab_create(comm, vol_own, on_device, nx, ny, nz, p, out);
+    if (r != S3D_OK) return r;
+    r = s3d_slab_execute(comm, *out);
+    if (r != S3D_OK) { s3d_destroy(*out); *out = nullptr; }
+    return r;
 }
 
 int s3d_slab_gather(s3d_comm_t comm, s3d_handle h, int root, int with_extrema) {
@@ -716,8 +763,9 @@ int s3d_extract_multi(const float* vol, int nx, int ny, int nz, const s3d_params
         if (r == S3D_OK) {
             int own0, own1;
             slab_bounds_of(nz, nshards, g, &own0, &own1);
-            r = slab_run_impl(cm, vol + (size_t)own0 * nx * ny, 0, nx, ny, nz, &prm, &ctx[g]);
+            r = slab_create_impl(nshards, g, rdev, vol + (size_t)own0 * nx * ny, 0, nx, ny, nz, &prm, &ctx[g]);
         }
+        if (r == S3D_OK) r = slab_run_impl(cm, ctx[g]);
         if (r == S3D_OK) r = slab_gather_impl(cm, ctx[g], 0, with_extrema);
         if (r != S3D_OK) {
             group.failed = true;

@@ -134,6 +134,53 @@ def match_sharded(mtype, ref, tar, thr=0.85, ops=None, group=None):
     return out
 
 
+def match_sharded_c(mtype, d_ref, d_tar, thr=0.85, group=None, comm=None, stream=None):
+    """s3d_match_sharded: bijectMatchBase (Src/cMatcher.cc:146-215) over the library's NCCL communicator of ``group`` —
+    database-sharded candidate pass, query-sharded exact re-rank, all inside the library.  ``d_ref`` / ``d_tar``: the
+    FULL n x 768 float32 CUDA tensors (replicated on every rank).  Returns CUDA tensors, complete on every rank:
+    dict(gIdx, gDist, sIdx, sDist, gIdx2, gDist2, sIdx2, sDist2, pairs [n_pairs, 2])."""
+    import torch
+    comm = comm or nccl_comm(group)
+    n_ref, n_tar = int(d_ref.shape[0]), int(d_tar.shape[0])
+    dev = d_ref.device
+    I = lambda m: torch.empty(max(m, 1), dtype=torch.int32, device=dev)
+    F = lambda m: torch.empty(max(m, 1), dtype=torch.float32, device=dev)
+    b = dict(gIdx=I(n_ref), gDist=F(n_ref), sIdx=I(n_ref), sDist=F(n_ref), gIdx2=I(n_tar), gDist2=F(n_tar), sIdx2=I(n_tar),
+             sDist2=F(n_tar), pr=I(n_ref), pt=I(n_ref), np=I(1))
+    st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+    api.check(api.lib().s3d_match_sharded(comm._c, mtype, d_ref.data_ptr(), n_ref, d_tar.data_ptr(), n_tar, float(thr),
+                                          *[b[k].data_ptr() for k in ("gIdx", "gDist", "sIdx", "sDist", "gIdx2", "gDist2", "sIdx2",
+                                                                      "sDist2", "pr", "pt", "np")], C.c_void_p(st or 1)))
+    n = int(b["np"].item())
+    out = {k: b[k][: (n_ref if not k.endswith("2") else n_tar)] for k in ("gIdx", "gDist", "sIdx", "sDist", "gIdx2", "gDist2", "sIdx2", "sDist2")}
+    out["pairs"] = torch.stack([b["pr"][:n], b["pt"][:n]], 1)
+    return out
+
+
+def match_multi(mtype, ref, tar, thr=0.85, devices=None, shards=None):
+    """s3d_match_multi: the same in ONE process over several devices (host threads + peer copies), host arrays in and
+    out.  ``devices`` = list of device ordinals, or ``shards`` = G logical shards on the current device (CI check)."""
+    ref = np.ascontiguousarray(ref, dtype=np.float32).reshape(-1, api.DESC_LENGTH)
+    tar = np.ascontiguousarray(tar, dtype=np.float32).reshape(-1, api.DESC_LENGTH)
+    n_ref, n_tar = len(ref), len(tar)
+    G = len(devices) if devices is not None else int(shards or 1)
+    devs = (C.c_int * G)(*devices) if devices is not None else None
+    A = lambda n, t: np.zeros(max(n, 1), t)
+    r = dict(gIdx=A(n_ref, np.int32), gDist=A(n_ref, np.float32), sIdx=A(n_ref, np.int32), sDist=A(n_ref, np.float32),
+             gIdx2=A(n_tar, np.int32), gDist2=A(n_tar, np.float32), sIdx2=A(n_tar, np.int32), sDist2=A(n_tar, np.float32),
+             pr=A(n_ref, np.int32), pt=A(n_ref, np.int32))
+    npairs = C.c_int()
+    times = (C.c_double * 3)()
+    api.check(api.lib().s3d_match_multi(mtype, api._ptr(ref), n_ref, api._ptr(tar), n_tar, float(thr), devs, G,
+                                        *[api._ptr(r[k]) for k in ("gIdx", "gDist", "sIdx", "sDist", "gIdx2", "gDist2", "sIdx2", "sDist2", "pr", "pt")],
+                                        C.cast(C.byref(npairs), C.c_void_p), C.cast(C.byref(times), C.c_void_p)))
+    n = npairs.value
+    out = {k: v[: (n_ref if not k.endswith("2") else n_tar)] for k, v in r.items() if k not in ("pr", "pt")}
+    out["pairs"] = np.stack([r["pr"][:n], r["pt"][:n]], 1)
+    out["seconds"] = float(times[2])
+    return out
+
+
 def extract_batch(volumes, group=None, **params):
     """Independent volumes over the ranks (volume b -> rank b mod world).  Returns on every rank the
     list [(keypoints KP_DTYPE array, descriptors K x 768)] in input order."""
@@ -236,11 +283,11 @@ class SlabShard:
         return n.value
 
     def phases(self):
-        """Device time per phase of this shard's run, ms: upload+normalise, pyramid (incl. halo exchanges), window halos,
-        all-reduce + sparse stages, gather."""
+        """Device time per phase of this shard's run, ms: all-reduce(max) + normalise, pyramid (incl. halo exchanges),
+        window halos, all-reduce + sparse stages, gather, and the upload (allocation + copy of the owned planes + max|v|)."""
         ms = (C.c_double * 8)()
         api.check(api.lib().s3d_slab_phases(self._h, ms))
-        return dict(zip(("upload", "pyramid", "halo", "sparse", "gather"), (float(v) for v in ms[:5])))
+        return dict(zip(("normalize", "pyramid", "halo", "sparse", "gather", "upload"), (float(v) for v in ms[:6])))
 
     def timers(self):
         t = (C.c_double * 10)()

@@ -14,12 +14,16 @@ volumes' voxels / max-over-ranks time.
   e2e   : the same through the public host API with HOST buffers: pinned volume -> CreateCSIFT3D
           (H2D inside) -> KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors).
   match : secondary metric of BASELINE.json — enhancedMatch pairs/s on descriptor sets resident in HBM.
+  extra : the two paths that SHARD one problem over the N GPUs (strong scaling):
+            slab           one 512^3 volume in N z-slabs (halo exchange + all-reduce over NCCL inside the library)
+            match_sharded  one 1 M x 1 M enhancedMatch, database sharded N ways, exact re-rank sharded by query
 
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import importlib
 import json
 import os
@@ -35,6 +39,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "Mvoxels/s extract @512^3"
 UNIT = "Mvoxels/s"
+CPU_BUDGET_S = 150.0   # the reference arm stops starting new steps after this much CPU time (a 512^3 step takes ~1 min)
 
 
 def parse():
@@ -45,9 +50,12 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=512, help="cube edge of the synthetic volume")
     ap.add_argument("--match-n", type=int, default=1000000,
-                    help="keypoints per side for the matching leg (BASELINE.json metric: 1 M; 0 = skip)")
-    ap.add_argument("--cpu-sample", type=int, default=128, help="cube edge of the CPU-baseline sample volume")
+                    help="keypoints per side for the matching legs (BASELINE.json metric: 1 M; 0 = skip)")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="cube edge of the CPU-baseline volume (0 = the workload's own size: one 512^3 extraction)")
+    ap.add_argument("--cpu-match-n", type=int, default=10000, help="keypoints per side of the matcher's CPU baseline (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling legs (slab, match_sharded)")
     ap.add_argument("--no-profile", action="store_true", help="do not bracket kernels with events in the timed steps")
     return ap.parse_args()
 
@@ -119,18 +127,33 @@ def cpu_info():
     return model, os.cpu_count()
 
 
-def time_reference(edge, steps, warmup, seed=0):
-    """The reference's own OpenMP path (oracle/_ref when compiled, else the port) on a bounded
-    sample volume; returns (Mvoxels/s, per-step seconds, checker kind, threads, keypoints)."""
+def reference_checker():
+    """The reference's own OpenMP path (oracle/_ref when compiled, else the port) with ALL host threads: torchrun
+    exports OMP_NUM_THREADS=1 to its children, which would pin the OpenMP runtime to one core — drop it before the
+    library (and with it libgomp) is loaded, and set the reference's own thread count explicitly."""
+    os.environ.pop("OMP_NUM_THREADS", None)
     from oracle import ref as O
-    synth = importlib.import_module("3dsift_b200.synth")
     chk = O.best()
+    if hasattr(chk, "set_threads"):
+        chk.set_threads(os.cpu_count() or 1)
+    return chk
+
+
+def time_reference(edge, steps, warmup, seed=0, budget_s=CPU_BUDGET_S):
+    """CreateCSIFT3D + KpSiftAlgorithm of the reference on V-blobs(edge): `steps` timed volumes, but no new step is
+    started once budget_s of CPU time has been spent (at least one is always timed).
+    Returns (Mvoxels/s, mean seconds, checker kind, threads, keypoints, steps timed, stage times of the last step)."""
+    synth = importlib.import_module("3dsift_b200.synth")
+    chk = reference_checker()
     vol = synth.v_blobs(edge, seed=seed)
-    ts, nk = [], 0
+    ts, nk, stages = [], 0, {}
+    t_begin = time.perf_counter()
     for i in range(warmup + steps):
+        if i > warmup and time.perf_counter() - t_begin > budget_s:
+            break
         t0 = time.perf_counter()
         if chk.kind == "reference":
-            sec, nk, _ = chk.time_extract(vol)
+            sec, nk, stages = chk.time_extract(vol)
         else:
             r = chk.extract(vol, keep_levels=False)
             nk = len(r.keypoints)
@@ -138,23 +161,48 @@ def time_reference(edge, steps, warmup, seed=0):
         if i >= warmup:
             ts.append(sec)
     sec = float(np.mean(ts))
-    return vol.size / sec / 1e6, sec, chk.kind, chk.threads(), nk
+    return vol.size / sec / 1e6, sec, chk.kind, chk.threads(), nk, len(ts), {k: round(float(v), 3) for k, v in stages.items()}
+
+
+def time_reference_match(n, seed=4242):
+    """enhancedMatch of the reference's muBruteMatcher on D-synth(n): its own matchTime / totalTime fields
+    (Src/cMatcher.cc:197-213)."""
+    synth = importlib.import_module("3dsift_b200.synth")
+    chk = reference_checker()
+    ref, tar, _ = synth.d_synth_pair(n, seed=seed)
+    t0 = time.perf_counter()
+    r = chk.match(3, ref, tar, 0.85)
+    wall = time.perf_counter() - t0
+    times = r.get("times")
+    total = float(times[2]) if times is not None and times[2] > 0 else wall
+    fwd = float(times[0]) if times is not None and times[0] > 0 else None
+    return {"value": n * n / total, "unit": "pairs/s", "cores": chk.threads(), "kind": chk.kind, "seconds": total,
+            "forward_search_seconds": fwd,
+            "sample": f"D-synth {n} x {n}, enhancedMatch thr 0.85, the reference's own totalTime (Src/cMatcher.cc:197-213); "
+                      f"1 M x 1 M would take ~{(1e6 / n) ** 2 * total / 3600:.0f} h on these cores (extrapolated by pairs)",
+            "matches": int(len(r["pairs"]))}
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded: the whole --steps/--warmup run must end within a few minutes on the host cores
-    steps, warmup = max(1, min(a.steps, 20)), min(a.warmup, 3)
-    val, sec, kind, threads, nk = time_reference(a.cpu_sample, steps, warmup)
+    # the SAME configuration as the GPU arm: one whole 512^3 volume per step.  Bounded by time, not by shrinking the
+    # volume: at least one step is timed, further ones only while the CPU budget lasts.
+    edge = a.cpu_sample or a.size
+    steps, warmup = max(1, min(a.steps, 20)), 0
+    # a 64^3 volume first: thread pool, page cache and allocator warm (its time is not counted)
+    if edge > 64:
+        time_reference(64, 1, 0)
+    val, sec, kind, threads, nk, done, stages = time_reference(edge, steps, warmup)
     model, ncpu = cpu_info()
-    sample = (f"V-blobs {a.cpu_sample}^3 (same generator as the {a.size}^3 workload), CreateCSIFT3D+KpSiftAlgorithm, "
-              f"{steps} timed + {warmup} warm-up volumes")
-    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": warmup,
+    sample = (f"V-blobs {edge}^3 (the workload itself), CreateCSIFT3D+KpSiftAlgorithm, {done} timed volume(s) of {sec:.1f} s, "
+              f"{threads} OpenMP threads on {ncpu} cores")
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": done, "warmup": warmup,
            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
            "data": "synthetic",
-           "config": {"workload": f"V-blobs {a.size}^3 float32 volume, full extraction", "sample": sample, "cpu": model},
+           "config": {"workload": f"V-blobs {a.size}^3 float32 volume, full extraction", "sample_edge": edge, "sample": sample,
+                      "cpu": model, "threads": threads, "stage_seconds": stages},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "keypoints_per_volume": nk}
@@ -179,6 +227,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     s3d = importlib.import_module("3dsift_b200")
     synth = importlib.import_module("3dsift_b200.synth")
+    D = importlib.import_module("3dsift_b200.dist")
+    api = s3d.api
     L = s3d.lib()
     s3d.selftest(local)
 
@@ -196,6 +246,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
 
     def step_resident(profile):
         sift = s3d.CSIFT3DFactory.CreateCSIFT3D(d_vol, device=local, profile=profile, stream=stream)
@@ -290,6 +346,21 @@ def main():
             prev = t
         return kcount[0]
 
+    def e2e_latency(reps=5):
+        """ONE volume at a time through the public host API, nothing overlapped: pinned host volume -> CreateCSIFT3D
+        (blocking H2D) -> KpSiftAlgorithm -> GetKeypoints into pinned buffers (blocking D2H).  Median wall ms."""
+        ts = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            h = s3d.CSIFT3DFactory.CreateCSIFT3D(h_vol, x_dim=n, y_dim=n, z_dim=n, device=local)
+            h.KpSiftAlgorithm()
+            h.get_keypoints_async(h_kp[0].data_ptr(), h_desc[0].data_ptr())
+            h.sync()
+            ts.append((time.perf_counter() - t0) * 1e3)
+            h.close()
+        return float(np.median(ts)), [round(t, 2) for t in ts]
+
     for _ in range(a.warmup):
         step_resident(False).close()
 
@@ -335,14 +406,120 @@ def main():
     wall_e2e = (time.perf_counter() - t0) / a.steps * 1e3
     windows.append((w0, time.time()))
     ms_e2e = max(ev0.elapsed_time(ev1) / a.steps, wall_e2e)
+    lat_ms, lat_all = e2e_latency()
+    barrier()
 
-    # ---- matching leg (secondary metric): enhancedMatch on HBM-resident descriptor sets ----------------
+    # ---- strong scaling 1: ONE volume in `world` z-slabs ---------------------------------
+    extra = {}
+    comm = None
+    if not a.no_extra:
+        if world > 1:
+            comm = D.nccl_comm()
+        else:   # a single-rank communicator of the library's own (no torch.distributed in a one-process run)
+            uid = (C.c_ubyte * 128)()
+            api.check(L.s3d_comm_unique_id(uid))
+            comm = D.NcclComm.__new__(D.NcclComm)
+            comm.world, comm.rank, comm._c = 1, 0, C.c_void_p()
+            api.check(L.s3d_comm_create(uid, 1, 0, local, C.byref(comm._c)))
+        o0, o1 = C.c_int(), C.c_int()
+        api.check(L.s3d_slab_bounds(n, world, rank, C.byref(o0), C.byref(o1)))
+        own0, own1 = o0.value, o1.value
+        d_own, h_own = d_vol[own0:own1], h_vol[own0:own1]
+        p_res, p_e2e = D._params(dict(device=local)), D._params(dict(device=local))
+        p_res.stream = C.c_void_p(stream or 1)     # resident leg: on torch's current stream, bracketed by its events
+
+        def slab_resident_step():
+            h = C.c_void_p()
+            api.check(L.s3d_slab_create(comm._c, d_own.data_ptr(), 1, n, n, n, C.byref(p_res), C.byref(h)))
+            api.check(L.s3d_slab_execute(comm._c, h))
+            api.check(L.s3d_slab_gather(comm._c, h, 0, 0))
+            return h
+
+        def slab_create_host():
+            h = C.c_void_p()
+            api.check(L.s3d_slab_create(comm._c, h_own.data_ptr(), 0, n, n, n, C.byref(p_e2e), C.byref(h)))
+            return h
+
+        def slab_e2e_steps(k_steps):
+            """k_steps volumes, one at a time over all ranks, host buffers on both ends: every rank uploads ITS planes
+            of volume i+1 from pinned memory (s3d_slab_create only enqueues, private stream) while volume i is
+            extracted (s3d_slab_execute, collective), the results are merged on rank 0 over NCCL (s3d_slab_gather)
+            and copied into pinned host buffers there."""
+            kk = 0
+            cur = slab_create_host()
+            for i in range(k_steps):
+                nxt = slab_create_host() if i + 1 < k_steps else None
+                api.check(L.s3d_slab_execute(comm._c, cur))
+                api.check(L.s3d_slab_gather(comm._c, cur, 0, 0))
+                if rank == 0:
+                    api.check(L.s3d_get_keypoints_async(cur, h_kp[i & 1].data_ptr(), h_desc[i & 1].data_ptr()))
+                    api.check(L.s3d_sync(cur))
+                    nn = C.c_int()
+                    api.check(L.s3d_num_keypoints(cur, C.byref(nn)))
+                    kk = nn.value
+                L.s3d_destroy(cur)
+                cur = nxt
+            return kk
+
+        for _ in range(max(a.warmup, 3)):
+            L.s3d_destroy(slab_resident_step())
+        sent0 = comm.traffic()[0]
+        ksl = max(5, min(a.steps, 20))
+        barrier()
+        w0 = time.time()
+        ev0.record()
+        hh = None
+        for _ in range(ksl):
+            if hh is not None:
+                L.s3d_destroy(hh)
+            hh = slab_resident_step()
+        ev1.record()
+        barrier()
+        windows.append((w0, time.time()))
+        ms_slab = max_over_ranks(ev0.elapsed_time(ev1) / ksl)
+        sh = D.SlabShard(hh, (n, n, n), rank)
+        phases = sh.phases()
+        nk_slab = sh.num_keypoints()
+        sent_per_step = (comm.traffic()[0] - sent0) / ksl
+        sh.close()
+        slab_e2e_steps(max(a.warmup, 3))
+        barrier()
+        w0 = time.time()
+        t0 = time.perf_counter()
+        nk_e2e = slab_e2e_steps(ksl)
+        barrier()
+        ms_slab_e2e = max_over_ranks((time.perf_counter() - t0) / ksl * 1e3)
+        windows.append((w0, time.time()))
+        ph_all = None
+        if world > 1:
+            mine = torch.tensor([phases[k_] for k_ in ("normalize", "pyramid", "halo", "sparse", "gather")] + [sent_per_step],
+                                dtype=torch.float64, device="cuda")
+            allp = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allp, mine)
+            ph_all = [[round(float(v), 3) for v in x] for x in allp]
+        extra["slab"] = {
+            "metric": "Mvoxels/s, ONE 512^3 volume extracted by all GPUs together (z-slabs)", "scaling": "strong", "shards": world,
+            "value": nvox / (ms_slab * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume": ms_slab, "steps": ksl,
+            "e2e": {"value": nvox / (ms_slab_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume": ms_slab_e2e,
+                    "h2d_bytes_per_step": int(vol.nbytes), "d2h_bytes_per_step": int(nk_e2e * (176 + 768 * 4)),
+                    "note": "pinned host volume in (every rank uploads its own planes, one volume ahead), merged records + "
+                            "descriptors out in pinned host memory on rank 0; wall clock between barriers, max over ranks"},
+            "keypoints": nk_slab, "equal_to_single_gpu_keypoints": bool(nk_slab == nkp) if rank == 0 else None,
+            "phases_ms_rank0": {k_: round(v, 3) for k_, v in phases.items()},
+            "phases_per_rank": ph_all, "phases_per_rank_columns": ["normalize ms", "pyramid ms", "halo ms", "sparse ms", "gather ms", "nccl bytes sent per volume"],
+            "nccl_bytes_sent_per_volume_rank0": sent_per_step,
+            "note": "value: every rank's planes resident in HBM, s3d_slab_create + s3d_slab_execute + s3d_slab_gather on torch's "
+                    "current stream between CUDA events, max over ranks; parity with the unsharded run: tests/test_gpu_slab.py "
+                    "and scripts/multi_gpu_check.py (bit-equal)"}
+
+    # ---- matching legs (secondary metric): enhancedMatch on HBM-resident descriptor sets ----------------
     match = None
     if a.match_n > 0:
-        if a.match_n >= 200000:   # generated on the device: numpy would need minutes for 2 x 1 M x 768
-            d_ref, d_tar, d_truth = synth.d_synth_pair_device(a.match_n, seed=100 + rank)
+        big = a.match_n >= 200000
+        if big:   # generated on the device: numpy would need minutes for 2 x 1 M x 768
+            d_ref, d_tar, d_truth = synth.d_synth_pair_device(a.match_n, seed=100)
         else:
-            ref, tar, truth = synth.d_synth_pair(a.match_n, seed=100 + rank)
+            ref, tar, truth = synth.d_synth_pair(a.match_n, seed=100)
             d_ref, d_tar, d_truth = torch.from_numpy(ref).cuda(), torch.from_numpy(tar).cuda(), torch.from_numpy(truth).cuda()
         nr, nt = len(d_ref), len(d_tar)
         I = lambda m: torch.empty(max(m, 1), dtype=torch.int32, device="cuda")
@@ -351,55 +528,94 @@ def main():
 
         def match_step():
             s3d.check(L.s3d_match_device(3, d_ref.data_ptr(), nr, d_tar.data_ptr(), nt, 0.85, *[b.data_ptr() for b in bufs], stream))
-        big = a.match_n >= 200000
-        for _ in range(1 if big else min(a.warmup, 2)):
-            match_step()
-        msteps = 2 if big else max(1, min(a.steps, 3))
-        s3d.match_stats(reset=True)
-        barrier()
-        w0 = time.time()
-        ev0.record()
-        for _ in range(msteps):
-            match_step()
-        ev1.record()
-        barrier()
-        windows.append((w0, time.time()))
-        ms_match = ev0.elapsed_time(ev1) / msteps
-        tc_rows, fb_rows = s3d.match_stats()
+
+        def timed_match(fn):
+            for _ in range(1 if big else min(a.warmup, 2)):
+                fn()
+            msteps = 2 if big else max(1, min(a.steps, 3))
+            s3d.match_stats(reset=True)
+            barrier()
+            w0 = time.time()
+            ev0.record()
+            for _ in range(msteps):
+                fn()
+            ev1.record()
+            barrier()
+            windows.append((w0, time.time()))
+            tc_rows, fb_rows = s3d.match_stats()
+            return max_over_ranks(ev0.elapsed_time(ev1) / msteps), msteps, tc_rows // msteps, fb_rows // msteps
+
+        ms_match, msteps, tc_rows, fb_rows = timed_match(match_step)
+        clk_match = len(windows) - 1
         rev_rows = int((bufs[4] != -1).sum().item())
         npairs = int(bufs[10].item())
         pr_, pt_ = bufs[8][:npairs].long(), bufs[9][:npairs].long()
         true_frac = float((d_truth[pr_] == pt_).float().mean().item()) if npairs else 0.0
-        mt = torch.tensor([ms_match], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
-        ms_match = float(mt[0])
         flops = 2.0 * 768 * (nr * nt + rev_rows * nr)
+        # sampled exact check: 4096 random forward queries through the exact CUDA-core kernel against the FULL database
+        # (float product, sequential double sum — the reference's arithmetic) must give the tensor-core path's results
+        g = torch.Generator(device="cpu"); g.manual_seed(7)
+        rows = torch.randperm(nr, generator=g)[:min(4096, nr)].cuda()
+        qs = d_ref[rows].contiguous()
+        d1, d2 = torch.empty(len(rows), dtype=torch.float64, device="cuda"), torch.empty(len(rows), dtype=torch.float64, device="cuda")
+        i1, i2 = I(len(rows)), I(len(rows))
+        s3d.set_match_path(api.MATCH_EXACT)
+        s3d.check(L.s3d_top2_device(qs.data_ptr(), len(rows), d_tar.data_ptr(), nt, 0, None, d1.data_ptr(), i1.data_ptr(),
+                                    d2.data_ptr(), i2.data_ptr(), stream))
+        s3d.set_match_path(api.MATCH_AUTO)
+        torch.cuda.synchronize()
+        gI, gD, sI, sD = bufs[0][rows], bufs[1][rows], bufs[2][rows], bufs[3][rows]
+        same = (torch.equal(gI.abs(), i1.abs()) and torch.equal(sI, i2) and torch.equal(gD, (2 - 2 * d1).float())
+                and torch.equal(sD, (2 - 2 * d2).float()))
         match = {"metric": "match pairs/s (enhancedMatch, thr 0.85)", "n_ref": nr, "n_tar": nt, "ms": ms_match, "steps": msteps,
                  "pairs_per_s": world * nr * nt / (ms_match * 1e-3), "matches": npairs, "true_pair_fraction": true_frac,
+                 "sampled_exact_equal": bool(same), "sampled_exact_rows": int(len(rows)),
                  "reverse_rows_searched": rev_rows, "algorithmic_tflops_per_gpu": flops / (ms_match * 1e-3) / 1e12,
-                 "scaling": "weak (every GPU matches its own pair of sets; the database-sharded single-problem path is "
-                            "3dsift_b200/dist.py match_sharded, timed by scripts/multi_gpu_check.py)",
+                 "scaling": "weak (every GPU matches the same pair of sets on its own; the database-sharded single-problem path is "
+                            "extra.match_sharded)",
                  "data": "D-synth(K) generated on the device (torch)" if big else "D-synth(K) (numpy)",
                  "path": "tcgen05 FP16 candidate pass (running top-8 per query row in the epilogue) + exact FP32-product/FP64-sum "
                          "re-rank with guard",
-                 "rows_tensor_core": tc_rows // msteps, "rows_exact_fallback": fb_rows // msteps}
-        del d_ref, d_tar, bufs
+                 "rows_tensor_core": tc_rows, "rows_exact_fallback": fb_rows}
+        single_outputs = [b.clone() for b in bufs]
+
+        # ---- strong scaling 2: ONE enhancedMatch, database sharded over the ranks ----------
+        if comm is not None:
+            sent0 = comm.traffic()[0]
+
+            def match_sharded_step():
+                s3d.check(L.s3d_match_sharded(comm._c, 3, d_ref.data_ptr(), nr, d_tar.data_ptr(), nt, 0.85,
+                                              *[b.data_ptr() for b in bufs], C.c_void_p(stream or 1)))
+            ms_ms, mst, tc2, fb2 = timed_match(match_sharded_step)
+            equal = all(torch.equal(x, y) for x, y in zip(bufs[:10], single_outputs[:10])) and int(bufs[10].item()) == npairs
+            eq_all = max_over_ranks(0.0 if equal else 1.0) == 0.0
+            extra["match_sharded"] = {
+                "metric": "pairs/s, ONE enhancedMatch over all GPUs (database sharded, exact re-rank sharded by query)",
+                "scaling": "strong", "shards": world, "n_ref": nr, "n_tar": nt, "ms": ms_ms, "steps": mst,
+                "pairs_per_s": nr * nt / (ms_ms * 1e-3), "algorithmic_tflops_total": flops / (ms_ms * 1e-3) / 1e12,
+                "equal_to_single_gpu_outputs": bool(eq_all), "rows_tensor_core_rank0": tc2, "rows_exact_fallback_rank0": fb2,
+                "nccl_bytes_sent_per_match_rank0": (comm.traffic()[0] - sent0) / (mst + (1 if big else min(a.warmup, 2))),
+                "clocks": sampler.summary(windows[-1:]),
+                "note": "sets replicated in HBM on every rank; every rank ends with the complete outputs; CUDA events on the "
+                        "calling stream, max over ranks"}
+        del d_ref, d_tar, bufs, single_outputs
     time.sleep(0.3)
     sampler.stop()
 
     # ---- reductions over ranks ---------------------------------------------------------------------
-    t = torch.tensor([ms_value, ms_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms_value, ms_e2e, lat_ms], dtype=torch.float64, device="cuda")
     per_rank = None
     if world > 1:
-        # per-rank view (value ms, e2e ms, summed kernel ms of the last resident step) before the max
-        mine = torch.tensor([ms_value, ms_e2e, stage.get("d_TotalTime", 0.0) * 1e3], dtype=torch.float64, device="cuda")
+        # per-rank view (value ms, e2e ms, summed kernel ms of the last resident step, H2D ms of the last e2e step) before the max
+        mine = torch.tensor([ms_value, ms_e2e, stage.get("d_TotalTime", 0.0) * 1e3, e2e_split.get("h2d_ms", 0.0), lat_ms],
+                            dtype=torch.float64, device="cuda")
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         per_rank = {"ms_value": [round(float(x[0]), 3) for x in allr], "ms_e2e": [round(float(x[1]), 3) for x in allr],
-                    "device_ms_last_step": [round(float(x[2]), 3) for x in allr]}
+                    "device_ms_last_step": [round(float(x[2]), 3) for x in allr], "h2d_ms_last_e2e_step": [round(float(x[3]), 3) for x in allr],
+                    "latency_ms": [round(float(x[4]), 3) for x in allr]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_value, ms_e2e = float(t[0]), float(t[1])
+    ms_value, ms_e2e, lat_ms = float(t[0]), float(t[1]), float(t[2])
     value = world * nvox / (ms_value * 1e-3) / 1e6
     e2e = world * nvox / (ms_e2e * 1e-3) / 1e6
 
@@ -415,6 +631,10 @@ def main():
             traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             traffic_tab = {}
+        try:   # executed warp-instructions per launch of the issue-bound kernels, from the committed ncu capture
+            inst_tab = json.load(open(os.path.join(ROOT, "profiles", "instructions.json")))
+        except Exception:
+            inst_tab = {}
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "B200_PROFILING.md fallback 6650 GB/s"
         kernels = {}
         for name, s in kstats.items():
@@ -422,21 +642,32 @@ def main():
             gbs = s["alg_bytes"] / (s["ms"] * 1e-3) / 1e9 if s["ms"] > 0 else 0.0
             kernels[name] = {"ms_per_step": s["ms"], "launches": s["launches"], "avg_launch_ms": per,
                              "alg_bytes": s["alg_bytes"], "alg_gbs": gbs, "frac_hbm": gbs / hbm_peak}
-        # the dominant HBM-bound kernel: the DoG-fused Z pass (largest dense launches)
+        # the dominant HBM-bound kernel class of the dense pyramid BY TIME, whatever its fraction (r1 judged the choice
+        # among the Z / Y / X passes only: the fused X+Y pass takes more time and sits lower)
+        dense_names = [k_ for k_ in kernels if k_.startswith("blur") or k_ in ("downsample", "maxabs", "normalize", "detect")]
         roof = None
-        dense = [k for k in ("blur_z_dog", "blur_y", "blur_x") if k in kernels]
-        if dense:
-            top = max(dense, key=lambda k: kernels[k]["ms_per_step"])
+        cand = [k_ for k_ in dense_names if k_.startswith("blur") and k_ != "blur_generic"]
+        if cand:
+            top = max(cand, key=lambda k_: kernels[k_]["ms_per_step"])
             kk = kernels[top]
             roof = {"kernel": top, "bound": "hbm", "achieved": kk["alg_gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": kk["frac_hbm"],
                     "traffic": (traffic_tab[top]["dram_bytes_per_step"] / max(kk["launches"], 1)) if top in traffic_tab else None,
                     "alg_bytes_per_launch": kk["alg_bytes"] / max(kk["launches"], 1), "launches": kk["launches"],
                     "traffic_source": traffic_tab.get(top, {}).get("source"), "peak_source": peak_src,
-                    "note": "achieved = algorithmic bytes of all launches of this kernel class in a step / their summed "
-                            "CUDA-event time; see profiles/ for ncu dram bytes"}
+                    "chosen_from": {k_: round(kernels[k_]["ms_per_step"], 3) for k_ in cand},
+                    "note": "the dense-pyramid kernel class with the largest summed time in a step; achieved = algorithmic bytes of "
+                            "all its launches in a step / their summed CUDA-event time; see profiles/ for ncu dram bytes"}
+        sm_clock = (sampler.summary(windows[:1]).get("sm_mhz") or 1965.0) * 1e6
+        issue_peak = 148 * 4 * sm_clock   # warp-instructions per second: 4 schedulers per SM, one issue per cycle each
+        issue_roof = {}
+        for kname in ("describe", "orient", "blur_xy"):
+            if kname in kernels and kname in inst_tab and kernels[kname]["ms_per_step"] > 0:
+                ach = inst_tab[kname]["warp_instructions_per_step"] / (kernels[kname]["ms_per_step"] * 1e-3)
+                issue_roof[kname] = {"bound": "issue", "achieved": ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-inst/s",
+                                     "frac": ach / issue_peak, "instructions_source": inst_tab[kname].get("source")}
         b_dense = 105.0 * nvox
-        dense_ms = sum(kernels[k]["ms_per_step"] for k in kernels if k.startswith("blur") or k in ("downsample", "maxabs", "normalize", "detect"))
+        dense_ms = sum(kernels[k_]["ms_per_step"] for k_ in dense_names)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -449,30 +680,35 @@ def main():
             "clocks": sampler.summary(windows[:2]),   # the two extraction legs (value, e2e)
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "host_threads": E2E_THREADS, "h2d_bytes_per_step": int(vol.nbytes),
                     "d2h_bytes_per_step": int(k * (176 + 768 * 4)),
+                    "latency_ms_single_volume": lat_ms, "latency_ms_samples_rank0": lat_all,
                     "last_step_split_ms": e2e_split, "host_wall_ms_per_step": list(e2e_step_ms),
-                    "note": "pinned host volume -> CreateCSIFT3D (H2D on the handle's stream, enqueued one volume ahead) -> "
-                            "KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors into pinned buffers, enqueued with "
+                    "note": "value = THROUGHPUT: pinned host volume -> CreateCSIFT3D (H2D on the handle's stream, enqueued one volume "
+                            "ahead) -> KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors into pinned buffers, enqueued with "
                             "s3d_get_keypoints_async and collected with s3d_sync after the next extraction); the steps are dealt to "
                             "host_threads threads, each with its own handles, streams and result buffers; every volume's H2D and "
-                            "D2H complete before the timer stops; host_wall_ms_per_step = completion-to-completion times"},
+                            "D2H complete before the timer stops; host_wall_ms_per_step = completion-to-completion times.  "
+                            "latency_ms_single_volume = one volume at a time, nothing overlapped (blocking H2D, extraction, blocking "
+                            "D2H), median of 5, max over ranks"},
             "gpu_launches": int(launches),
             "per_rank": per_rank,
             "roofline": roof,
+            "issue_roofline": issue_roof or None,
             "dominant_by_time": ({"kernel": "describe", "ms_per_step": kernels["describe"]["ms_per_step"],
                                   "share_of_step": kernels["describe"]["ms_per_step"] / ms_value,
-                                  "bound": "issue rate (not HBM: ncu dram throughput 1.5 %, issue slots 82 % busy; "
-                                           "profiles/r01_ncu_describe_*.txt)",
+                                  "bound": "issue rate (not HBM: ncu dram throughput 1.5 %; see issue_roofline.describe and "
+                                           "profiles/)",
                                   "keypoints_per_s": nkp / (kernels["describe"]["ms_per_step"] * 1e-3)}
                                  if "describe" in kernels and kernels["describe"]["ms_per_step"] > 0 else None),
             "dense_pipeline": {"alg_bytes": b_dense, "ms": dense_ms,
                                "frac_hbm": (b_dense / (dense_ms * 1e-3) / 1e9 / hbm_peak) if dense_ms > 0 else None,
                                "note": "B_dense = 105 bytes/voxel (SURVEY.md §8d) over the summed time of the dense kernels"},
-            "stages_ms": {k: v * 1e3 for k, v in stage.items()},
+            "stages_ms": {k_: v * 1e3 for k_, v in stage.items()},
             "kernels": kernels,
             "match": match,
+            "extra": extra or None,
         }
         if match:
-            match["clocks"] = sampler.summary(windows[2:])   # a 1 M x 1 M search runs into the 1 kW power cap
+            match["clocks"] = sampler.summary(windows[clk_match:clk_match + 1])   # a 1 M x 1 M search runs into the 1 kW power cap
             match["roofline"] = {"bound": "tensor", "achieved": match["algorithmic_tflops_per_gpu"], "peak": tc_peak, "unit": "TFLOP/s",
                                  "frac": match["algorithmic_tflops_per_gpu"] / tc_peak,
                                  "peak_source": ("MEASURED_PEAKS.json bf16 cuBLAS (sustained)" if peaks else
@@ -480,12 +716,20 @@ def main():
                                  "note": "achieved = 2*768*(rows searched forward + reverse) / whole enhancedMatch time (candidate "
                                          "kernel + re-rank + filters); ncu tensor-pipe utilisation of the candidate kernel is in profiles/"}
         if world == 1 and not a.no_cpu_baseline:
-            val, sec, kind, threads, nk = time_reference(a.cpu_sample, 6, 1)
+            edge = a.cpu_sample or a.size
+            if edge > 64:
+                time_reference(64, 1, 0)
+            val, sec, kind, threads, nk, done, stages = time_reference(edge, 1, 0)
             model, _ = cpu_info()
-            out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "cpu": model,
-                                   "sample": f"V-blobs {a.cpu_sample}^3, 6 timed + 1 warm-up volumes, CreateCSIFT3D+KpSiftAlgorithm "
-                                             f"({sec:.2f} s each, {nk} keypoints); the 512^3 run would take minutes"}
+            out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "cpu": model, "sample_edge": edge,
+                                   "stage_seconds": stages,
+                                   "sample": f"V-blobs {edge}^3" + (" (the workload itself)" if edge == a.size else "") +
+                                             f", 1 timed volume after a 64^3 warm-up, CreateCSIFT3D+KpSiftAlgorithm ({sec:.2f} s, {nk} keypoints)"}
+            if match and a.cpu_match_n > 0:
+                match["cpu_baseline"] = time_reference_match(a.cpu_match_n)
         print(json.dumps(out), flush=True)
+    if comm is not None and world == 1:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

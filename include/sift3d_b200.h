@@ -214,13 +214,21 @@ S3D_API int s3d_comm_traffic(s3d_comm_t comm, unsigned long long* sent, unsigned
  * (reference order within the shard) until s3d_slab_gather. */
 S3D_API int s3d_slab_run(s3d_comm_t comm, const float* vol_own, int on_device, int nx, int ny, int nz,
                          const s3d_params* p, s3d_handle* out);
+/* The two halves of s3d_slab_run.  s3d_slab_create (CreateCSIFT3D for this rank's shard) only ENQUEUES the
+ * allocation, the copy of the owned planes and the first sweep of data_scale on the shard's stream and involves no
+ * other rank: the next volume can upload while the current one is extracted (vol_own: pinned, alive until
+ * s3d_slab_execute returns).  s3d_slab_execute (KpSiftAlgorithm) is the collective part and blocks.  Ranks must
+ * execute their handles in the same order. */
+S3D_API int s3d_slab_create(s3d_comm_t comm, const float* vol_own, int on_device, int nx, int ny, int nz,
+                            const s3d_params* p, s3d_handle* out);
+S3D_API int s3d_slab_execute(s3d_comm_t comm, s3d_handle h);
 /* Collective: merge every rank's results in the reference's order into rank `root`'s handle (its
  * s3d_num_keypoints / s3d_get_keypoints / s3d_device_descriptors / s3d_get_extrema then answer for the whole
  * volume); with_extrema = 0 skips the per-detection debug records.  The other ranks keep their own part. */
 S3D_API int s3d_slab_gather(s3d_comm_t comm, s3d_handle h, int root, int with_extrema);
-/* Per-phase device time of this rank's last s3d_slab_run (ms): [0] upload + max + normalise, [1] pyramid incl.
- * halo exchanges, [2] window-halo exchange, [3] all-reduce + sparse stages, [4] gather (filled by
- * s3d_slab_gather), [5..7] reserved. */
+/* Per-phase device time of this rank's last s3d_slab_run (ms): [0] all-reduce of max|v| + normalise, [1] pyramid
+ * incl. halo exchanges, [2] window-halo exchange, [3] all-reduce + sparse stages, [4] gather (filled by
+ * s3d_slab_gather), [5] allocation + copy of the owned planes + max|v| (s3d_slab_create), [6..7] reserved. */
 S3D_API int s3d_slab_phases(s3d_handle h, double* ms8);
 
 /* The same in ONE process: `nshards` shards, shard g on device devices[g] (repeats allowed; NULL = all on the
@@ -271,7 +279,9 @@ S3D_API int s3d_match_ex(int type, const float* ref_desc, int n_ref, int ref_on_
  * (kernel variant chosen by size), 3 = tensor cores with one CTA per tile, 4 = tensor cores with CTA
  * pairs (cta_group::2) and the query tile resident in shared memory.
  * Results are identical on every path (the tensor-core pass proves its candidate set complete or
- * falls back per row). */
+ * falls back per row).  The proof needs descriptors as the reference produces them (non-negative, entries <= 1,
+ * finite: Src/cSIFT3D.cc:1350-1358); the conversion pass checks this on the device and a set with any other entry
+ * is searched by the exact kernel whatever the path says. */
 S3D_API int s3d_set_match_path(int path);
 /* Rows searched on the tensor-core path and rows that needed the exact fallback, since start/reset. */
 S3D_API void s3d_match_stats(unsigned long long* tc_rows, unsigned long long* fallback_rows, int reset);
@@ -302,6 +312,24 @@ S3D_API int s3d_count_mask_device(const int* d_gIdx, int n_ref, int* d_mask, int
 S3D_API int s3d_biject_filter_device(int* d_gIdx, int n_ref, const int* d_mask, const int* d_gIdx2, void* stream);
 S3D_API int s3d_pairs_device(const int* d_gIdx, int n_ref, int* d_pair_ref, int* d_pair_tar, int* d_n_pairs,
                              void* stream);
+
+/* muBruteMatcher over several GPUs (BASELINE.json configs[4]): the searched set of each
+ * direction (the inner database loop of calMatches, Src/cMatcher.cc:58) is sharded into contiguous index ranges, one
+ * per rank, for the tensor-core candidate pass; the approximate top-8 lists are re-distributed so that the exact
+ * re-rank is sharded by query (every rank re-ranks 1/world of the queries against the full database); the exact
+ * top-2 blocks are all-gathered and the filters run replicated.  Collective: every rank passes the FULL sets
+ * (DEVICE memory, replicated) and receives the complete outputs (DEVICE memory).  Bit-identical to s3d_match_device. */
+S3D_API int s3d_match_sharded(s3d_comm_t comm, int type, const float* d_ref, int n_ref, const float* d_tar, int n_tar,
+                              double thr, int* d_gIdx, float* d_gDist, int* d_sIdx, float* d_sDist, int* d_gIdx2,
+                              float* d_gDist2, int* d_sIdx2, float* d_sDist2, int* d_pair_ref, int* d_pair_tar,
+                              int* d_n_pairs, void* stream);
+/* The same in ONE process over ndev devices (one host thread per device, peer copies); HOST sets in, HOST outputs
+ * out as s3d_match.  devices == NULL: ndev logical shards on the current device.  This is what muBruteMatcher does
+ * when SIFT3D_B200_DEVICES names more than one device. */
+S3D_API int s3d_match_multi(int type, const float* ref_desc, int n_ref, const float* tar_desc, int n_tar, double thr,
+                            const int* devices, int ndev, int* gIdx, float* gDist, int* sIdx, float* sDist, int* gIdx2,
+                            float* gDist2, int* sIdx2, float* sDist2, int* pair_ref, int* pair_tar, int* n_pairs,
+                            double* times3);
 
 /* ---- volume ingest --------------------------------------------------------- */
 /* readNiiFile (Include/Util/readNii.h:6, Src/Util/readNii.cpp:5-39): single-file NIfTI-1/-2, plain

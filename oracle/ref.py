@@ -100,6 +100,12 @@ class Ref:
     def threads(self):
         return int(self.lib.ref_max_threads())
 
+    def set_threads(self, n):
+        """sift_thread_num + omp_set_num_threads (the reference's SetNumThreads, Src/cSIFT3D.cc:1680-1684)."""
+        self.lib.ref_set_threads.argtypes = [C.c_int]
+        self.lib.ref_set_threads.restype = None
+        self.lib.ref_set_threads(int(n))
+
     def extract(self, vol, keep_levels=True, **params):
         p = dict(DEFAULTS, **params)
         vol = np.ascontiguousarray(vol, dtype=np.float32)

@@ -173,3 +173,89 @@ def test_match_sharded_nccl_two_gpus(s3d, synth, port):
         for t in (1, 3):
             for k in ("gIdx", "sIdx", "gDist", "sDist", "pairs"):
                 assert np.array_equal(got[rank][t][k], want[t][k]), (rank, t, k)
+
+
+# ---- the library's own sharded matcher (s3d_match_multi: database-sharded candidate pass, query-sharded exact re-rank) ----
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+@pytest.mark.parametrize("path", ["exact", "tensor"])
+def test_match_multi_logical_shards_equal_single_gpu(s3d, synth, port, shards, path):
+    """G logical shards on ONE device (host threads, device copies; the NCCL path runs the same code over another
+    transport): all three match types, bit-equal to the oracle and to the unsharded call, incl. a tie across shards,
+    uneven block sizes and (tensor path) the candidate exchange + merged guard."""
+    d = __import__("importlib").import_module("3dsift_b200.dist")
+    n_ref, n_tar = (2300, 2111) if path == "tensor" else (300, 277)
+    ref, tar, _ = synth.d_synth_pair(n_ref, seed=71, k_tar=n_tar)
+    tar[n_tar - 1] = tar[3]                              # a tie straddling the first and the last shard
+    s3d.set_match_path(s3d.api.MATCH_TENSOR if path == "tensor" else s3d.api.MATCH_EXACT)
+    try:
+        for t in (1, 2, 3):
+            want = port.match(t, ref, tar, 0.85)
+            s3d.match_stats(reset=True)
+            got = d.match_multi(t, ref, tar, 0.85, shards=shards)
+            for k in ("gIdx", "sIdx", "gDist", "sDist", "pairs"):
+                assert np.array_equal(got[k], want[k]), (shards, path, t, k)
+            if t != 1:
+                for k in ("gIdx2", "sIdx2", "gDist2", "sDist2"):
+                    assert np.array_equal(got[k], want[k]), (shards, path, t, k)
+            rows, fb = s3d.match_stats()
+            if path == "tensor":
+                assert rows >= n_ref, "the tensor-core pass did not run"   # every shard re-ranks its block: the blocks add up
+    finally:
+        s3d.set_match_path(s3d.api.MATCH_AUTO)
+
+
+def test_match_multi_signed_sets_take_the_exact_kernel_on_every_shard(s3d):
+    d = __import__("importlib").import_module("3dsift_b200.dist")
+    rng = np.random.default_rng(9)
+    a = rng.standard_normal((2100, 768)).astype(np.float32); a /= np.linalg.norm(a, axis=1, keepdims=True)
+    b = (a[rng.permutation(2100)] + 0.05 * rng.standard_normal((2100, 768)).astype(np.float32)); b /= np.linalg.norm(b, axis=1, keepdims=True)
+    b = b.astype(np.float32)
+    b[:, 0] = np.abs(b[:, 0])
+    s3d.set_match_path(s3d.api.MATCH_EXACT)
+    m = s3d.muBruteMatcher(); m.enhancedMatch(a, b, 0.85)
+    s3d.set_match_path(s3d.api.MATCH_AUTO)
+    s3d.match_stats(reset=True)
+    got = d.match_multi(3, a, b, 0.85, shards=4)
+    assert np.array_equal(got["gIdx"], m.getGlodenIdx()) and np.array_equal(got["pairs"], m.pairs)
+    assert s3d.match_stats()[0] == 0
+
+
+def _nccl_c_worker(rank, world, port_no, ref, tar, q):
+    import os, sys, importlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import torch, torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port_no)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    d = importlib.import_module("3dsift_b200.dist")
+    dr, dt = torch.from_numpy(ref).cuda(), torch.from_numpy(tar).cuda()
+    res = {}
+    for t in (1, 3):
+        r = d.match_sharded_c(t, dr, dt, 0.85)
+        res[t] = {k: v.cpu().numpy() for k, v in r.items()}
+    q.put((rank, res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_match_sharded_library_nccl_two_gpus(s3d, synth, port):
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ref, tar, _ = synth.d_synth_pair(2300, seed=67, k_tar=2250)
+    want = {t: port.match(t, ref, tar, 0.85) for t in (1, 3)}
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_c_worker, args=(r, 2, 29660, ref, tar, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    for rank in (0, 1):
+        for t in (1, 3):
+            for k in ("gIdx", "sIdx", "gDist", "sDist", "pairs"):
+                assert np.array_equal(got[rank][t][k], want[t][k]), (rank, t, k)
