@@ -168,6 +168,7 @@ def lib():
     L.s3d_slab_run.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
     L.s3d_slab_create.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), C.POINTER(vp)]
     L.s3d_slab_execute.argtypes = [vp, vp]
+    L.s3d_slab_execute_async.argtypes = [vp, vp]
     L.s3d_slab_gather.argtypes = [vp, vp, C.c_int, C.c_int]
     L.s3d_slab_phases.argtypes = [vp, C.POINTER(C.c_double * 8)]
     L.s3d_extract_multi.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(s3d_params), ip, C.c_int, C.c_int, C.POINTER(vp)]
@@ -409,7 +410,7 @@ class CSIFT3D:
         """dict(orient_rechecked, orient_flipped, desc_redo): safeguard bookkeeping of the last run."""
         out = (C.c_int * 4)()
         check(lib().s3d_get_counters(self._h, out))
-        return dict(orient_rechecked=int(out[0]), orient_flipped=int(out[1]), desc_redo=int(out[2]))
+        return dict(orient_rechecked=int(out[0]), orient_flipped=int(out[1]), desc_redo=int(out[2]), sparse_resized=int(out[3]))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:

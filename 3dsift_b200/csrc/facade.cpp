@@ -59,6 +59,20 @@ std::ostream& operator<<(std::ostream& os, const SIFT_PROCESS& sp) {
     return os;
 }
 
+// SIFT3D_B200_DEVICES="0,1,2,3": the devices one extraction / one match is spread over (the API
+// stays the reference's, device selection comes from the environment).  One entry or unset: the single-device path.
+static std::vector<int> multi_devices() {
+    std::vector<int> out;
+    const char* e = getenv("SIFT3D_B200_DEVICES");
+    if (!e) return out;
+    std::stringstream ss(e);
+    std::string tok;
+    while (std::getline(ss, tok, ','))
+        if (!tok.empty()) out.push_back(atoi(tok.c_str()));
+    if (out.size() < 2) out.clear();
+    return out;
+}
+
 namespace CPUSIFT {
 
 int sift_thread_num = 1;
@@ -142,10 +156,24 @@ const char* CSIFT3D::LastError() const { return impl->err.c_str(); }
 void CSIFT3D::KpSiftAlgorithm() {
     if (impl->ran) return;  // single-shot
     impl->ran = true;
-    impl->create();
-    if (!impl->h) return;
-    int rc = s3d_run(impl->h);
-    if (rc != S3D_OK) return impl->fail(rc);
+    int rc = S3D_OK;
+    const std::vector<int> devs = impl->keep ? std::vector<int>() : multi_devices();
+    if (!devs.empty() && !impl->h && !impl->volume.empty()) {
+        // one volume over several GPUs: z-slabs with halo exchange between the devices (s3d_extract_multi); the merged
+        // results live in the first shard's handle, which then answers like a single-device run.  (KeepLevels keeps the
+        // single-device path: GET_GSS / GET_DOG return whole levels.)
+        std::vector<s3d_handle> hs(devs.size(), nullptr);
+        rc = s3d_extract_multi(impl->volume.data(), impl->nx, impl->ny, impl->nz, &impl->prm, devs.data(), (int)devs.size(), 1, hs.data());
+        std::vector<float>().swap(impl->volume);
+        if (rc != S3D_OK) return impl->fail(rc);
+        impl->h = hs[0];
+        for (size_t g = 1; g < hs.size(); ++g) s3d_destroy(hs[g]);
+    } else {
+        impl->create();
+        if (!impl->h) return;
+        rc = s3d_run(impl->h);
+        if (rc != S3D_OK) return impl->fail(rc);
+    }
     int n = 0;
     s3d_num_keypoints(impl->h, &n);
     impl->filter.resize(n);
@@ -292,8 +320,11 @@ std::vector<int> muBruteMatcher::getSilverIdx() { return sIdx; }
 // Keypoint::desc pointers (Src/cMatcher.cc:20) -> one n x 768 block.  Returns the block and whether
 // it lives on the device (descriptors of a live extractor, no copy) — else a host pointer, which
 // is the caller's own memory when the pointers already form base + 768*i, or `scratch`.
+// (*on_device < 0 on entry: the caller wants host memory whatever the registry knows — the multi-device matcher
+// uploads a replica to every device itself)
 static const float* gather(const std::vector<Keypoint>& kp, std::vector<float>& scratch, int* on_device) {
-    *on_device = 0;
+    const bool host_only = *on_device < 0;
+    *on_device = host_only ? -1 : 0;
     const size_t n = kp.size();
     if (n == 0) return nullptr;
     bool contiguous = kp[0].desc != nullptr;
@@ -301,12 +332,14 @@ static const float* gather(const std::vector<Keypoint>& kp, std::vector<float>& 
     if (contiguous) {
         std::lock_guard<std::mutex> lk(g_reg_mu);
         auto it = g_registry.find(kp[0].desc);
-        if (it != g_registry.end() && (size_t)it->second.n == n) {
+        if (*on_device >= 0 && it != g_registry.end() && (size_t)it->second.n == n) {
             *on_device = 1;
             return it->second.d_desc;
         }
+        if (host_only) *on_device = 0;
         return kp[0].desc;
     }
+    if (host_only) *on_device = 0;
     scratch.assign(n * DESC_LENGTH, 0.0f);
     for (size_t i = 0; i < n; ++i)
         if (kp[i].desc) memcpy(&scratch[i * DESC_LENGTH], kp[i].desc, sizeof(float) * DESC_LENGTH);
@@ -317,7 +350,8 @@ void muBruteMatcher::run(int type, std::vector<Cvec>& refMatch, std::vector<Cvec
                          const std::vector<Keypoint>& tar_kp, double thr) {
     const int n_ref = (int)ref_kp.size(), n_tar = (int)tar_kp.size();
     std::vector<float> s_ref, s_tar;
-    int ref_dev = 0, tar_dev = 0;
+    const std::vector<int> devs = multi_devices();
+    int ref_dev = devs.empty() ? 0 : -1, tar_dev = devs.empty() ? 0 : -1;
     const float* p_ref = gather(ref_kp, s_ref, &ref_dev);
     const float* p_tar = gather(tar_kp, s_tar, &tar_dev);
     // the reference (re)initialises its work vectors on every call (Src/cMatcher.cc:152-161)
@@ -326,8 +360,13 @@ void muBruteMatcher::run(int type, std::vector<Cvec>& refMatch, std::vector<Cvec
     std::vector<int> pr(std::max(n_ref, 1)), pt(std::max(n_ref, 1));
     int np = 0;
     double times[3] = {0, 0, 0};
-    status = s3d_match_ex(type, p_ref, n_ref, ref_dev, p_tar, n_tar, tar_dev, thr, gIdx.data(), gDist.data(), sIdx.data(),
-                          sDist.data(), gIdx2.data(), gDist2.data(), sIdx2.data(), sDist2.data(), pr.data(), pt.data(), &np, times);
+    if (!devs.empty())  // one match over several GPUs: database-sharded search, query-sharded exact re-rank (s3d_match_multi)
+        status = s3d_match_multi(type, p_ref, n_ref, p_tar, n_tar, thr, devs.data(), (int)devs.size(), gIdx.data(), gDist.data(),
+                                 sIdx.data(), sDist.data(), gIdx2.data(), gDist2.data(), sIdx2.data(), sDist2.data(), pr.data(),
+                                 pt.data(), &np, times);
+    else
+        status = s3d_match_ex(type, p_ref, n_ref, ref_dev, p_tar, n_tar, tar_dev, thr, gIdx.data(), gDist.data(), sIdx.data(),
+                              sDist.data(), gIdx2.data(), gDist2.data(), sIdx2.data(), sDist2.data(), pr.data(), pt.data(), &np, times);
     if (status != S3D_OK) {
         std::cerr << "[sift3d_b200] " << s3d_last_error() << std::endl;
         return;

@@ -117,8 +117,12 @@ struct s3d_ctx {
     s3d_keypoint* d_kps = nullptr;
     float* d_desc = nullptr;
     int n_rechecked = 0, n_flipped = 0;
-    int* d_redo = nullptr;          // [0] = count, [1..] = keypoint indices (freed in s3d_wait)
+    int* d_redo = nullptr;          // keypoint indices for the FP32 descriptor kernel (freed in s3d_wait)
     int n_desc_redo = 0;            // keypoints the fixed-point descriptor kernel handed to the FP32 one
+    int* d_counts = nullptr;        // the run's device-side counters (read once, in s3d_wait)
+    int cap_extre = 0, cap_kps = 0; // capacities of the detection / keypoint buffers (0: choose in stage_sparse)
+    size_t own_total = 0;           // owned voxels over all octaves (the capacities' yardstick)
+    int n_resized = 0;              // times the sparse stage was repeated with larger buffers
     bool ran = false, levels_alive = false, queued = false, h2d_pending = false, d2h_pending = false;
     // z-slab sharding.  Unsharded: slab = false, za = p0 = 0, zb = p1 = nz_o.
     // A shard OWNS global planes [p0[o], p1[o]) of octave o (plane k of octave o belongs to the owner of octave-0 plane

@@ -597,7 +597,7 @@ void s3d_destroy(s3d_handle c) {
     if (c->stream) {
         cudaSetDevice(c->device);
         free_levels(c);
-        void* ptrs[] = {c->d_input, c->d_slots, c->d_thres, c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc, c->d_redo};
+        void* ptrs[] = {c->d_input, c->d_slots, c->d_thres, c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc, c->d_redo, c->d_counts};
         for (void* q : ptrs) if (q) s3d::dev_free(q, c->stream);
         cudaStreamSynchronize(c->stream);
         c->prof.resolve();
@@ -629,9 +629,10 @@ int slab_window_halo(const s3d_ctx* c, int lvl) {
 static int halo_for(const s3d_ctx* c) {
     // local planes a shard keeps beyond its owned range: the source halo of the widest blur (hw + 1: every level is
     // produced on owned +-1 so that the DoG neighbours of detection are local) and the widest descriptor window
-    int hwmax = 0;
-    for (int i = 0; i < c->G; i++) hwmax = std::max(hwmax, c->taps[i].hw);
-    return std::max(hwmax + 2, slab_window_halo(c, c->L));
+    // (s3d_slab.cu builds the levels in groups with one exchange per group: the deepest source halo is 1 + sum(hw))
+    int hwsum = 0;
+    for (int i = 0; i < c->G; i++) hwsum += c->taps[i].hw;
+    return std::max(hwsum + 2, slab_window_halo(c, c->L));
 }
 
 int slab_halo_from_params(const s3d_params* p, int* halo) {
@@ -779,6 +780,21 @@ int stage_level(s3d_ctx* c, int o, int i, int zlo, int zhi) {
     return S3D_OK;
 }
 
+// ---- capacities of the sparse stage ------------------------------------------------------------------------------
+// Detection and survivor counts are produced on the device and consumed there (grids are fixed or persistent, kernels
+// read the counts): a step is ONE uninterrupted stream, the host learns the counts in s3d_wait.  Buffers are therefore
+// sized optimistically — from the densities this process has seen so far (times two), else from small defaults —
+// and a run that exceeds them is repeated from the kept pyramid with exact sizes (s3d_wait), so results never depend
+// on the guess.
+static std::atomic<double> g_dens_extre{1.0 / 512.0}, g_dens_kps{1.0 / 4096.0};  // per owned voxel
+static void learn_density(std::atomic<double>& a, double v) {
+    double cur = a.load();
+    while (v > cur && !a.compare_exchange_weak(cur, v)) {}
+}
+
+// Counter block of one run (ints, device): see s3d_wait.
+enum { CT_NE = 0, CT_RECHECK = 1, CT_FLIPPED = 2, CT_NKPS = 3, CT_STAGED = 4, CT_WORK_A = 5, CT_WORK_B = 6, CT_REDO = 7, CT_N = 8 };
+
 int stage_sparse(s3d_ctx* c) {
     cudaStream_t st = c->stream;
     const int L = c->L, G = c->G, D = c->D;
@@ -795,20 +811,32 @@ int stage_sparse(s3d_ctx* c) {
         own_total += nown;
         for (int j = 0; j < L; j++) gb_base[o * L + j + 1] = gb_base[o * L + j] + s3d_blocks(nown, kDetectChunk);
     }
+    c->own_total = own_total;
+    {   // tests force tiny capacities to exercise the resize path
+        const char* e1 = getenv("S3D_CAP_EXTRE");
+        const char* e2 = getenv("S3D_CAP_KPS");
+        if (c->cap_extre <= 0 && e1 && atoi(e1) > 0) c->cap_extre = atoi(e1);
+        if (c->cap_kps <= 0 && e2 && atoi(e2) > 0) c->cap_kps = atoi(e2);
+    }
+    if (c->cap_extre <= 0) c->cap_extre = (int)std::min<double>(2.0e9 / 256, std::max(65536.0, 2.0 * g_dens_extre.load() * (double)own_total));
+    if (c->cap_kps <= 0) c->cap_kps = (int)std::min<double>((double)c->cap_extre, std::max(8192.0, 2.0 * g_dens_kps.load() * (double)own_total));
+    const int cap_e = c->cap_extre, cap_k = c->cap_kps;
     const int nblk = std::max<int>(1, (int)gb_base[(size_t)c->noct * L]);
-    const unsigned stage_cap = (unsigned)std::max<size_t>(65536, own_total / 28);
-    int *d_blk_cnt = nullptr, *d_blk_off = nullptr, *d_total = nullptr;
+    const unsigned stage_cap = (unsigned)cap_e;
+    int *d_blk_cnt = nullptr, *d_blk_off = nullptr;
     StageEntry* d_stage = nullptr;
-    unsigned* d_stage_count = nullptr;
     Cand* d_cand = nullptr;
     S3D_CUDA(s3d::dev_alloc((void**)&d_blk_cnt, sizeof(int) * nblk, st));
     S3D_CUDA(s3d::dev_alloc((void**)&d_blk_off, sizeof(int) * nblk, st));
-    S3D_CUDA(s3d::dev_alloc((void**)&d_total, sizeof(int) * 4, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_counts, sizeof(int) * CT_N, st));
     S3D_CUDA(s3d::dev_alloc((void**)&d_stage, sizeof(StageEntry) * (size_t)stage_cap, st));
-    S3D_CUDA(s3d::dev_alloc((void**)&d_stage_count, sizeof(unsigned), st));
-    S3D_CUDA(cudaMemsetAsync(d_stage_count, 0, sizeof(unsigned), st));
-    S3D_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int) * 4, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_cand, sizeof(Cand) * (size_t)cap_e, st));
+    int* d_total = c->d_counts;
+    unsigned* d_stage_count = (unsigned*)(d_total + CT_STAGED);
+    S3D_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int) * CT_N, st));
     S3D_CUDA(cudaMemsetAsync(d_blk_cnt, 0, sizeof(int) * nblk, st));
+    // One launch per (octave, level) unit.  (A single launch per octave over its three units was considered: the
+    // kernel reads one level's threshold slot, and the launches of an octave already run back to back on the stream.)
     for (int o = 0; o < c->noct; o++) {
         const ll vb = (ll)c->p0[o] * (ll)c->plane(o), ve = (ll)c->p1[o] * (ll)c->plane(o);
         if (ve <= vb) continue;
@@ -823,21 +851,11 @@ int stage_sparse(s3d_ctx* c) {
     }
     {
         ProfScope ps(&c->prof, K_COMPACT, 8.0 * nblk);
-        S3D_LAUNCH(scan_kernel, 1, 1024, 0, st, d_blk_cnt, d_blk_off, nblk, d_total);
+        S3D_LAUNCH(scan_kernel, 1, 1024, 0, st, d_blk_cnt, d_blk_off, nblk, d_total + CT_NE);
     }
-    unsigned h_stage = 0;
-    int h_total[4] = {0, 0, 0, 0};
-    S3D_CUDA(cudaMemcpyAsync(&h_stage, d_stage_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    S3D_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(int), cudaMemcpyDeviceToHost, st));
-    S3D_CUDA(cudaStreamSynchronize(st));
-    if (h_stage > stage_cap)
-        return fail(S3D_ERR_CAPACITY, "detection staged %u candidates, capacity %u", h_stage, stage_cap);
-    c->n_extre = h_total[0];
-    const int ne = c->n_extre;
-    if (ne > 0) {
-        S3D_CUDA(s3d::dev_alloc((void**)&d_cand, sizeof(Cand) * (size_t)ne, st));
-        ProfScope ps(&c->prof, K_COMPACT, 24.0 * ne);
-        S3D_LAUNCH(scatter_kernel, s3d_blocks(ne, 256), 256, 0, st, d_stage, d_stage_count, stage_cap, d_blk_off, d_cand);
+    {
+        ProfScope ps(&c->prof, K_COMPACT, 0.0);
+        S3D_LAUNCH(scatter_kernel, 148 * 4, 256, 0, st, d_stage, d_stage_count, stage_cap, d_blk_off, d_cand, cap_e);
     }
     S3D_CUDA(cudaEventRecord(c->ev[3], st));
 
@@ -867,53 +885,43 @@ int stage_sparse(s3d_ctx* c) {
             }
         S3D_CUDA(s3d::dev_alloc((void**)&d_wtab, sizeof(float) * std::max(off, 1), st));
         tab.wtab = d_wtab;
-        if (ne > 0) S3D_LAUNCH(wtab_kernel, dim3(2, c->noct * G), 256, 0, st, tab, c->noct, d_wtab);
+        S3D_LAUNCH(wtab_kernel, dim3(2, c->noct * G), 256, 0, st, tab, c->noct, d_wtab);
     }
     int *d_recheck = nullptr;
     int* d_surv = nullptr;
     int* d_order = nullptr;
-    const size_t nea = std::max(ne, 1);
-    S3D_CUDA(s3d::dev_alloc((void**)&c->d_extre, sizeof(s3d_keypoint) * nea, st));
-    S3D_CUDA(s3d::dev_alloc((void**)&c->d_codes, sizeof(int) * nea, st));
-    S3D_CUDA(s3d::dev_alloc((void**)&c->d_xyz5, sizeof(int) * 5 * nea, st));
-    S3D_CUDA(s3d::dev_alloc((void**)&d_recheck, sizeof(int) * nea, st));
-    S3D_CUDA(s3d::dev_alloc((void**)&d_surv, sizeof(int) * nea, st));
-    if (ne > 0) {
-        const unsigned grid = (unsigned)std::min<size_t>(s3d_blocks((size_t)ne * 32, 256), 148 * 32);
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_extre, sizeof(s3d_keypoint) * (size_t)cap_e, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_codes, sizeof(int) * (size_t)cap_e, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_xyz5, sizeof(int) * 5 * (size_t)cap_e, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_recheck, sizeof(int) * (size_t)cap_e, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&d_surv, sizeof(int) * (size_t)cap_e, st));
+    {
         {
-            ProfScope ps(&c->prof, K_ORIENT, 200.0 * ne);
-            S3D_LAUNCH(orient_kernel, grid, 256, 0, st, d_cand, ne, tab, c->d_extre, c->d_codes, c->d_xyz5,
+            ProfScope ps(&c->prof, K_ORIENT, 0.0);
+            S3D_LAUNCH(orient_kernel, 148 * 32, 256, 0, st, d_cand, (const int*)(d_total + CT_NE), cap_e, tab, c->d_extre, c->d_codes, c->d_xyz5,
                        c->prm.max_eig_thres, c->prm.corner_thresh, 2e-3f, c->prm.exact_recheck ? d_recheck : (int*)nullptr,
-                       d_total + 1);
+                       d_total + CT_RECHECK);
         }
         ProfScope ps(&c->prof, K_ORIENT_EXACT, 0.0);
         if (c->prm.exact_recheck)
-            S3D_LAUNCH(orient_exact_kernel, (unsigned)std::min<size_t>((size_t)ne, 148 * 6),
-                       kExactWarps * 32, 0, st, d_cand, tab, c->d_extre, c->d_codes, d_recheck, d_total + 1,
-                       c->prm.max_eig_thres, c->prm.corner_thresh, d_total + 2);
+            S3D_LAUNCH(orient_exact_kernel, 148 * 6, kExactWarps * 32, 0, st, d_cand, tab, c->d_extre, c->d_codes, d_recheck,
+                       d_total + CT_RECHECK, c->prm.max_eig_thres, c->prm.corner_thresh, d_total + CT_FLIPPED);
     }
     {
-        ProfScope ps(&c->prof, K_SURVIVORS, 8.0 * ne);
-        S3D_LAUNCH(survivors_kernel, 1, 1024, 0, st, c->d_codes, ne, d_surv, d_total + 3);
+        ProfScope ps(&c->prof, K_SURVIVORS, 0.0);
+        S3D_LAUNCH(survivors_kernel, 1, 1024, 0, st, c->d_codes, (const int*)(d_total + CT_NE), cap_e, d_surv, d_total + CT_NKPS);
         // heavy-first launch order of the descriptor CTAs (S3D_DESC_ORDER=0: list order)
-        if (desc_order_enabled() && ne > 0) {
-            S3D_CUDA(s3d::dev_alloc((void**)&d_order, sizeof(int) * nea, st));
-            S3D_LAUNCH(desc_order_kernel, 1, 1024, 0, st, c->d_extre, d_surv, d_total + 3, G - 1, d_order);
+        if (desc_order_enabled()) {
+            S3D_CUDA(s3d::dev_alloc((void**)&d_order, sizeof(int) * (size_t)cap_e, st));
+            S3D_LAUNCH(desc_order_kernel, 1, 1024, 0, st, c->d_extre, d_surv, d_total + CT_NKPS, G - 1, d_order);
         }
     }
-    S3D_CUDA(cudaMemcpyAsync(h_total, d_total, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-    S3D_CUDA(cudaStreamSynchronize(st));
-    c->n_rechecked = h_total[1];
-    c->n_flipped = h_total[2];
-    c->n_kps = h_total[3];
     S3D_CUDA(cudaEventRecord(c->ev[4], st));
 
     // ---- Description -----------------------------------------------------------------------------
-    const size_t nka = std::max(c->n_kps, 1);
-    S3D_CUDA(s3d::dev_alloc((void**)&c->d_kps, sizeof(s3d_keypoint) * nka, st));
-    S3D_CUDA(s3d::dev_alloc((void**)&c->d_desc, sizeof(float) * S3D_DESC_LEN * nka, st));
-    int* d_redo = nullptr;
-    if (c->n_kps > 0) {
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_kps, sizeof(s3d_keypoint) * (size_t)cap_k, st));
+    S3D_CUDA(s3d::dev_alloc((void**)&c->d_desc, sizeof(float) * S3D_DESC_LEN * (size_t)cap_k, st));
+    {
         static bool attr_set[64] = {false};
         if (c->device < 64 && !attr_set[c->device]) {
             S3D_CUDA(cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DescSmem)));
@@ -921,34 +929,34 @@ int stage_sparse(s3d_ctx* c) {
             attr_set[c->device] = true;
         }
         const int path = g_describe_path.load();
+        // one CTA per keypoint SLOT (the count is on the device; surplus CTAs leave at once)
+        const int grid_q = cap_k, grid_f = cap_k;
         if (path == 1) {  // FP32 staged/ordered accumulation for every keypoint
-            ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
-            S3D_LAUNCH(describe_kernel<false>, c->n_kps, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, c->n_kps, tab,
-                       (const MeshConst*)c->d_mesh, c->d_kps, c->d_desc, (const int*)nullptr, (const int*)nullptr, (int*)nullptr, (int*)nullptr, 0.0f);
+            ProfScope ps(&c->prof, K_DESCRIBE, 0.0);
+            S3D_LAUNCH(describe_kernel<false>, grid_f, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, cap_e, tab,
+                       (const MeshConst*)c->d_mesh, c->d_kps, c->d_desc, (const int*)d_order, (const int*)(d_total + CT_NKPS), (int*)nullptr,
+                       (int*)nullptr, 0.0f, cap_k);
         } else {
             // fixed-point atomics for all; the (normally empty) list of keypoints whose scale estimate was
-            // too low is redone in FP32 — its grid is sized for the worst case and reads the count on the device
-            S3D_CUDA(s3d::dev_alloc((void**)&d_redo, sizeof(int) * ((size_t)c->n_kps + 1), st));
-            S3D_CUDA(cudaMemsetAsync(d_redo, 0, sizeof(int), st));
+            // too low is redone in FP32 — its grid reads the redo count on the device, so there is no host sync
+            S3D_CUDA(s3d::dev_alloc((void**)&c->d_redo, sizeof(int) * ((size_t)cap_k + 1), st));
             {
-                ProfScope ps(&c->prof, K_DESCRIBE, (176.0 + 3072.0) * c->n_kps);
-                S3D_LAUNCH(describe_kernel<true>, c->n_kps, kDescWarps * 32, sizeof(DescSmemQ), st, c->d_extre, d_surv, c->n_kps, tab,
-                           (const MeshConst*)c->d_mesh, c->d_kps, c->d_desc, (const int*)d_order, (const int*)nullptr, d_redo + 1, d_redo,
-                           path == 2 ? 0.02f : kQMargin);
+                ProfScope ps(&c->prof, K_DESCRIBE, 0.0);
+                S3D_LAUNCH(describe_kernel<true>, grid_q, kDescWarps * 32, sizeof(DescSmemQ), st, c->d_extre, d_surv, cap_e, tab,
+                           (const MeshConst*)c->d_mesh, c->d_kps, c->d_desc, (const int*)d_order, (const int*)(d_total + CT_NKPS), c->d_redo,
+                           d_total + CT_REDO, path == 2 ? 0.02f : kQMargin, cap_k);
             }
             ProfScope ps(&c->prof, K_DESCRIBE_REDO, 0.0);
-            S3D_LAUNCH(describe_kernel<false>, c->n_kps, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, c->n_kps, tab,
-                       (const MeshConst*)c->d_mesh, c->d_kps, c->d_desc, (const int*)(d_redo + 1), (const int*)d_redo, (int*)nullptr, (int*)nullptr, 0.0f);
-            c->d_redo = d_redo;  // the count is read in s3d_wait
-            d_redo = nullptr;
+            S3D_LAUNCH(describe_kernel<false>, grid_f, kDescWarps * 32, sizeof(DescSmem), st, c->d_extre, d_surv, cap_k, tab,
+                       (const MeshConst*)c->d_mesh, c->d_kps, c->d_desc, (const int*)c->d_redo, (const int*)(d_total + CT_REDO), (int*)nullptr,
+                       (int*)nullptr, 0.0f, cap_k);
         }
     }
     S3D_CUDA(cudaGetLastError());
     S3D_CUDA(cudaEventRecord(c->ev[5], st));
 
-    // ---- Release_SIFT (:1659-1678) unless the caller asked to keep the pyramids ---------------
-    if (!c->prm.keep_levels) free_levels(c);
-    void* tmp[] = {d_blk_cnt, d_blk_off, d_total, d_stage, d_stage_count, d_cand, d_recheck, d_surv, d_order, d_wtab, d_redo};
+    // ---- Release_SIFT (:1659-1678): the pyramids are released in s3d_wait, once the counts have confirmed the capacities
+    void* tmp[] = {d_blk_cnt, d_blk_off, d_stage, d_cand, d_recheck, d_surv, d_order, d_wtab};
     for (void* q : tmp) if (q) s3d::dev_free(q, st);
     S3D_CUDA(cudaEventRecord(c->ev[6], st));
     c->queued = true;
@@ -982,13 +990,45 @@ int s3d_wait(s3d_handle c) {
     if (!c) return fail(S3D_ERR_ARG, "null handle");
     if (!c->queued) return fail(S3D_ERR_STATE, "s3d_wait before s3d_run_async");
     S3D_CUDA(cudaSetDevice(c->device));
-    S3D_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->d_redo) {
-        S3D_CUDA(cudaMemcpy(&c->n_desc_redo, c->d_redo, sizeof(int), cudaMemcpyDeviceToHost));
-        s3d::dev_free(c->d_redo, c->stream);
-        c->d_redo = nullptr;
+    if (c->ran) {
+        S3D_CUDA(cudaStreamSynchronize(c->stream));
+        return S3D_OK;
     }
-    if (!c->ran) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        // the ONLY host wait of a step: the counts the device produced and consumed on its own
+        int h[CT_N] = {0};
+        S3D_CUDA(cudaMemcpyAsync(h, c->d_counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        S3D_CUDA(cudaStreamSynchronize(c->stream));
+        const int ne = h[CT_NE], nk = h[CT_NKPS];
+        const bool fits = ne <= c->cap_extre && (unsigned)h[CT_STAGED] <= (unsigned)c->cap_extre && nk <= c->cap_kps;
+        if (c->own_total > 0) {
+            learn_density(g_dens_extre, (double)ne / (double)c->own_total);
+            learn_density(g_dens_kps, (double)nk / (double)c->own_total);
+        }
+        if (fits) {
+            c->n_extre = ne; c->n_rechecked = h[CT_RECHECK]; c->n_flipped = h[CT_FLIPPED]; c->n_kps = nk; c->n_desc_redo = h[CT_REDO];
+            break;
+        }
+        if (attempt == 1 || !c->levels_alive)
+            return fail(S3D_ERR_CAPACITY, "sparse stage: %d detections / %d keypoints exceed the buffers (%d / %d) after resizing", ne, nk,
+                        c->cap_extre, c->cap_kps);
+        // the optimistic buffers were too small for this volume: repeat the sparse stage from the kept pyramid with
+        // exact sizes (the densities are learned, so the next volume of the job is sized right)
+        void* old[] = {c->d_extre, c->d_codes, c->d_xyz5, c->d_kps, c->d_desc, c->d_redo, c->d_counts};
+        for (void* q : old) if (q) s3d::dev_free(q, c->stream);
+        c->d_extre = nullptr; c->d_codes = nullptr; c->d_xyz5 = nullptr; c->d_kps = nullptr; c->d_desc = nullptr; c->d_redo = nullptr;
+        c->d_counts = nullptr;
+        c->cap_extre = std::max(ne, h[CT_STAGED]) + 1024;
+        c->cap_kps = std::max(nk, 1) + 1024;
+        c->n_resized++;
+        c->prof.resolve();
+        for (int k = 0; k < K_NCLS; ++k) if (k >= K_DETECT) { c->prof.ms[k] = 0; c->prof.cnt[k] = 0; c->prof.bytes[k] = 0; }
+        S3D_TRY(stage_sparse(c));
+    }
+    if (c->d_redo) { s3d::dev_free(c->d_redo, c->stream); c->d_redo = nullptr; }
+    if (c->d_counts) { s3d::dev_free(c->d_counts, c->stream); c->d_counts = nullptr; }
+    if (!c->prm.keep_levels) free_levels(c);
+    {
         float ms;
         for (int i = 0; i < 6; i++) {
             cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
@@ -1225,7 +1265,7 @@ int s3d_get_counters(s3d_handle c, int* out4) {
     clear_error();
     if (!c || !out4) return fail(S3D_ERR_ARG, "null argument");
     if (!c->ran) return fail(S3D_ERR_STATE, "s3d_get_counters before s3d_run");
-    out4[0] = c->n_rechecked; out4[1] = c->n_flipped; out4[2] = c->n_desc_redo; out4[3] = 0;
+    out4[0] = c->n_rechecked; out4[1] = c->n_flipped; out4[2] = c->n_desc_redo; out4[3] = c->n_resized;
     return S3D_OK;
 }
 

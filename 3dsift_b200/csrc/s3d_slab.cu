@@ -276,6 +276,12 @@ static void owned_of(int nz, int world, int rank, int o, int* p0, int* p1) {
     *p1 = std::min(nzo, (own1 + sh - 1) >> o);
 }
 
+static int slab_group_size() {
+    const char* e = getenv("S3D_SLAB_GROUP");  // levels per halo exchange (1..6), read per call: the tests switch it
+    const int v = e ? atoi(e) : 3;
+    return v < 1 ? 1 : (v > 8 ? 8 : v);
+}
+
 static int min_sharded_nz() {
     const char* e = getenv("S3D_SLAB_MIN_NZ");  // read per call: the tests switch it
     return e ? atoi(e) : 96;
@@ -395,7 +401,8 @@ static int slab_create_impl(int world, int rank, int device, const float* vol_ow
 }
 
 // KpSiftAlgorithm over the shards (collective): second sweep of data_scale with the global maximum, pyramid with halo
-// exchanges, thresholds, sparse stages on the owned planes.  Blocks until this shard's results are ready.
+// exchanges, thresholds, sparse stages on the owned planes.  Only ENQUEUES (kernels and collectives) on the shard's
+// stream: the host can go on to enqueue the next volume while this one runs; s3d_wait completes the run.
 static int slab_run_impl(Comm& cm, s3d_ctx* c) {
     if (!c->slab || c->stage != 1 || c->ran) return fail(S3D_ERR_STATE, "not a freshly created slab handle");
     cudaStream_t st = c->stream;
@@ -422,11 +429,24 @@ static int slab_run_impl(Comm& cm, s3d_ctx* c) {
             for (int i = 0; i < G; ++i) S3D_TRY(stage_level(c, o, i, 0, nzo));
         } else {
             if (o > 0) S3D_TRY(stage_seed(c, o, c->p0[o], c->p1[o]));
-            const int zlo = std::max(0, c->p0[o] - 1), zhi = std::min(nzo, c->p1[o] + 1);
-            for (int i = (o == 0 ? 0 : 1); i < G; ++i) {
-                float* src = (o == 0 && i == 0) ? c->d_input : c->gss[o * G + i - 1];
-                S3D_TRY(exchange(c, cm, src, o, c->taps[i].hw + 1));
-                S3D_TRY(stage_level(c, o, i, zlo, zhi));
+            // Levels are built in GROUPS of `gsz` with one halo exchange per group: the group's first source level is
+            // exchanged 1 + sum(hw) planes deep and level j is produced on owned +- (1 + the hw of the group's later
+            // levels), so the later levels find their halo locally (the same arithmetic on the same inputs: the
+            // redundant planes carry the owner's bits).  gsz = 1: an exchange of hw + 1 planes before every level.
+            // Every exchange is a rendezvous of neighbouring ranks; fewer, deeper exchanges trade a few redundant
+            // planes for fewer collective launches.
+            const int gsz = slab_group_size();
+            for (int a = (o == 0 ? 0 : 1); a < G; a += gsz) {
+                const int b = std::min(G - 1, a + gsz - 1);
+                int depth = 1;
+                for (int j = a; j <= b; ++j) depth += c->taps[j].hw;
+                float* src = (o == 0 && a == 0) ? c->d_input : c->gss[o * G + a - 1];
+                S3D_TRY(exchange(c, cm, src, o, depth));
+                for (int j = a; j <= b; ++j) {
+                    int ext = 1;
+                    for (int k = j + 1; k <= b; ++k) ext += c->taps[k].hw;
+                    S3D_TRY(stage_level(c, o, j, std::max(0, c->p0[o] - ext), std::min(nzo, c->p1[o] + ext)));
+                }
             }
             for (int l = 1; l <= L; ++l) add_halo(c, cm, c->gss[o * G + l], o, slab_window_halo(c, l), wsends, wrecvs);
         }
@@ -443,18 +463,7 @@ static int slab_run_impl(Comm& cm, s3d_ctx* c) {
     // ---- Detect_KeyPoints, Assign_Orientation, Extract_Description on the owned planes ---------------------------
     S3D_TRY(stage_sparse(c));
     S3D_CUDA(cudaEventRecord(c->ph_ev[4], st));
-    S3D_TRY(s3d_wait(c));
-    for (int k = 0; k < 4; ++k) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ph_ev[k], c->ph_ev[k + 1]);
-        c->ph_ms[k] = ms;
-    }
-    {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ph_ev[6], c->ph_ev[5]);
-        c->ph_ms[5] = ms;
-    }
-    return S3D_OK;
+    return S3D_OK;  // everything is enqueued; s3d_wait(c) completes the run
 }
 
 // ---- result gather ------------------------------------------------------------------------------------------
@@ -705,11 +714,16 @@ int s3d_slab_create(s3d_comm_t comm, const float* vol_own, int on_device, int nx
     return S3D_OK;
 }
 
-int s3d_slab_execute(s3d_comm_t comm, s3d_handle h) {
+int s3d_slab_execute_async(s3d_comm_t comm, s3d_handle h) {
     clear_error();
     if (!comm || !comm->impl || !h) return fail(S3D_ERR_ARG, "null argument");
     S3D_CUDA(cudaSetDevice(comm->impl->device));
     return slab_run_impl(*comm->impl, h);
+}
+
+int s3d_slab_execute(s3d_comm_t comm, s3d_handle h) {
+    const int r = s3d_slab_execute_async(comm, h);
+    return r != S3D_OK ? r : s3d_wait(h);
 }
 
 int s3d_slab_run(s3d_comm_t comm, const float* vol_own, int on_device, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out) {
@@ -730,6 +744,15 @@ int s3d_slab_gather(s3d_comm_t comm, s3d_handle h, int root, int with_extrema) {
 
 int s3d_slab_phases(s3d_handle h, double* ms8) {
     if (!h || !ms8) return fail(S3D_ERR_ARG, "null argument");
+    if (h->slab && h->ran && h->ph_ev[0]) {
+        for (int k = 0; k < 4; ++k) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, h->ph_ev[k], h->ph_ev[k + 1]) == cudaSuccess) h->ph_ms[k] = ms;
+        }
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, h->ph_ev[6], h->ph_ev[5]) == cudaSuccess) h->ph_ms[5] = ms;
+        cudaGetLastError();
+    }
     for (int k = 0; k < 8; ++k) ms8[k] = h->ph_ms[k];
     return S3D_OK;
 }
@@ -766,6 +789,7 @@ int s3d_extract_multi(const float* vol, int nx, int ny, int nz, const s3d_params
             r = slab_create_impl(nshards, g, rdev, vol + (size_t)own0 * nx * ny, 0, nx, ny, nz, &prm, &ctx[g]);
         }
         if (r == S3D_OK) r = slab_run_impl(cm, ctx[g]);
+        if (r == S3D_OK) r = s3d_wait(ctx[g]);
         if (r == S3D_OK) r = slab_gather_impl(cm, ctx[g], 0, with_extrema);
         if (r != S3D_OK) {
             group.failed = true;

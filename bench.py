@@ -220,6 +220,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line: libraries that print there from C (NCCL's version banner) are sent to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on STDOUT: rank 0 must print one JSON line only
@@ -277,12 +281,50 @@ def main():
     e2e_split = {}
     e2e_step_ms = []
 
-    # host threads of the e2e leg: every thread's first upload is exposed (9.7 ms each, one copy engine direction), so
-    # concurrency only pays off on longer runs - measured at 10 steps: 19.6 ms/step with 1 thread, 18.9 with 3, 20.8 with 4
+    # e2e host side.  A step has no host round trip (s3d_run_async only enqueues; the counts stay on the device until
+    # s3d_wait), so ONE host thread keeps E2E_DEPTH volumes in flight on private handles/streams: volume i+1 uploading,
+    # volume i extracting, volume i-1's results on their way to the host.  S3D_E2E_THREADS > 0 selects the round-1
+    # variant instead (blocking KpSiftAlgorithm calls dealt to several host threads).
     _thr_env = os.environ.get("S3D_E2E_THREADS")
-    E2E_THREADS = max(1, int(_thr_env)) if _thr_env else (1 if a.steps < 16 else 2 if a.steps < 32 else 3)
+    E2E_THREADS = max(0, int(_thr_env)) if _thr_env else 0
+    E2E_DEPTH = max(1, int(os.environ.get("S3D_E2E_DEPTH", "2")))
+
+    def e2e_steps_async(k_steps):
+        del e2e_step_ms[:]
+        t_prev = [time.perf_counter()]
+        inflight, kcount = [], 0
+
+        def finish(h, slot):
+            h.wait()
+            nk = h.num_keypoints()
+            h.get_keypoints_async(h_kp[slot].data_ptr(), h_desc[slot].data_ptr())
+            h.sync()
+            t = h.m_timer
+            e2e_split.update(h2d_ms=t["d_h2d"] * 1e3, d2h_ms=t["d_d2h"] * 1e3, device_ms=t["d_TotalTime"] * 1e3)
+            now = time.perf_counter()
+            e2e_step_ms.append(round((now - t_prev[0]) * 1e3, 2))
+            t_prev[0] = now
+            h.close()
+            return nk
+
+        cur = upload() if k_steps > 0 else None
+        for i in range(k_steps):
+            nxt = upload() if i + 1 < k_steps else None
+            cur.run_async()
+            inflight.append((cur, i % n_res))
+            if len(inflight) >= E2E_DEPTH:
+                kcount = finish(*inflight.pop(0))
+            cur = nxt
+        while inflight:
+            kcount = finish(*inflight.pop(0))
+        return kcount
 
     def e2e_steps(k_steps):
+        if E2E_THREADS == 0:
+            return e2e_steps_async(k_steps)
+        return e2e_steps_threads(k_steps)
+
+    def e2e_steps_threads(k_steps):
         """k_steps volumes through the public host API, dealt to E2E_THREADS host threads (the C calls release the GIL).
         Each thread keeps three volumes in flight on private handles/streams: volume i+1 uploading (copy engine), volume i
         extracting, volume i-1's records + descriptors on their way into one of the thread's two pinned result buffers
@@ -394,7 +436,7 @@ def main():
     # ---- e2e: host buffers, H2D + D2H inside --------------------------------------------------------
     # its own W untimed warm-up steps first: the e2e handles run on private streams, and the first
     # volumes after the resident leg re-home the stream-ordered memory pool's blocks
-    e2e_steps(max(a.warmup, 3 * E2E_THREADS))   # every thread reaches its three-volumes-in-flight state (block cache warm)
+    e2e_steps(max(a.warmup, 3 * max(E2E_THREADS, 1)))   # the pipeline reaches its steady state (block cache warm)
     barrier()
     w0 = time.time()
     ev0.record()
@@ -425,70 +467,90 @@ def main():
         api.check(L.s3d_slab_bounds(n, world, rank, C.byref(o0), C.byref(o1)))
         own0, own1 = o0.value, o1.value
         d_own, h_own = d_vol[own0:own1], h_vol[own0:own1]
-        p_res, p_e2e = D._params(dict(device=local)), D._params(dict(device=local))
-        p_res.stream = C.c_void_p(stream or 1)     # resident leg: on torch's current stream, bracketed by its events
+        p_e2e = D._params(dict(device=local))
 
-        def slab_resident_step():
+        def slab_create(resident):
             h = C.c_void_p()
-            api.check(L.s3d_slab_create(comm._c, d_own.data_ptr(), 1, n, n, n, C.byref(p_res), C.byref(h)))
-            api.check(L.s3d_slab_execute(comm._c, h))
-            api.check(L.s3d_slab_gather(comm._c, h, 0, 0))
+            if resident:
+                api.check(L.s3d_slab_create(comm._c, d_own.data_ptr(), 1, n, n, n, C.byref(p_e2e), C.byref(h)))
+            else:
+                api.check(L.s3d_slab_create(comm._c, h_own.data_ptr(), 0, n, n, n, C.byref(p_e2e), C.byref(h)))
             return h
 
-        def slab_create_host():
-            h = C.c_void_p()
-            api.check(L.s3d_slab_create(comm._c, h_own.data_ptr(), 0, n, n, n, C.byref(p_e2e), C.byref(h)))
-            return h
+        slab_last = {}
 
-        def slab_e2e_steps(k_steps):
-            """k_steps volumes, one at a time over all ranks, host buffers on both ends: every rank uploads ITS planes
-            of volume i+1 from pinned memory (s3d_slab_create only enqueues, private stream) while volume i is
-            extracted (s3d_slab_execute, collective), the results are merged on rank 0 over NCCL (s3d_slab_gather)
-            and copied into pinned host buffers there."""
-            kk = 0
-            cur = slab_create_host()
+        def slab_steps(k_steps, resident, keep_last=False):
+            """k_steps volumes, each extracted by all ranks together, two volumes in flight: s3d_slab_create (allocation +
+            copy of the rank's own planes: device-to-device for the resident leg, from pinned host memory for the e2e leg)
+            and s3d_slab_execute_async (kernels + NCCL collectives, enqueue only) of volume i+1 are issued while volume i
+            runs; s3d_wait, s3d_slab_gather (merge on rank 0 over NCCL) and — e2e leg — the copy of the merged records
+            + descriptors into pinned host memory on rank 0 complete volume i."""
+            inflight, kk = [], 0
+
+            def finish(h, slot):
+                api.check(L.s3d_wait(h))
+                api.check(L.s3d_slab_gather(comm._c, h, 0, 0))
+                nn = C.c_int()
+                api.check(L.s3d_num_keypoints(h, C.byref(nn)))
+                if rank == 0 and not resident:
+                    api.check(L.s3d_get_keypoints_async(h, h_kp[slot].data_ptr(), h_desc[slot].data_ptr()))
+                    api.check(L.s3d_sync(h))
+                if keep_last and not inflight:
+                    slab_last["h"] = h
+                else:
+                    L.s3d_destroy(h)
+                return nn.value
+
+            cur = slab_create(resident) if k_steps > 0 else None
             for i in range(k_steps):
-                nxt = slab_create_host() if i + 1 < k_steps else None
-                api.check(L.s3d_slab_execute(comm._c, cur))
-                api.check(L.s3d_slab_gather(comm._c, cur, 0, 0))
-                if rank == 0:
-                    api.check(L.s3d_get_keypoints_async(cur, h_kp[i & 1].data_ptr(), h_desc[i & 1].data_ptr()))
-                    api.check(L.s3d_sync(cur))
-                    nn = C.c_int()
-                    api.check(L.s3d_num_keypoints(cur, C.byref(nn)))
-                    kk = nn.value
-                L.s3d_destroy(cur)
+                nxt = slab_create(resident) if i + 1 < k_steps else None
+                api.check(L.s3d_slab_execute_async(comm._c, cur))
+                inflight.append((cur, i & 1))
+                if len(inflight) >= 2:
+                    kk = finish(*inflight.pop(0))
                 cur = nxt
+            while inflight:
+                kk = finish(*inflight.pop(0))
             return kk
 
-        for _ in range(max(a.warmup, 3)):
-            L.s3d_destroy(slab_resident_step())
+        slab_steps(max(a.warmup, 3), True)
         sent0 = comm.traffic()[0]
         ksl = max(5, min(a.steps, 20))
         barrier()
         w0 = time.time()
         ev0.record()
-        hh = None
-        for _ in range(ksl):
-            if hh is not None:
-                L.s3d_destroy(hh)
-            hh = slab_resident_step()
+        slab_steps(ksl, True, keep_last=True)
+        torch.cuda.synchronize()
         ev1.record()
         barrier()
         windows.append((w0, time.time()))
         ms_slab = max_over_ranks(ev0.elapsed_time(ev1) / ksl)
-        sh = D.SlabShard(hh, (n, n, n), rank)
-        phases = sh.phases()
-        nk_slab = sh.num_keypoints()
+        L.s3d_destroy(slab_last.pop("h"))
         sent_per_step = (comm.traffic()[0] - sent0) / ksl
-        sh.close()
-        slab_e2e_steps(max(a.warmup, 3))
+        # latency of ONE volume, nothing in flight besides it (resident planes): create -> execute -> gather; the
+        # per-phase device times are taken from these runs (with two volumes in flight a phase's event span also
+        # covers the other volume's kernels)
+        lat_slab = []
+        for _ in range(5):
+            barrier()
+            t0 = time.perf_counter()
+            slab_steps(1, True, keep_last=True)
+            torch.cuda.synchronize()
+            lat_slab.append((time.perf_counter() - t0) * 1e3)
+            sh = D.SlabShard(slab_last.pop("h"), (n, n, n), rank)
+            phases = sh.phases()
+            nk_slab = sh.num_keypoints()
+            sh.close()
+        lat_slab_ms = max_over_ranks(float(np.median(lat_slab)))
+        slab_steps(max(a.warmup, 3), False)
         barrier()
         w0 = time.time()
-        t0 = time.perf_counter()
-        nk_e2e = slab_e2e_steps(ksl)
+        ev0.record()
+        nk_e2e = slab_steps(ksl, False)
+        torch.cuda.synchronize()
+        ev1.record()
         barrier()
-        ms_slab_e2e = max_over_ranks((time.perf_counter() - t0) / ksl * 1e3)
+        ms_slab_e2e = max_over_ranks(ev0.elapsed_time(ev1) / ksl)
         windows.append((w0, time.time()))
         ph_all = None
         if world > 1:
@@ -499,17 +561,19 @@ def main():
             ph_all = [[round(float(v), 3) for v in x] for x in allp]
         extra["slab"] = {
             "metric": "Mvoxels/s, ONE 512^3 volume extracted by all GPUs together (z-slabs)", "scaling": "strong", "shards": world,
-            "value": nvox / (ms_slab * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume": ms_slab, "steps": ksl,
+            "value": nvox / (ms_slab * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume": ms_slab, "steps": ksl, "volumes_in_flight": 2,
+            "latency_ms_single_volume": lat_slab_ms,
             "e2e": {"value": nvox / (ms_slab_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume": ms_slab_e2e,
                     "h2d_bytes_per_step": int(vol.nbytes), "d2h_bytes_per_step": int(nk_e2e * (176 + 768 * 4)),
                     "note": "pinned host volume in (every rank uploads its own planes, one volume ahead), merged records + "
-                            "descriptors out in pinned host memory on rank 0; wall clock between barriers, max over ranks"},
+                            "descriptors out in pinned host memory on rank 0; CUDA events around the synchronised loop, max over ranks"},
             "keypoints": nk_slab, "equal_to_single_gpu_keypoints": bool(nk_slab == nkp) if rank == 0 else None,
             "phases_ms_rank0": {k_: round(v, 3) for k_, v in phases.items()},
             "phases_per_rank": ph_all, "phases_per_rank_columns": ["normalize ms", "pyramid ms", "halo ms", "sparse ms", "gather ms", "nccl bytes sent per volume"],
             "nccl_bytes_sent_per_volume_rank0": sent_per_step,
-            "note": "value: every rank's planes resident in HBM, s3d_slab_create + s3d_slab_execute + s3d_slab_gather on torch's "
-                    "current stream between CUDA events, max over ranks; parity with the unsharded run: tests/test_gpu_slab.py "
+            "note": "value = THROUGHPUT with every rank's planes resident in HBM: s3d_slab_create + s3d_slab_execute_async + s3d_wait + "
+                    "s3d_slab_gather, two volumes in flight on private streams, CUDA events around the synchronised loop, max over "
+                    "ranks; latency_ms_single_volume = one volume at a time; parity with the unsharded run: tests/test_gpu_slab.py "
                     "and scripts/multi_gpu_check.py (bit-equal)"}
 
     # ---- matching legs (secondary metric): enhancedMatch on HBM-resident descriptor sets ----------------
@@ -678,14 +742,15 @@ def main():
                        "l2": f"inputs ({vol.nbytes >> 20} MiB/volume) are larger than L2; no flush needed",
                        "parallelism": f"dp{world} (one volume per GPU, no collective on the data path)"},
             "clocks": sampler.summary(windows[:2]),   # the two extraction legs (value, e2e)
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "host_threads": E2E_THREADS, "h2d_bytes_per_step": int(vol.nbytes),
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "host_threads": max(E2E_THREADS, 1), "volumes_in_flight": E2E_DEPTH if E2E_THREADS == 0 else 3 * E2E_THREADS,
+                    "h2d_bytes_per_step": int(vol.nbytes),
                     "d2h_bytes_per_step": int(k * (176 + 768 * 4)),
                     "latency_ms_single_volume": lat_ms, "latency_ms_samples_rank0": lat_all,
                     "last_step_split_ms": e2e_split, "host_wall_ms_per_step": list(e2e_step_ms),
                     "note": "value = THROUGHPUT: pinned host volume -> CreateCSIFT3D (H2D on the handle's stream, enqueued one volume "
-                            "ahead) -> KpSiftAlgorithm -> GetKeypoints (D2H of records + descriptors into pinned buffers, enqueued with "
-                            "s3d_get_keypoints_async and collected with s3d_sync after the next extraction); the steps are dealt to "
-                            "host_threads threads, each with its own handles, streams and result buffers; every volume's H2D and "
+                            "ahead) -> KpSiftAlgorithm (s3d_run_async: no host round trip inside a step) -> GetKeypoints (D2H of records + "
+                            "descriptors into pinned buffers after s3d_wait, under the next volume's kernels); one host thread, "
+                            "volumes_in_flight private handles/streams; every volume's H2D and "
                             "D2H complete before the timer stops; host_wall_ms_per_step = completion-to-completion times.  "
                             "latency_ms_single_volume = one volume at a time, nothing overlapped (blocking H2D, extraction, blocking "
                             "D2H), median of 5, max over ranks"},
@@ -727,7 +792,8 @@ def main():
                                              f", 1 timed volume after a 64^3 warm-up, CreateCSIFT3D+KpSiftAlgorithm ({sec:.2f} s, {nk} keypoints)"}
             if match and a.cpu_match_n > 0:
                 match["cpu_baseline"] = time_reference_match(a.cpu_match_n)
-        print(json.dumps(out), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if comm is not None and world == 1:
         comm.close()
     if world > 1:

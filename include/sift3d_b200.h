@@ -153,7 +153,9 @@ S3D_API int s3d_get_thresholds(s3d_handle h, float* out, int n);
 S3D_API int s3d_get_timers(s3d_handle h, double* t10);
 /* Bookkeeping of the exactness safeguards of one run: out4[0] = detections re-evaluated in the
  * reference's serial FP32 order (orientation), [1] = accept/reject codes that changed, [2] = keypoints
- * whose descriptor the fixed-point kernel handed to the FP32 kernel, [3] = reserved. */
+ * whose descriptor the fixed-point kernel handed to the FP32 kernel, [3] = times the sparse stage was repeated
+ * because the optimistically sized detection / keypoint buffers were too small (a step has no host round trip:
+ * counts stay on the device until s3d_wait; S3D_CAP_EXTRE / S3D_CAP_KPS in the environment force the capacities). */
 S3D_API int s3d_get_counters(s3d_handle h, int* out4);
 /* Descriptor accumulation (Extract_Descriptor_Imp Src/cSIFT3D.cc:1152-1381 adds 24 weighted
  * contributions per voxel into the 768-bin histogram): 0 = fixed point with native shared-memory
@@ -222,6 +224,9 @@ S3D_API int s3d_slab_run(s3d_comm_t comm, const float* vol_own, int on_device, i
 S3D_API int s3d_slab_create(s3d_comm_t comm, const float* vol_own, int on_device, int nx, int ny, int nz,
                             const s3d_params* p, s3d_handle* out);
 S3D_API int s3d_slab_execute(s3d_comm_t comm, s3d_handle h);
+/* s3d_slab_execute without the final wait: kernels and collectives of the whole run are only enqueued (there is no
+ * host round trip inside a run), s3d_wait(h) completes it.  Lets every rank enqueue volume k+1 while volume k runs. */
+S3D_API int s3d_slab_execute_async(s3d_comm_t comm, s3d_handle h);
 /* Collective: merge every rank's results in the reference's order into rank `root`'s handle (its
  * s3d_num_keypoints / s3d_get_keypoints / s3d_device_descriptors / s3d_get_extrema then answer for the whole
  * volume); with_extrema = 0 skips the per-detection debug records.  The other ranks keep their own part. */

@@ -21,8 +21,9 @@ def client(tmp_path_factory, s3d):
     return exe
 
 
-def _run(client, a, b, *extra):
-    out = subprocess.run([client, a, b, *extra], capture_output=True, text=True, timeout=300)
+def _run(client, a, b, *extra, env=None):
+    out = subprocess.run([client, a, b, *extra], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, **env) if env else None)
     return out
 
 
@@ -63,3 +64,21 @@ def test_client_matches_python_api(client, tmp_path, s3d, synth, mode):
     want = [f"{r[0]:g},{r[1]:g},{r[2]:g};{t[0]:g},{t[1]:g},{t[2]:g}" for r, t in zip(rm, tm)]
     assert got == want and len(got) > 5
     assert "STATUS 0 0 0" in lines
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0"])
+def test_client_multi_device_env_gives_the_single_device_output(client, tmp_path, s3d, synth, devices):
+    """SIFT3D_B200_DEVICES spreads CreateCSIFT3D + KpSiftAlgorithm (z-slabs, s3d_extract_multi) and the matcher
+    (database shards, s3d_match_multi) of an UNCHANGED Example.cpp-shaped client over the listed devices; the same
+    device listed several times = logical shards, which a one-GPU box can run.  Output must not change by a character."""
+    va, vb = synth.v_blobs_pair((64, 64, 128), seed=3)
+    a, b = str(tmp_path / "a.bin"), str(tmp_path / "b.bin")
+    s3d.write_matrix_to_disk(a, va)
+    s3d.write_matrix_to_disk(b, vb)
+    one = _run(client, a, b, "--mem")
+    many = _run(client, a, b, "--mem", env={"SIFT3D_B200_DEVICES": devices, "S3D_SLAB_MIN_NZ": "0"})
+    assert one.returncode == 0 and many.returncode == 0, many.stderr
+    assert "STATUS 0 0 0" in many.stdout
+    assert one.stdout == many.stdout
+    assert len([l for l in many.stdout.splitlines() if ";" in l]) > 5

@@ -33,9 +33,11 @@ def _same_records(a, b):
 @pytest.mark.parametrize("shape,shards,min_nz", [((96, 64, 72), 2, 0), ((96, 64, 72), 3, 0), ((128, 48, 64), 4, 0), ((70, 66, 68), 2, 0),
                                                  ((160, 48, 64), 4, 0), ((160, 46, 50), 3, 0), ((64, 96, 160), 5, 0),
                                                  ((96, 64, 72), 3, 1000), ((64, 64, 128), 4, 96), ((48, 56, 200), 8, 0)])
-def test_slabs_equal_unsharded(s3d, synth, shape, shards, min_nz, monkeypatch):
+@pytest.mark.parametrize("group", [1, 3, 6])
+def test_slabs_equal_unsharded(s3d, synth, shape, shards, min_nz, group, monkeypatch):
     d = importlib.import_module("3dsift_b200.dist")
     monkeypatch.setenv("S3D_SLAB_MIN_NZ", str(min_nz))
+    monkeypatch.setenv("S3D_SLAB_GROUP", str(group))      # levels per halo exchange (1 = an exchange before every level)
     vol = synth.v_blobs(shape, seed=11)
     ref = _unsharded(s3d, vol)
     out = d.extract_slabs(vol, shards=shards, params=dict(keep_levels=1), keep=True)

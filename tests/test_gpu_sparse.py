@@ -180,3 +180,32 @@ def test_fixed_point_descriptor_on_low_contrast_volume(s3d, synth, checker, desc
     sift = s3d.CSIFT3DFactory.CreateCSIFT3D(vol)
     sift.KpSiftAlgorithm()
     _compare_sparse(s3d, r, sift)
+
+
+def test_undersized_sparse_buffers_are_resized_and_results_unchanged(s3d, synth, monkeypatch):
+    """A step has no host round trip: detection and keypoint buffers are sized optimistically and the counts stay on the
+    device until s3d_wait.  When a volume exceeds the buffers the sparse stage is repeated from the kept pyramid with
+    exact sizes: forced here with absurdly small capacities, the results must be those of the default run."""
+    vol = synth.v_blobs(64, seed=3)
+    a = s3d.CSIFT3DFactory.CreateCSIFT3D(vol)
+    a.KpSiftAlgorithm()
+    ka, da = a.GetKeypoints(), a.descriptors
+    ea = a.extrema()
+    assert a.counters()["sparse_resized"] == 0 and len(ka) > 8
+    monkeypatch.setenv("S3D_CAP_EXTRE", "16")
+    monkeypatch.setenv("S3D_CAP_KPS", "4")
+    b = s3d.CSIFT3DFactory.CreateCSIFT3D(vol)
+    b.KpSiftAlgorithm()
+    assert b.counters()["sparse_resized"] == 1
+    kb, db = b.GetKeypoints(), b.descriptors
+    eb = b.extrema()
+    assert len(ka) == len(kb) and np.array_equal(da, db)
+    for f in ka.dtype.names:
+        if f != "desc":
+            assert np.array_equal(ka[f], kb[f]), f
+    assert np.array_equal(ea[1], eb[1]) and np.array_equal(ea[2], eb[2])
+    monkeypatch.setenv("S3D_CAP_EXTRE", "100000")     # detections fit, keypoints do not
+    monkeypatch.setenv("S3D_CAP_KPS", "4")
+    c = s3d.CSIFT3DFactory.CreateCSIFT3D(vol)
+    c.KpSiftAlgorithm()
+    assert c.counters()["sparse_resized"] == 1 and np.array_equal(c.descriptors, da)
