@@ -282,8 +282,16 @@ class CSIFT3D:
             z_dim, y_dim, x_dim = (int(v) for v in volume.shape)
         self.dims = (int(x_dim), int(y_dim), int(z_dim))
         if on_device:
+            # s3d_create_device reads raw float32 memory: refuse anything else instead of misreading it
+            import torch
+            if volume.dtype != torch.float32 or not volume.is_contiguous():
+                raise S3DError(f"device volume must be a contiguous float32 tensor (got {volume.dtype}, contiguous={volume.is_contiguous()})")
             if p.device < 0:
                 p.device = volume.device.index
+            if not stream:
+                # without an explicit stream the handle works on a private non-blocking stream, which is not ordered
+                # against the stream that produced `volume`: finish that work first
+                torch.cuda.current_stream(volume.device).synchronize()
             check(L.s3d_create_device(_ptr(volume), x_dim, y_dim, z_dim, C.byref(p), C.byref(self._h)))
         elif async_upload:
             # the upload is only enqueued: `volume` (pinned) must stay alive until KpSiftAlgorithm returns

@@ -194,9 +194,23 @@ void CSIFT3D::KpSiftAlgorithm() {
     m_timer.d_AssignOrientation = t[4]; m_timer.d_Extraction = t[5]; m_timer.d_release = t[6]; m_timer.d_TotalTime = t[7];
     m_timer.d_memoryOverhead = t[8] + t[9];
     if (!quiet()) {
+        // SIFT3D_B200_VERBOSE=1: the lines the reference prints unconditionally while it runs (time_info
+        // Src/cSIFT3D.cc:78-101, KpSiftAlgorithm :165-235), in its order and format, for scripts that scrape them.  The
+        // stages are one fused submission here, so the lines appear together after the run, carrying the device times.
         int ne = 0;
         s3d_num_extrema(impl->h, &ne);
-        std::cout << "After detecting keypoints, kp size is : " << ne << "\nAfter Orientation, kp size is : " << n << std::endl;
+        auto stage_line = [](double seconds, const char* info) { std::cout << "\t\ttime:" << 1000.0 * seconds << "ms  ----" << info << std::endl; };
+        stage_line(0.0, "----start");
+        std::cout << "Initialization is OK" << std::endl;
+        stage_line(t[0], "----Init done");
+        stage_line(t[1], "----Build GSS");
+        stage_line(t[2], "----Build DOG");
+        stage_line(t[3], "----Detect keypoint");
+        std::cout << "After detecting keypoints, kp size is : " << ne << std::endl;
+        std::cout << "After Orientation, kp size is : " << n << std::endl;
+        stage_line(t[4], "----Orientation");
+        stage_line(t[5], "----Description");
+        std::cout << "\ttotal time:" << t[7] << "s  ----" << "finish" << std::endl;
     }
 }
 
@@ -397,6 +411,9 @@ void write_sift_kp(std::vector<Cvec>& kp, const char* file_name) {
 }
 
 void read_sift_kp(const char* file_name, std::vector<Cvec>& kp) {
+    // one "x,y,z" per line, fields split at ',' and parsed with operator>>(float) as the reference's explode /
+    // stringToNum<float> do (Src/cUtil.cc:956-1000); points are APPENDED (:1002-1016).  A line with fewer than three
+    // fields reads past its vector in the reference; here the missing fields are 0.
     std::ifstream in(file_name);
     std::string line;
     int n = 0;
@@ -404,7 +421,12 @@ void read_sift_kp(const char* file_name, std::vector<Cvec>& kp) {
         float v[3] = {0, 0, 0};
         std::stringstream ss(line);
         std::string tok;
-        for (int k = 0; k < 3 && std::getline(ss, tok, ','); ++k) v[k] = (float)atof(tok.c_str());
+        for (int k = 0; k < 3 && std::getline(ss, tok, ','); ++k) {
+            std::istringstream iss(tok);
+            float num = 0.0f;
+            iss >> num;
+            v[k] = num;
+        }
         kp.push_back(Cvec(v[0], v[1], v[2]));
         ++n;
     }
@@ -437,8 +459,34 @@ bool nii_fail(const char* fname, const char* why) {
 
 }  // namespace
 
-float* readNiiFile(const char* fname, int& nx, int& ny, int& nz) {
+// Name of the voxel file of a NIfTI-1 .hdr/.img pair (nifti_findimgname, nifti2_io.cpp): same base name, .img or .img.gz.
+static std::string nii_pair_image(const std::string& hdr_name) {
+    std::string base = hdr_name;
+    if (base.size() > 3 && base.compare(base.size() - 3, 3, ".gz") == 0) base.resize(base.size() - 3);
+    if (base.size() > 4 && (base.compare(base.size() - 4, 4, ".hdr") == 0 || base.compare(base.size() - 4, 4, ".img") == 0)) base.resize(base.size() - 4);
+    for (const char* ext : {".img", ".img.gz"}) {
+        const std::string cand = base + ext;
+        if (FILE* t = fopen(cand.c_str(), "rb")) { fclose(t); return cand; }
+    }
+    return std::string();
+}
+
+float* readNiiFile(const char* fname_in, int& nx, int& ny, int& nz) {
     nx = ny = nz = 0;
+    // a pair may be named by its image file: the header is then <base>.hdr[.gz] (nifti_findhdrname)
+    std::string fname_s = fname_in ? fname_in : "";
+    {
+        std::string base = fname_s;
+        if (base.size() > 3 && base.compare(base.size() - 3, 3, ".gz") == 0) base.resize(base.size() - 3);
+        if (base.size() > 4 && base.compare(base.size() - 4, 4, ".img") == 0) {
+            base.resize(base.size() - 4);
+            for (const char* ext : {".hdr", ".hdr.gz"}) {
+                const std::string cand = base + ext;
+                if (FILE* t = fopen(cand.c_str(), "rb")) { fclose(t); fname_s = cand; break; }
+            }
+        }
+    }
+    const char* fname = fname_s.c_str();
     // gzopen reads plain files transparently, so .nii and .nii.gz share one path
     gzFile f = gzopen(fname, "rb");
     if (!f) { nii_fail(fname, "cannot open"); return nullptr; }
@@ -454,8 +502,11 @@ float* readNiiFile(const char* fname, int& nx, int& ny, int& nz) {
     int64_t dim[8] = {0};
     int datatype = 0;
     int64_t vox_offset = 0;
+    bool pair = false;  // NIfTI-1 two-file form: magic "ni1", voxels in <base>.img at vox_offset (usually 0)
     if (sz == 348) {  // NIfTI-1: dim[8] int16 @40, datatype int16 @70, vox_offset float @108, magic @344
-        if (!(hdr[344] == 'n' && hdr[345] == '+' && hdr[346] == '1')) { gzclose(f); nii_fail(fname, "not a single-file NIfTI-1 (magic n+1)"); return nullptr; }
+        const bool single = hdr[344] == 'n' && hdr[345] == '+' && hdr[346] == '1';
+        pair = hdr[344] == 'n' && hdr[345] == 'i' && hdr[346] == '1';
+        if (!single && !pair) { gzclose(f); nii_fail(fname, "not a NIfTI-1 file (magic n+1 / ni1)"); return nullptr; }
         for (int i = 0; i < 8; ++i) dim[i] = nii_get<int16_t>(hdr + 40 + 2 * i, swap);
         datatype = nii_get<int16_t>(hdr + 70, swap);
         vox_offset = (int64_t)nii_get<float>(hdr + 108, swap);
@@ -481,9 +532,19 @@ float* readNiiFile(const char* fname, int& nx, int& ny, int& nz) {
         case 1024: case 1280: case 64: bpv = 8; break;  // int64, uint64, float64
         default: gzclose(f); nii_fail(fname, "unsupported datatype"); return nullptr;
     }
-    const int64_t have = sz;
-    if (vox_offset < have) vox_offset = have == 348 ? 352 : 544;
-    {   // skip the header extension up to vox_offset
+    int64_t have = sz;  // bytes of the voxel file consumed so far
+    if (pair) {
+        gzclose(f);
+        const std::string img = nii_pair_image(fname_s);
+        f = img.empty() ? nullptr : gzopen(img.c_str(), "rb");
+        if (!f) { nii_fail(fname, "the .img file of the pair cannot be opened"); return nullptr; }
+        gzbuffer(f, 1 << 20);
+        have = 0;
+        if (vox_offset < 0) vox_offset = 0;
+    } else if (vox_offset < have) {
+        vox_offset = have;  // the reference clamps a too-small offset to sizeof(header) (nifti_convert_n1hdr2nim / n2hdr2nim)
+    }
+    {   // skip the header extension (single file) / leading bytes (pair) up to vox_offset
         std::vector<unsigned char> skip((size_t)(vox_offset - have));
         if (!skip.empty() && gzread(f, skip.data(), (unsigned)skip.size()) != (int)skip.size()) { gzclose(f); nii_fail(fname, "short file (extension)"); return nullptr; }
     }
@@ -511,6 +572,11 @@ float* readNiiFile(const char* fname, int& nx, int& ny, int& nz) {
         case 1280: nii_convert<uint64_t>(raw.data(), n, swap, out); break;
         case 64: nii_convert<double>(raw.data(), n, swap, out); break;
     }
+    // copy_nifti_as_float32 ends with "Replace nans with zeros" (laynii_lib.cpp:303-308); readNiiFile only converts
+    // inputs that are not float32 (Src/Util/readNii.cpp:16-20), so a float32 file keeps its NaNs
+    if (datatype != 16)
+        for (size_t i = 0; i < n; ++i)
+            if (out[i] != out[i]) out[i] = 0.0f;
     nx = (int)dx; ny = (int)dy; nz = (int)dz;
     return out;
 }

@@ -128,7 +128,7 @@ private:
         const char* e = getenv("S3D_ALLOC");
         enabled_ = !(e && strcmp(e, "pool") == 0);
         const char* c = getenv("S3D_ALLOC_CAP_GB");
-        cap_ = (size_t)(c ? atof(c) : 64.0) * (size_t)1 << 30;
+        cap_ = (size_t)((c ? atof(c) : 64.0) * (double)((size_t)1 << 30));  // fractional GB allowed (0.5 is 512 MiB, not 0)
         memset(cached_, 0, sizeof cached_);
         memset(total_, 0, sizeof total_);
     }

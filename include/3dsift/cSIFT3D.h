@@ -59,6 +59,33 @@ static_assert(sizeof(Keypoint) == 176, "Keypoint layout must match the reference
 SIFT_LIBRARY_API bool cmp_kp(const Keypoint& a, const Keypoint& b);
 SIFT_LIBRARY_API bool cmp_kp_orig(const Keypoint& a, const Keypoint& b);
 
+// Plain types of the reference's header (Include/cSIFT3D.h:77-116), kept so that client sources naming them still
+// compile.  The icosahedron (Tri / Mesh, 20 faces) lives in device constant data here, Image is the reference's own
+// legacy container (dead code there too), EigenVal pairs an eigenvalue with its vector.
+typedef struct _cTri {
+    Cvec v[3];   // vertices
+    int idx[3];  // index of each vertex in the solid
+} Tri;
+
+typedef struct _Mesh {
+    Tri* tri;  // triangles
+    int num;   // number of triangles
+} Mesh;
+
+typedef struct _cImage {
+    float* data;
+    int nx, ny, nz;
+    size_t xs, ys, zs;  // strides: xs = 1, ys = nx, zs = nx * ny
+    float ux, uy, uz;
+    size_t size;        // total size in voxels
+    float s;            // scale-space location
+} Image;
+
+typedef struct _cEigenVal {
+    float val;
+    float vec[3];
+} EigenVal;
+
 class SIFT_LIBRARY_API CSIFT3D {
 public:
     SIFT_TimerPara m_timer;
@@ -114,7 +141,10 @@ public:
                                   float max_eigo_thres = EIG_THRES, float corner_thresh = CORNER_THRESH);
 };
 
-// Free kernels of the reference that make sense on host buffers (cSIFT3D.h:208-214)
+// Free kernels of the reference that make sense on host buffers (cSIFT3D.h:208-214).  The reference declares the rest
+// of its kernels (Sub, IsExtrema_neighbor, Assign_Orientation_Imp, Extract_Descriptor_Imp, ... :216-239) WITHOUT
+// SIFT_LIBRARY_API: they are not exported from its DLL, so no client can link them and they are not part of the
+// drop-in surface; their work is the device kernels' (parity hooks: s3d_blur_axis, s3d_get_level, s3d_get_extrema).
 SIFT_LIBRARY_API void DownSample_3D(TexImage* src, TexImage* dst);
 SIFT_LIBRARY_API void GaussianSmooth_3D(TexImage* src, TexImage* dst, float sigma);
 

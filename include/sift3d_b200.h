@@ -94,7 +94,11 @@ S3D_API int s3d_create(const float* vol, int nx, int ny, int nz, const s3d_param
  * s3d_run / s3d_wait on this handle has returned.  Lets the upload of volume k+1 overlap the
  * extraction of volume k (each handle has its own stream unless params.stream is set). */
 S3D_API int s3d_create_async(const float* vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out);
-/* Same, for a volume already resident in device memory (HBM-resident timing, chained pipelines). */
+/* Same, for a volume already resident in device memory (HBM-resident timing, chained pipelines).  d_vol is contiguous
+ * float32 on params.device.  ORDERING: the volume is read on the handle's stream — params.stream when given, else a
+ * private non-blocking stream that is NOT ordered against the stream that produced d_vol: either pass the producing
+ * stream in params.stream or make sure the producer has finished.  The call returns after the normalised copy has been
+ * made; d_vol is not needed afterwards.  (All entry points leave `params.device` as the thread's current device.) */
 S3D_API int s3d_create_device(const float* d_vol, int nx, int ny, int nz, const s3d_params* p, s3d_handle* out);
 /* CSIFT3D::KpSiftAlgorithm()  Src/cSIFT3D.cc:165-235: Initialize, Gaussian scale space, DoG,
  * detection, orientation, description.  Blocks until the results are on the host side of the

@@ -88,3 +88,45 @@ def test_nifti_volume_through_the_extractor(s3d, synth, tmp_path):
     b = s3d.CSIFT3DFactory.CreateCSIFT3D(vol)
     b.KpSiftAlgorithm()
     assert len(a.GetKeypoints()) == len(b.GetKeypoints()) > 0 and np.array_equal(a.descriptors, b.descriptors)
+
+
+# ---- fixtures produced by the reference's own code (layNii writer + readNiiFile): tests/golden/make_nii_golden.py --------
+
+import os
+
+NII_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nii")
+
+
+def _golden_cases():
+    exp = np.load(os.path.join(NII_DIR, "expected.npz"))
+    return sorted(exp.files)
+
+
+@pytest.mark.parametrize("name", _golden_cases())
+def test_files_written_by_laynii_read_like_the_reference(s3d, name):
+    """Every scalar type, gzip, NIfTI-2, the .hdr/.img pair and float64 NaNs (zeroed by the reference's conversion,
+    laynii_lib.cpp:303-308): the product's parser must return the reference's readNiiFile output bit for bit."""
+    want = np.load(os.path.join(NII_DIR, "expected.npz"))[name]
+    got = s3d.readNiiFile(os.path.join(NII_DIR, name))
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert np.array_equal(got, want), name
+    if "nan" in name:
+        assert not np.isnan(got).any() and (got == 0).sum() >= got.size // 17
+
+
+def test_pair_named_by_its_image_file(s3d):
+    want = np.load(os.path.join(NII_DIR, "expected.npz"))["pair_i16.hdr"]
+    assert np.array_equal(s3d.readNiiFile(os.path.join(NII_DIR, "pair_i16.img")), want)
+
+
+def test_float32_keeps_nans_and_small_vox_offset_is_clamped_to_the_header(s3d, tmp_path):
+    """readNiiFile converts (and de-NaNs) only inputs that are not float32 (Src/Util/readNii.cpp:16-20); a vox_offset
+    below the header size is clamped to sizeof(header) = 348, not to 352 (nifti_convert_n1hdr2nim)."""
+    vol = np.arange(2 * 3 * 4, dtype=np.float32).reshape(2, 3, 4)
+    vol[1, 2, 3] = np.nan
+    raw = bytearray(nifti1_bytes(vol))
+    struct.pack_into("<f", raw, 108, 0.0)                       # vox_offset 0 in a single-file NIfTI-1
+    p = tmp_path / "v.nii"
+    p.write_bytes(bytes(raw[:348]) + bytes(raw[352:]))          # voxels directly after the 348-byte header
+    got = s3d.readNiiFile(str(p))
+    assert np.array_equal(got, vol, equal_nan=True) and np.isnan(got[1, 2, 3])
