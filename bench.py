@@ -127,6 +127,37 @@ def cpu_info():
     return model, os.cpu_count()
 
 
+def bind_to_gpu_numa_node(local):
+    """Best effort, multi-rank runs only: run this rank on the CPUs of the NUMA node its GPU hangs off BEFORE the pinned
+    host buffers are allocated (first touch puts them on that node).  r1/r2 measurements at 8 ranks: the last e2e step's
+    H2D took 35 ms on ranks 0-3 and 15-19 ms on ranks 4-7 (profiles/r02_bench_n8_b.json per_rank) — ingest that crosses
+    the socket interconnect.  Returns what was done, for the JSON line."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        if all(hasattr(pr, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            q = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                               capture_output=True, text=True, timeout=20).stdout.strip().lower()
+            bus = q[-12:] if len(q) >= 12 else q      # nvidia-smi prints an 8-digit domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return {"gpu_bus": bus, "node": None, "bound": False, "why": "the platform reports no NUMA node for the GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return {"gpu_bus": bus, "node": node, "bound": False, "why": "none of the node's CPUs is in this process's cpuset"}
+        os.sched_setaffinity(0, use)
+        return {"gpu_bus": bus, "node": node, "bound": True, "cpus": len(use)}
+    except Exception as ex:   # never fail the bench over placement
+        return {"bound": False, "why": f"{type(ex).__name__}: {ex}"}
+
+
 def reference_checker():
     """The reference's own OpenMP path (oracle/_ref when compiled, else the port) with ALL host threads: torchrun
     exports OMP_NUM_THREADS=1 to its children, which would pin the OpenMP runtime to one core — drop it before the
@@ -225,6 +256,7 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("S3D_NUMA_BIND", "1") != "0" else {"bound": False, "why": "single rank"}
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on STDOUT: rank 0 must print one JSON line only
     if world > 1:
@@ -671,13 +703,14 @@ def main():
     per_rank = None
     if world > 1:
         # per-rank view (value ms, e2e ms, summed kernel ms of the last resident step, H2D ms of the last e2e step) before the max
-        mine = torch.tensor([ms_value, ms_e2e, stage.get("d_TotalTime", 0.0) * 1e3, e2e_split.get("h2d_ms", 0.0), lat_ms],
-                            dtype=torch.float64, device="cuda")
+        mine = torch.tensor([ms_value, ms_e2e, stage.get("d_TotalTime", 0.0) * 1e3, e2e_split.get("h2d_ms", 0.0), lat_ms,
+                             float(numa.get("node")) if numa.get("bound") else -1.0], dtype=torch.float64, device="cuda")
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         per_rank = {"ms_value": [round(float(x[0]), 3) for x in allr], "ms_e2e": [round(float(x[1]), 3) for x in allr],
                     "device_ms_last_step": [round(float(x[2]), 3) for x in allr], "h2d_ms_last_e2e_step": [round(float(x[3]), 3) for x in allr],
-                    "latency_ms": [round(float(x[4]), 3) for x in allr]}
+                    "latency_ms": [round(float(x[4]), 3) for x in allr],
+                    "numa_node_bound_to": [int(x[5]) for x in allr], "numa_rank0": numa}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_value, ms_e2e, lat_ms = float(t[0]), float(t[1]), float(t[2])
     value = world * nvox / (ms_value * 1e-3) / 1e6
