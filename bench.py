@@ -487,126 +487,131 @@ def main():
     extra = {}
     comm = None
     if not a.no_extra:
-        if world > 1:
-            comm = D.nccl_comm()
-        else:   # a single-rank communicator of the library's own (no torch.distributed in a one-process run)
-            uid = (C.c_ubyte * 128)()
-            api.check(L.s3d_comm_unique_id(uid))
-            comm = D.NcclComm.__new__(D.NcclComm)
-            comm.world, comm.rank, comm._c = 1, 0, C.c_void_p()
-            api.check(L.s3d_comm_create(uid, 1, 0, local, C.byref(comm._c)))
-        o0, o1 = C.c_int(), C.c_int()
-        api.check(L.s3d_slab_bounds(n, world, rank, C.byref(o0), C.byref(o1)))
-        own0, own1 = o0.value, o1.value
-        d_own, h_own = d_vol[own0:own1], h_vol[own0:own1]
-        p_e2e = D._params(dict(device=local))
+        # A failure in a strong-scaling leg must not take the headline line with it: the leg reports the error instead.
+        try:
+            if world > 1:
+                comm = D.nccl_comm()
+            else:   # a single-rank communicator of the library's own (no torch.distributed in a one-process run)
+                uid = (C.c_ubyte * 128)()
+                api.check(L.s3d_comm_unique_id(uid))
+                comm = D.NcclComm.__new__(D.NcclComm)
+                comm.world, comm.rank, comm._c = 1, 0, C.c_void_p()
+                api.check(L.s3d_comm_create(uid, 1, 0, local, C.byref(comm._c)))
+            o0, o1 = C.c_int(), C.c_int()
+            api.check(L.s3d_slab_bounds(n, world, rank, C.byref(o0), C.byref(o1)))
+            own0, own1 = o0.value, o1.value
+            d_own, h_own = d_vol[own0:own1], h_vol[own0:own1]
+            p_e2e = D._params(dict(device=local))
 
-        def slab_create(resident):
-            h = C.c_void_p()
-            if resident:
-                api.check(L.s3d_slab_create(comm._c, d_own.data_ptr(), 1, n, n, n, C.byref(p_e2e), C.byref(h)))
-            else:
-                api.check(L.s3d_slab_create(comm._c, h_own.data_ptr(), 0, n, n, n, C.byref(p_e2e), C.byref(h)))
-            return h
-
-        slab_last = {}
-
-        def slab_steps(k_steps, resident, keep_last=False):
-            """k_steps volumes, each extracted by all ranks together, two volumes in flight: s3d_slab_create (allocation +
-            copy of the rank's own planes: device-to-device for the resident leg, from pinned host memory for the e2e leg)
-            and s3d_slab_execute_async (kernels + NCCL collectives, enqueue only) of volume i+1 are issued while volume i
-            runs; s3d_wait, s3d_slab_gather (merge on rank 0 over NCCL) and — e2e leg — the copy of the merged records
-            + descriptors into pinned host memory on rank 0 complete volume i."""
-            inflight, kk = [], 0
-
-            def finish(h, slot):
-                api.check(L.s3d_wait(h))
-                api.check(L.s3d_slab_gather(comm._c, h, 0, 0))
-                nn = C.c_int()
-                api.check(L.s3d_num_keypoints(h, C.byref(nn)))
-                if rank == 0 and not resident:
-                    api.check(L.s3d_get_keypoints_async(h, h_kp[slot].data_ptr(), h_desc[slot].data_ptr()))
-                    api.check(L.s3d_sync(h))
-                if keep_last and not inflight:
-                    slab_last["h"] = h
+            def slab_create(resident):
+                h = C.c_void_p()
+                if resident:
+                    api.check(L.s3d_slab_create(comm._c, d_own.data_ptr(), 1, n, n, n, C.byref(p_e2e), C.byref(h)))
                 else:
-                    L.s3d_destroy(h)
-                return nn.value
+                    api.check(L.s3d_slab_create(comm._c, h_own.data_ptr(), 0, n, n, n, C.byref(p_e2e), C.byref(h)))
+                return h
 
-            cur = slab_create(resident) if k_steps > 0 else None
-            for i in range(k_steps):
-                nxt = slab_create(resident) if i + 1 < k_steps else None
-                api.check(L.s3d_slab_execute_async(comm._c, cur))
-                inflight.append((cur, i & 1))
-                if len(inflight) >= 2:
+            slab_last = {}
+
+            def slab_steps(k_steps, resident, keep_last=False):
+                """k_steps volumes, each extracted by all ranks together, two volumes in flight: s3d_slab_create (allocation +
+                copy of the rank's own planes: device-to-device for the resident leg, from pinned host memory for the e2e leg)
+                and s3d_slab_execute_async (kernels + NCCL collectives, enqueue only) of volume i+1 are issued while volume i
+                runs; s3d_wait, s3d_slab_gather (merge on rank 0 over NCCL) and — e2e leg — the copy of the merged records
+                + descriptors into pinned host memory on rank 0 complete volume i."""
+                inflight, kk = [], 0
+
+                def finish(h, slot):
+                    api.check(L.s3d_wait(h))
+                    api.check(L.s3d_slab_gather(comm._c, h, 0, 0))
+                    nn = C.c_int()
+                    api.check(L.s3d_num_keypoints(h, C.byref(nn)))
+                    if rank == 0 and not resident:
+                        api.check(L.s3d_get_keypoints_async(h, h_kp[slot].data_ptr(), h_desc[slot].data_ptr()))
+                        api.check(L.s3d_sync(h))
+                    if keep_last and not inflight:
+                        slab_last["h"] = h
+                    else:
+                        L.s3d_destroy(h)
+                    return nn.value
+
+                cur = slab_create(resident) if k_steps > 0 else None
+                for i in range(k_steps):
+                    nxt = slab_create(resident) if i + 1 < k_steps else None
+                    api.check(L.s3d_slab_execute_async(comm._c, cur))
+                    inflight.append((cur, i & 1))
+                    if len(inflight) >= 2:
+                        kk = finish(*inflight.pop(0))
+                    cur = nxt
+                while inflight:
                     kk = finish(*inflight.pop(0))
-                cur = nxt
-            while inflight:
-                kk = finish(*inflight.pop(0))
-            return kk
+                return kk
 
-        slab_steps(max(a.warmup, 3), True)
-        sent0 = comm.traffic()[0]
-        ksl = max(5, min(a.steps, 20))
-        barrier()
-        w0 = time.time()
-        ev0.record()
-        slab_steps(ksl, True, keep_last=True)
-        torch.cuda.synchronize()
-        ev1.record()
-        barrier()
-        windows.append((w0, time.time()))
-        ms_slab = max_over_ranks(ev0.elapsed_time(ev1) / ksl)
-        L.s3d_destroy(slab_last.pop("h"))
-        sent_per_step = (comm.traffic()[0] - sent0) / ksl
-        # latency of ONE volume, nothing in flight besides it (resident planes): create -> execute -> gather; the
-        # per-phase device times are taken from these runs (with two volumes in flight a phase's event span also
-        # covers the other volume's kernels)
-        lat_slab = []
-        for _ in range(5):
+            slab_steps(max(a.warmup, 3), True)
+            sent0 = comm.traffic()[0]
+            ksl = max(5, min(a.steps, 20))
             barrier()
-            t0 = time.perf_counter()
-            slab_steps(1, True, keep_last=True)
+            w0 = time.time()
+            ev0.record()
+            slab_steps(ksl, True, keep_last=True)
             torch.cuda.synchronize()
-            lat_slab.append((time.perf_counter() - t0) * 1e3)
-            sh = D.SlabShard(slab_last.pop("h"), (n, n, n), rank)
-            phases = sh.phases()
-            nk_slab = sh.num_keypoints()
-            sh.close()
-        lat_slab_ms = max_over_ranks(float(np.median(lat_slab)))
-        slab_steps(max(a.warmup, 3), False)
-        barrier()
-        w0 = time.time()
-        ev0.record()
-        nk_e2e = slab_steps(ksl, False)
-        torch.cuda.synchronize()
-        ev1.record()
-        barrier()
-        ms_slab_e2e = max_over_ranks(ev0.elapsed_time(ev1) / ksl)
-        windows.append((w0, time.time()))
-        ph_all = None
-        if world > 1:
-            mine = torch.tensor([phases[k_] for k_ in ("normalize", "pyramid", "halo", "sparse", "gather")] + [sent_per_step],
-                                dtype=torch.float64, device="cuda")
-            allp = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(allp, mine)
-            ph_all = [[round(float(v), 3) for v in x] for x in allp]
-        extra["slab"] = {
-            "metric": "Mvoxels/s, ONE 512^3 volume extracted by all GPUs together (z-slabs)", "scaling": "strong", "shards": world,
-            "value": nvox / (ms_slab * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume": ms_slab, "steps": ksl, "volumes_in_flight": 2,
-            "latency_ms_single_volume": lat_slab_ms,
-            "e2e": {"value": nvox / (ms_slab_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume": ms_slab_e2e,
-                    "h2d_bytes_per_step": int(vol.nbytes), "d2h_bytes_per_step": int(nk_e2e * (176 + 768 * 4)),
-                    "note": "pinned host volume in (every rank uploads its own planes, one volume ahead), merged records + "
-                            "descriptors out in pinned host memory on rank 0; CUDA events around the synchronised loop, max over ranks"},
-            "keypoints": nk_slab, "equal_to_single_gpu_keypoints": bool(nk_slab == nkp) if rank == 0 else None,
-            "phases_ms_rank0": {k_: round(v, 3) for k_, v in phases.items()},
-            "phases_per_rank": ph_all, "phases_per_rank_columns": ["normalize ms", "pyramid ms", "halo ms", "sparse ms", "gather ms", "nccl bytes sent per volume"],
-            "nccl_bytes_sent_per_volume_rank0": sent_per_step,
-            "note": "value = THROUGHPUT with every rank's planes resident in HBM: s3d_slab_create + s3d_slab_execute_async + s3d_wait + "
-                    "s3d_slab_gather, two volumes in flight on private streams, CUDA events around the synchronised loop, max over "
-                    "ranks; latency_ms_single_volume = one volume at a time; parity with the unsharded run: tests/test_gpu_slab.py "
-                    "and scripts/multi_gpu_check.py (bit-equal)"}
+            ev1.record()
+            barrier()
+            windows.append((w0, time.time()))
+            ms_slab = max_over_ranks(ev0.elapsed_time(ev1) / ksl)
+            L.s3d_destroy(slab_last.pop("h"))
+            sent_per_step = (comm.traffic()[0] - sent0) / ksl
+            # latency of ONE volume, nothing in flight besides it (resident planes): create -> execute -> gather; the
+            # per-phase device times are taken from these runs (with two volumes in flight a phase's event span also
+            # covers the other volume's kernels)
+            lat_slab = []
+            for _ in range(5):
+                barrier()
+                t0 = time.perf_counter()
+                slab_steps(1, True, keep_last=True)
+                torch.cuda.synchronize()
+                lat_slab.append((time.perf_counter() - t0) * 1e3)
+                sh = D.SlabShard(slab_last.pop("h"), (n, n, n), rank)
+                phases = sh.phases()
+                nk_slab = sh.num_keypoints()
+                sh.close()
+            lat_slab_ms = max_over_ranks(float(np.median(lat_slab)))
+            slab_steps(max(a.warmup, 3), False)
+            barrier()
+            w0 = time.time()
+            ev0.record()
+            nk_e2e = slab_steps(ksl, False)
+            torch.cuda.synchronize()
+            ev1.record()
+            barrier()
+            ms_slab_e2e = max_over_ranks(ev0.elapsed_time(ev1) / ksl)
+            windows.append((w0, time.time()))
+            ph_all = None
+            if world > 1:
+                mine = torch.tensor([phases[k_] for k_ in ("normalize", "pyramid", "halo", "sparse", "gather")] + [sent_per_step],
+                                    dtype=torch.float64, device="cuda")
+                allp = [torch.zeros_like(mine) for _ in range(world)]
+                dist.all_gather(allp, mine)
+                ph_all = [[round(float(v), 3) for v in x] for x in allp]
+            extra["slab"] = {
+                "metric": "Mvoxels/s, ONE 512^3 volume extracted by all GPUs together (z-slabs)", "scaling": "strong", "shards": world,
+                "value": nvox / (ms_slab * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume": ms_slab, "steps": ksl, "volumes_in_flight": 2,
+                "latency_ms_single_volume": lat_slab_ms,
+                "e2e": {"value": nvox / (ms_slab_e2e * 1e-3) / 1e6, "unit": UNIT, "ms_per_volume": ms_slab_e2e,
+                        "h2d_bytes_per_step": int(vol.nbytes), "d2h_bytes_per_step": int(nk_e2e * (176 + 768 * 4)),
+                        "note": "pinned host volume in (every rank uploads its own planes, one volume ahead), merged records + "
+                                "descriptors out in pinned host memory on rank 0; CUDA events around the synchronised loop, max over ranks"},
+                "keypoints": nk_slab, "equal_to_single_gpu_keypoints": bool(nk_slab == nkp) if rank == 0 else None,
+                "phases_ms_rank0": {k_: round(v, 3) for k_, v in phases.items()},
+                "phases_per_rank": ph_all, "phases_per_rank_columns": ["normalize ms", "pyramid ms", "halo ms", "sparse ms", "gather ms", "nccl bytes sent per volume"],
+                "nccl_bytes_sent_per_volume_rank0": sent_per_step,
+                "note": "value = THROUGHPUT with every rank's planes resident in HBM: s3d_slab_create + s3d_slab_execute_async + s3d_wait + "
+                        "s3d_slab_gather, two volumes in flight on private streams, CUDA events around the synchronised loop, max over "
+                        "ranks; latency_ms_single_volume = one volume at a time; parity with the unsharded run: tests/test_gpu_slab.py "
+                        "and scripts/multi_gpu_check.py (bit-equal)"}
+        except Exception as ex:   # noqa: BLE001
+            extra["slab"] = {"error": f"{type(ex).__name__}: {ex}"}
+            print(f"[bench] slab leg failed on rank {rank}: {ex}", file=sys.stderr, flush=True)
 
     # ---- matching legs (secondary metric): enhancedMatch on HBM-resident descriptor sets ----------------
     match = None
@@ -677,23 +682,27 @@ def main():
 
         # ---- strong scaling 2: ONE enhancedMatch, database sharded over the ranks ----------
         if comm is not None:
-            sent0 = comm.traffic()[0]
+            try:
+                sent0 = comm.traffic()[0]
 
-            def match_sharded_step():
-                s3d.check(L.s3d_match_sharded(comm._c, 3, d_ref.data_ptr(), nr, d_tar.data_ptr(), nt, 0.85,
-                                              *[b.data_ptr() for b in bufs], C.c_void_p(stream or 1)))
-            ms_ms, mst, tc2, fb2 = timed_match(match_sharded_step)
-            equal = all(torch.equal(x, y) for x, y in zip(bufs[:10], single_outputs[:10])) and int(bufs[10].item()) == npairs
-            eq_all = max_over_ranks(0.0 if equal else 1.0) == 0.0
-            extra["match_sharded"] = {
-                "metric": "pairs/s, ONE enhancedMatch over all GPUs (database sharded, exact re-rank sharded by query)",
-                "scaling": "strong", "shards": world, "n_ref": nr, "n_tar": nt, "ms": ms_ms, "steps": mst,
-                "pairs_per_s": nr * nt / (ms_ms * 1e-3), "algorithmic_tflops_total": flops / (ms_ms * 1e-3) / 1e12,
-                "equal_to_single_gpu_outputs": bool(eq_all), "rows_tensor_core_rank0": tc2, "rows_exact_fallback_rank0": fb2,
-                "nccl_bytes_sent_per_match_rank0": (comm.traffic()[0] - sent0) / (mst + (1 if big else min(a.warmup, 2))),
-                "clocks": sampler.summary(windows[-1:]),
-                "note": "sets replicated in HBM on every rank; every rank ends with the complete outputs; CUDA events on the "
-                        "calling stream, max over ranks"}
+                def match_sharded_step():
+                    s3d.check(L.s3d_match_sharded(comm._c, 3, d_ref.data_ptr(), nr, d_tar.data_ptr(), nt, 0.85,
+                                                  *[b.data_ptr() for b in bufs], C.c_void_p(stream or 1)))
+                ms_ms, mst, tc2, fb2 = timed_match(match_sharded_step)
+                equal = all(torch.equal(x, y) for x, y in zip(bufs[:10], single_outputs[:10])) and int(bufs[10].item()) == npairs
+                eq_all = max_over_ranks(0.0 if equal else 1.0) == 0.0
+                extra["match_sharded"] = {
+                    "metric": "pairs/s, ONE enhancedMatch over all GPUs (database sharded, exact re-rank sharded by query)",
+                    "scaling": "strong", "shards": world, "n_ref": nr, "n_tar": nt, "ms": ms_ms, "steps": mst,
+                    "pairs_per_s": nr * nt / (ms_ms * 1e-3), "algorithmic_tflops_total": flops / (ms_ms * 1e-3) / 1e12,
+                    "equal_to_single_gpu_outputs": bool(eq_all), "rows_tensor_core_rank0": tc2, "rows_exact_fallback_rank0": fb2,
+                    "nccl_bytes_sent_per_match_rank0": (comm.traffic()[0] - sent0) / (mst + (1 if big else min(a.warmup, 2))),
+                    "clocks": sampler.summary(windows[-1:]),
+                    "note": "sets replicated in HBM on every rank; every rank ends with the complete outputs; CUDA events on the "
+                            "calling stream, max over ranks"}
+            except Exception as ex:   # noqa: BLE001
+                extra["match_sharded"] = {"error": f"{type(ex).__name__}: {ex}"}
+                print(f"[bench] match_sharded leg failed on rank {rank}: {ex}", file=sys.stderr, flush=True)
         del d_ref, d_tar, bufs, single_outputs
     time.sleep(0.3)
     sampler.stop()
