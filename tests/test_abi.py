@@ -85,3 +85,25 @@ def test_matrix_io_roundtrip(tmp_path, s3d):
     assert w.shape == (2, 3, 4) and np.array_equal(v, w)
     raw = np.fromfile(p, dtype=np.int32, count=3)
     assert list(raw) == [4, 3, 2]  # m n p = nx ny nz (Include/Util/matrixIO3D.h:22-64)
+
+
+def test_multi_gpu_entries_fail_loudly_without_a_device(s3d):
+    """The library-side multi-GPU entries (z-slabs, database-sharded matcher) have no CPU path either: without a usable
+    sm_100 device they return S3D_ERR_CUDA and say so; bad arguments are refused before anything is touched."""
+    if s3d.device_count() > 0:
+        pytest.skip("a GPU is present")
+    import ctypes as C
+    L = s3d.lib()
+    v = np.zeros((16, 16, 16), np.float32)
+    hs = (C.c_void_p * 2)()
+    assert L.s3d_extract_multi(None, 16, 16, 16, None, None, 2, 1, hs) == 1                       # S3D_ERR_ARG
+    rc = L.s3d_extract_multi(v.ctypes.data_as(C.c_void_p), 16, 16, 16, None, None, 2, 1, hs)
+    assert rc == 2 and b"no CPU fallback" in L.s3d_last_error()                                     # S3D_ERR_CUDA
+    a = np.zeros((4, 768), np.float32)
+    p = a.ctypes.data_as(C.c_void_p)
+    rc = L.s3d_match_multi(3, p, 4, p, 4, 0.85, None, 2, *([None] * 12))
+    assert rc == 2 and b"no CPU fallback" in L.s3d_last_error()
+    assert L.s3d_match_multi(7, p, 4, p, 4, 0.85, None, 2, *([None] * 12)) == 1
+    o0, o1 = C.c_int(), C.c_int()
+    assert L.s3d_slab_bounds(512, 8, 3, C.byref(o0), C.byref(o1)) == 0 and (o0.value, o1.value) == (192, 256)
+    assert L.s3d_slab_bounds(512, 8, 8, C.byref(o0), C.byref(o1)) == 1
