@@ -227,7 +227,8 @@ def run_reference(a):
         time_reference(64, 1, 0)
     val, sec, kind, threads, nk, done, stages = time_reference(edge, steps, warmup)
     model, ncpu = cpu_info()
-    sample = (f"V-blobs {edge}^3 (the workload itself), CreateCSIFT3D+KpSiftAlgorithm, {done} timed volume(s) of {sec:.1f} s, "
+    sample = (f"V-blobs {edge}^3" + (" (the workload itself)" if edge == a.size else " (a reduced sample: --cpu-sample)") +
+              f", CreateCSIFT3D+KpSiftAlgorithm, {done} timed volume(s) of {sec:.1f} s, "
               f"{threads} OpenMP threads on {ncpu} cores")
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": done, "warmup": warmup,
            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
