@@ -827,6 +827,12 @@ def main():
             edge = a.cpu_sample or a.size
             if edge > 64:
                 time_reference(64, 1, 0)
+            if not a.cpu_sample and edge > 256:
+                # the default line must finish within minutes on any host: a 128^3 probe predicts the full-size run (the
+                # reference gets ~1.6x faster per voxel from 128^3 to 512^3); above ~2.5 min the baseline falls back to 256^3
+                _, probe_s, *_ = time_reference(128, 1, 0)
+                if probe_s * (edge / 128.0) ** 3 / 1.6 > 150.0:
+                    edge = 256
             val, sec, kind, threads, nk, done, stages = time_reference(edge, 1, 0)
             model, _ = cpu_info()
             out["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "cpu": model, "sample_edge": edge,
