@@ -260,7 +260,10 @@ Comm* local_comm_create(LocalGroup* g, int rank, int device) {
 // =================================================================================================
 // Plane bookkeeping (host logic; identical on every rank)
 // =================================================================================================
-constexpr int kMinOwnedPlanes = 10;  // a sharded octave gives every shard > hw_max + 1 planes: halos come from direct neighbours
+// A sharded octave gives every shard at least this many planes (> hw_max + 1): a per-level halo then comes from the direct
+// neighbours only.  Grouped exchanges and window halos can be deeper than a thin slab; halo_plan handles any depth by
+// intersecting the needed planes with every peer's owned range.
+constexpr int kMinOwnedPlanes = 10;
 
 static void slab_bounds_of(int nz, int world, int rank, int* own0, int* own1) {
     auto b = [&](int r) { return r <= 0 ? 0 : (r >= world ? nz : std::min(nz, (int)(((long long)nz * r / world) & ~1LL))); };
